@@ -1,0 +1,219 @@
+/*
+ * openmines_b200 -- C ABI of the batched, B200-native discrete-event engine for OpenMines.
+ *
+ * This is the drop-in boundary for ONE hot path of 370025263/openmines: stepping many
+ * independent mine instances (seed x dispatcher x config).  Each entry point below names the
+ * reference interface (file:line, relative to the reference tree) that it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative OM_E_* code on failure; the message is
+ *     available from om_last_error(handle) (or om_last_error(NULL) for om_create failures);
+ *   - no exception crosses the boundary; the caller (PyTorch on the host side) owns every device
+ *     buffer, the library owns only the opaque handle and its packed copy of the mine config;
+ *   - all pointers marked "device" are device pointers on the handle's GPU; all work is enqueued
+ *     on the cudaStream_t passed in (as void*, 0 = legacy default stream); calls are not
+ *     thread-safe per handle;
+ *   - there is NO CPU fallback: without a CUDA device om_create fails with OM_E_CUDA.
+ */
+#ifndef OPENMINES_B200_H
+#define OPENMINES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OM_ABI_VERSION 1
+
+/* error codes */
+#define OM_OK 0
+#define OM_E_INVALID (-1)
+#define OM_E_CUDA (-2)
+#define OM_E_NOMEM (-3)
+#define OM_E_UNSUPPORTED (-4)
+
+/* dispatcher ids: the six built-ins of openmines/src/dispatch_algorithms/ as device functions
+ * behind BaseDispatcher.give_init_order / give_haul_order / give_back_order (dispatcher.py:91-98) */
+#define OM_DISP_NAIVE 0       /* naive_dispatcher.py:12-22 */
+#define OM_DISP_RANDOM 1      /* random_dispatcher.py:12-30 */
+#define OM_DISP_NEAREST 2     /* nearest_dispatcher.py:17-67 */
+#define OM_DISP_FIXEDGROUP 3  /* fixed_group_dispatcher.py:21-110 */
+#define OM_DISP_SPTF 4        /* sptf_dispatcher.py:21-61 */
+#define OM_DISP_SQ 5          /* sq_dispatcher.py:18-100 */
+#define OM_DISP_EXTERNAL 255  /* decisions supplied by the host through om_step (rl_dispatch.py:58-123) */
+
+/* RNG modes */
+#define OM_RNG_DET 0     /* no stochastic event can fire; RandomDispatcher uses keyed Philox */
+#define OM_RNG_PHILOX 1  /* counter-based Philox4x32-10, key=(seed), counter=(epoch, entity, site, 0) */
+#define OM_RNG_TAPE 2    /* replay recorded draws (post-transform values) in call order */
+
+/* order kinds */
+#define OM_ORDER_INIT 0
+#define OM_ORDER_HAUL 1
+#define OM_ORDER_BACK 2
+
+/* per-instance error codes (OmSummary.err) -- the reference would raise at these points */
+#define OM_IERR_NONE 0
+#define OM_IERR_SQ_KEYERROR 1    /* sq_dispatcher.py:31,60,88: order at an integer minute before its monitor block */
+#define OM_IERR_BAD_ORDER 2      /* IndexError at truck.py:305,390,442 */
+#define OM_IERR_JAM_OVERFLOW 3   /* engine limit: more simultaneously active jams than jam_capacity */
+#define OM_IERR_TAPE 4           /* tape exhausted or site-id mismatch */
+#define OM_IERR_TRACE_OVERFLOW 5 /* trace buffer too small (simulation itself is unaffected) */
+
+/* Packed mine configuration: what run_dispatch_sim (cli/run.py:48-107) builds from the mine JSON
+ * (conf/north_pit_mine.json), flattened into structure-of-arrays.  All arrays are HOST pointers and
+ * are copied by om_create.  Locations are coded 0 = charging site, 1..L = load sites,
+ * L+1..L+D = dump sites.  Units are shovels 0..S-1 (grouped by load site) then dumpers S..S+M-1
+ * (grouped by dump site).  Roads are numbered in the monitor's order (mine.py:138-154):
+ * [0,L) charging->load i; L+i*D+j load i->dump j; L+L*D+j*L+i dump j->load i. */
+typedef struct OmConfig {
+  int32_t abi_version;      /* OM_ABI_VERSION */
+  int32_t n_trucks;         /* T */
+  int32_t n_load_sites;     /* L */
+  int32_t n_dump_sites;     /* D */
+  int32_t n_shovels;        /* S */
+  int32_t n_dumpers;        /* M */
+  int32_t n_truck_types;    /* distinct (capacity) classes used by the tables below */
+  int32_t jam_capacity;     /* max simultaneously tracked jam events per instance */
+  int32_t sum_mode;         /* 1 = CPython>=3.12 Neumaier sum() (default), 0 = naive left-to-right */
+  int32_t nearest_init;     /* nearest_dispatcher.py:24-26 */
+  int32_t reserved0;
+  int32_t reserved1;
+  const double* truck_capacity;   /* [T]  truck.py:56 */
+  const double* truck_speed;      /* [T]  truck.py:57 */
+  const int32_t* truck_type;      /* [T]  index into load_time / sptf_cost */
+  const int32_t* site_unit_begin; /* [L+D+1] first unit of each site (load sites then dump sites) */
+  const double* dumper_cycle;     /* [M]  dump_site.py:15 */
+  const double* road_distance;    /* [R]  road.py:311-323 (d2l indexed [load][dump], road.py:314-316) */
+  const double* load_time;        /* [n_types*S] (cap/shovel_tons)*cycle, truck.py:223 */
+  const double* sptf_cost;        /* [n_types*L] cap/load_site_productivity, sptf_dispatcher.py:35 */
+  const double* jam_chance;       /* [T+1] 1-exp(-0.05*n), road.py:164-167 */
+  const int32_t* nearest_haul;    /* [L]  argmin l2d[i,:], nearest_dispatcher.py:42-45 */
+  const int32_t* nearest_back;    /* [D]  argmin d2l[:,j], nearest_dispatcher.py:64-66 */
+  const int32_t* fixed_group;     /* [T]  fixed_group_dispatcher.py:21-56 (0 when unassigned) */
+  /* stochastic-event parameters (reference defaults are hard-coded where cited) */
+  double road_lambda;        /* road.py:38 / config road_event_params */
+  double road_mu;            /* road.py:39 */
+  double road_sigma;         /* road.py:40 */
+  double detour_mu;          /* road.py:41 */
+  double detour_sigma;       /* road.py:42 */
+  double breakdown_mean;     /* truck.py:66  (360) */
+  double repair_mu;          /* truck.py:68  (10) */
+  double repair_sigma;       /* truck.py:69  (3) */
+  double unrepairable_mean;  /* truck.py:67  (70560) */
+  double maint_mean;         /* truck.py:358 (1440) */
+  double maint_mu;           /* truck.py:362 (45) */
+  double maint_sigma;        /* truck.py:362 (5) */
+  double jam_sd;             /* road.py:185  (0.1) */
+  double jam_scale;          /* road.py:212  (10, Weibull shape 2) */
+} OmConfig;
+
+/* One record per entry the reference appends to an EventPool during env.run (truck.py:143,188,
+ * 203,311,332,346,395,414,425,447; road.py:218,259; truck.py:364,373).  Kinds 0..11 are the
+ * "truck events" of the headline metric. */
+typedef struct OmTraceRecord {
+  double time;    /* env.now when the record was created */
+  double a, b;    /* kind-specific payload, see openmines_b200/trace.py */
+  uint16_t truck; /* 0xFFFF for road events */
+  uint8_t kind;
+  uint8_t flags;
+  uint16_t arg0, arg1;
+} OmTraceRecord;
+
+/* Per-minute KPI sample written by the monitor block (mine.py:102-119); 32 bytes. */
+typedef struct OmTickRecord {
+  double produced_tons;      /* mine.produce_tons */
+  int32_t service_count;
+  uint16_t working, waiting, load_unload, moving, repairing;        /* truck status counts */
+  uint16_t n_jams, n_road_repairs, n_truck_repairs, n_unrepairable; /* cumulative event counts */
+  uint16_t pad;
+} OmTickRecord;
+
+/* Per-instance end-of-run summary; 64 bytes. */
+typedef struct OmSummary {
+  double reported_tons; /* mine.status[last tick]["produced_tons"] (the reported production) */
+  double dumped_tons;   /* sum of dumper tons at the stop time */
+  double now;           /* simulation clock when the call returned */
+  uint32_t n_truck_events;
+  uint32_t n_decisions;      /* dispatch decisions taken */
+  uint32_t n_wrapper_orders; /* dispatcher.total_order_count (SPTF back orders count twice) */
+  uint32_t n_hops;           /* scheduler pops executed (truck/unit/tick entries) */
+  uint32_t n_jams, n_road_repairs, n_truck_repairs, n_unrepairable;
+  uint32_t n_ticks;
+  uint32_t err; /* OM_IERR_* */
+} OmSummary;
+
+/* Output buffers of om_run; any pointer may be NULL to skip that output.  All device pointers. */
+typedef struct OmOutputs {
+  OmSummary* summary;         /* [N] */
+  OmTickRecord* ticks;        /* [N * tick_capacity], sample k of instance n at n*tick_capacity+k */
+  int32_t tick_capacity;
+  int32_t trace_capacity;     /* records per instance */
+  OmTraceRecord* trace;       /* [N * trace_capacity] */
+  uint16_t* site_queue_ticks; /* [N * tick_capacity * (L+D)] minute-sampled queue totals (load_site.py:81-83) */
+  double* site_tons_ticks;    /* [N * tick_capacity * (L+D)] minute-sampled site tons (load_site.py:175, dump_site.py:69) */
+  int16_t* orders;            /* [N * order_capacity] (kind<<12 | site) per decision, in order; NULL to skip */
+  int32_t order_capacity;
+  int32_t reserved;
+} OmOutputs;
+
+/* Byte offsets of the per-instance state arrays inside one state blob (om_state_bytes).  Truck
+ * arrays have n_trucks elements, unit arrays n_shovels+n_dumpers, road arrays R. */
+typedef struct OmStateLayout {
+  uint32_t total_bytes;
+  uint32_t hdr;
+  uint32_t t_time, t_load, t_jstart, t_prejam, t_lastbrk, t_repair, t_total, t_cycle, t_dist; /* f64 */
+  uint32_t t_key;                                                                            /* u32 */
+  uint32_t t_svc, t_epoch, t_next, t_unit;                                                   /* u16 */
+  uint32_t t_phase, t_status, t_cur, t_tgt;                                                  /* u8  */
+  uint32_t u_rel_time, u_last_start, u_last_done, u_tons, u_lastbrk;                         /* f64 */
+  uint32_t u_rel_key, u_svc;                                                                 /* u32 */
+  uint32_t u_user, u_head, u_tail, u_qlen;                                                   /* u16 */
+  uint32_t u_repair;                                                                         /* u8  */
+  uint32_t r_repair_end;                                                                     /* f64 */
+  uint32_t j_pos, j_start, j_end;                                                            /* f64 [jam_capacity] */
+  uint32_t j_road;                                                                           /* u16 [jam_capacity] */
+  uint32_t s_qtotal, s_coming;                                                               /* u16 [L+D] */
+  uint32_t scratch;                                                                          /* f64 [max(U, 32)] */
+} OmStateLayout;
+
+typedef struct OmEngine* OmHandle;
+
+/* Replaces building Mine + sites + road (cli/run.py:48-107).  Copies the config to the device. */
+int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* out);
+int om_destroy(OmHandle h);
+const char* om_last_error(OmHandle h);
+
+/* Size / layout of one instance's state blob; the caller allocates n_instances * bytes. */
+int om_state_bytes(OmHandle h, size_t* per_instance);
+int om_state_layout(OmHandle h, OmStateLayout* out);
+
+/* Replaces Mine.__init__ + Truck.__init__ + registration of the generator processes
+ * (mine.py:30-48, 357-389): writes the t=0 state of every instance.
+ *   seeds       device [N]  Philox key per instance
+ *   dispatcher  device [N]  OM_DISP_* per instance
+ *   tape_values/tape_sites/tape_offsets: device, only for OM_RNG_TAPE (offsets has N+1 entries) */
+int om_reset(OmHandle h, const uint64_t* seeds, const int32_t* dispatcher, int rng_mode,
+             const double* tape_values, const uint8_t* tape_sites, const int64_t* tape_offsets,
+             void* state, void* stream);
+
+/* Replaces env.run(until) (mine.py:391): advances every instance until no pending entry has
+ * time < until (the reference's stop event is URGENT at `until`).  May be called repeatedly
+ * with increasing `until`. */
+int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* stream);
+
+/* Local partial statistics for the cross-GPU all-reduce (issued by the caller with NCCL):
+ * stats_out device [6*16] doubles = per dispatcher id {count, sum tons, sum tons^2, sum events,
+ * sum decisions, sum jams, sum road repairs, sum truck repairs, sum unrepairable, n_err, ...}. */
+int om_stats_reduce(OmHandle h, const OmSummary* summary, const int32_t* dispatcher,
+                    double* stats_out, void* stream);
+
+/* Kernel launch geometry actually used by om_run (for bench.py's launch accounting). */
+int om_launch_info(OmHandle h, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* warps_per_cta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENMINES_B200_H */

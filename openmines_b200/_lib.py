@@ -1,0 +1,76 @@
+"""Loader of the C-ABI shared library ``libopenmines_b200.so`` (include/openmines_b200.h).
+
+There is no CPU fallback: if the library has not been built (``python -c "import
+__graft_entry__ as g; g.build()"`` or ``python -m openmines_b200.build``) importing the engine
+raises.  The library is built in-tree next to this file so it travels with the repo snapshot.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libopenmines_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+_lib = None
+
+
+def sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + \
+        [os.path.join(INCLUDE, "openmines_b200.h")]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in sources())
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source of the engine for sm_100a with nvcc into the in-tree .so."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cus = [s for s in sources() if s.endswith(".cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", LIB_PATH] + cus
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("openmines_b200: %s is missing -- build it first (__graft_entry__.build()); "
+                           "the engine has no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+    lib.om_last_error.restype = ctypes.c_char_p
+    lib.om_last_error.argtypes = [vp]
+    lib.om_create.argtypes = [vp, i64, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.om_destroy.argtypes = [vp]
+    lib.om_state_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
+    lib.om_state_layout.argtypes = [vp, vp]
+    lib.om_launch_info.argtypes = [vp] + [ctypes.POINTER(i32)] * 4
+    lib.om_reset.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp]
+    lib.om_run.argtypes = [vp, dbl, vp, vp, vp]
+    lib.om_stats_reduce.argtypes = [vp, vp, vp, vp, vp]
+    for f in ("om_create", "om_destroy", "om_state_bytes", "om_state_layout", "om_launch_info", "om_reset",
+              "om_run", "om_stats_reduce"):
+        getattr(lib, f).restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ["om_create", "om_destroy", "om_last_error", "om_state_bytes", "om_state_layout", "om_reset",
+                    "om_run", "om_stats_reduce", "om_launch_info"]

@@ -1,0 +1,329 @@
+// Kernels + C ABI of the batched OpenMines engine (see include/openmines_b200.h).
+//
+// Compile for sm_100a with -fmad=false: all simulation times / tonnages are fp64 and must be
+// bit-identical to CPython's IEEE-754 double arithmetic (no FMA contraction).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "om_engine.cuh"
+
+#define OM_MAX_WARPS_PER_CTA 20
+#define OM_SMEM_LIMIT (227 * 1024)
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void om_reset_kernel(DevCfg c, OmStateLayout ly, unsigned char* state, const uint64_t* seeds,
+                                const int32_t* dispatcher, long long n) {
+  long long inst = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (inst >= n) return;
+  om_init_state(state + (size_t)inst * ly.total_bytes, c, ly, threadIdx.x & 31, seeds[inst], dispatcher[inst]);
+}
+
+template <int RNG>
+__global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(const __grid_constant__ RunParams p) {
+  extern __shared__ __align__(16) unsigned char om_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* sm = om_smem + (size_t)warp * p.ly.total_bytes;
+  const uint32_t n16 = p.ly.total_bytes >> 4;
+  while (true) {
+    unsigned long long inst = 0;
+    if (lane == 0) inst = atomicAdd(p.counter, 1ull);
+    inst = __shfl_sync(OM_FULL, inst, 0);
+    if (inst >= (unsigned long long)p.n_instances) break;
+    // stage the instance's SoA blob HBM -> shared memory (coalesced 16-byte vectors)
+    unsigned char* g = p.state + (size_t)inst * p.ly.total_bytes;
+    {
+      const uint4* src = (const uint4*)g;
+      uint4* dst = (uint4*)sm;
+      for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
+    }
+    __syncwarp();
+    Sim<RNG> s(sm, p, lane, (long long)inst);
+    s.load_hdr(p);
+    s.run(p.until);
+    s.store_hdr(p);
+    if (p.out.summary != nullptr) {
+      double dumped = s.dumped_tons();
+      if (lane == 0) {
+        OmSummary r;
+        r.reported_tons = s.reported_tons; r.dumped_tons = dumped; r.now = s.now;
+        r.n_truck_events = s.n_events; r.n_decisions = s.n_decisions; r.n_wrapper_orders = s.n_orders;
+        r.n_hops = s.n_hops; r.n_jams = s.n_jams; r.n_road_repairs = s.n_road_rep;
+        r.n_truck_repairs = s.n_brk; r.n_unrepairable = s.n_unrep; r.n_ticks = s.n_ticks; r.err = s.err;
+        p.out.summary[inst] = r;
+      }
+    }
+    __syncwarp();
+    {
+      uint4* dst = (uint4*)g;
+      const uint4* src = (const uint4*)sm;
+      for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
+    }
+    __syncwarp();
+  }
+}
+
+#define OM_STATS_PER_DISP 16
+__global__ void om_stats_kernel(const OmSummary* summary, const int32_t* dispatcher, long long n, double* stats) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int d = dispatcher[i];
+  if (d < 0 || d > 5) return;
+  const OmSummary& s = summary[i];
+  double* o = stats + d * OM_STATS_PER_DISP;
+  atomicAdd(o + 0, 1.0);
+  atomicAdd(o + 1, s.reported_tons);
+  atomicAdd(o + 2, s.reported_tons * s.reported_tons);
+  atomicAdd(o + 3, (double)s.n_truck_events);
+  atomicAdd(o + 4, (double)s.n_decisions);
+  atomicAdd(o + 5, (double)s.n_jams);
+  atomicAdd(o + 6, (double)s.n_road_repairs);
+  atomicAdd(o + 7, (double)s.n_truck_repairs);
+  atomicAdd(o + 8, (double)s.n_unrepairable);
+  atomicAdd(o + 9, (s.err != 0 && s.err != OM_IERR_TRACE_OVERFLOW) ? 1.0 : 0.0);
+  atomicAdd(o + 10, (double)s.n_hops);
+  atomicAdd(o + 11, s.dumped_tons);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct OmEngine {
+  int device = 0;
+  long long n = 0;
+  DevCfg c;
+  OmStateLayout ly;
+  std::vector<void*> dev_allocs;
+  unsigned long long* counter = nullptr;
+  int rng_mode = OM_RNG_DET;
+  const double* tape_values = nullptr;
+  const uint8_t* tape_sites = nullptr;
+  const int64_t* tape_offsets = nullptr;
+  int grid = 0, block = 0, smem = 0, warps = 0;
+  std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int set_err(OmEngine* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return set_err(h, OM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+template <typename T>
+static int upload(OmEngine* h, const T* src, size_t count, const T** dst) {
+  void* d = nullptr;
+  size_t bytes = (count ? count : 1) * sizeof(T);
+  CK(cudaMalloc(&d, bytes));
+  h->dev_allocs.push_back(d);
+  if (count) CK(cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = (const T*)d;
+  return OM_OK;
+}
+
+static uint32_t take(uint32_t& off, size_t elem, size_t count) {
+  off = (uint32_t)((off + elem - 1) / elem * elem);
+  uint32_t r = off;
+  off += (uint32_t)(elem * count);
+  return r;
+}
+
+static void build_layout(const DevCfg& c, OmStateLayout& ly) {
+  memset(&ly, 0, sizeof(ly));
+  uint32_t off = 0;
+  const size_t T = c.T, U = c.U, S = c.S, R = c.R, J = c.J, NS = c.NS;
+  ly.hdr = take(off, 8, OM_HDR_BYTES / 8);
+  ly.t_time = take(off, 8, T); ly.t_load = take(off, 8, T); ly.t_jstart = take(off, 8, T);
+  ly.t_prejam = take(off, 8, T); ly.t_lastbrk = take(off, 8, T); ly.t_repair = take(off, 8, T);
+  ly.t_total = take(off, 8, T); ly.t_cycle = take(off, 8, T); ly.t_dist = take(off, 8, T);
+  ly.u_rel_time = take(off, 8, U); ly.u_last_start = take(off, 8, U); ly.u_last_done = take(off, 8, U);
+  ly.u_tons = take(off, 8, U); ly.u_lastbrk = take(off, 8, S);
+  ly.r_repair_end = take(off, 8, R);
+  ly.j_pos = take(off, 8, J); ly.j_start = take(off, 8, J); ly.j_end = take(off, 8, J);
+  size_t nscr = U;
+  if (nscr < (R + 1) / 2) nscr = (R + 1) / 2;
+  if (nscr < 32) nscr = 32;
+  ly.scratch = take(off, 8, nscr);
+  ly.t_key = take(off, 4, T); ly.u_rel_key = take(off, 4, U); ly.u_svc = take(off, 4, U);
+  ly.t_svc = take(off, 2, T); ly.t_epoch = take(off, 2, T); ly.t_next = take(off, 2, T); ly.t_unit = take(off, 2, T);
+  ly.u_user = take(off, 2, U); ly.u_head = take(off, 2, U); ly.u_tail = take(off, 2, U); ly.u_qlen = take(off, 2, U);
+  ly.j_road = take(off, 2, J); ly.s_qtotal = take(off, 2, NS); ly.s_coming = take(off, 2, NS);
+  ly.t_phase = take(off, 1, T); ly.t_status = take(off, 1, T); ly.t_cur = take(off, 1, T); ly.t_tgt = take(off, 1, T);
+  ly.u_repair = take(off, 1, S);
+  ly.total_bytes = (off + 15u) & ~15u;
+}
+
+extern "C" {
+
+const char* om_last_error(OmHandle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* out) {
+  OmEngine* h = nullptr;
+  if (!cfg || !out) return set_err(h, OM_E_INVALID, "om_create: null argument");
+  if (cfg->abi_version != OM_ABI_VERSION) return set_err(h, OM_E_INVALID, "om_create: ABI version mismatch");
+  if (n_instances <= 0) return set_err(h, OM_E_INVALID, "om_create: n_instances must be > 0");
+  const int T = cfg->n_trucks, L = cfg->n_load_sites, D = cfg->n_dump_sites, S = cfg->n_shovels, M = cfg->n_dumpers;
+  if (T <= 0 || L <= 0 || D <= 0 || S <= 0 || M <= 0 || cfg->n_truck_types <= 0)
+    return set_err(h, OM_E_INVALID, "om_create: empty mine (mine.py:346-351 asserts)");
+  if (T >= 0xFFFF || L + D > 32 || L + D >= 0xFF || cfg->jam_capacity <= 0 || cfg->jam_capacity > 4096)
+    return set_err(h, OM_E_UNSUPPORTED, "om_create: need T < 65535, L + D <= 32, 0 < jam_capacity <= 4096");
+  for (int s = 0; s < L + D; ++s) {
+    int nu = cfg->site_unit_begin[s + 1] - cfg->site_unit_begin[s];
+    if (nu <= 0 || nu > 32) return set_err(h, OM_E_UNSUPPORTED, "om_create: each site needs 1..32 shovels/dumpers");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return set_err(h, OM_E_CUDA, "om_create: no CUDA device (this engine has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_err(h, OM_E_INVALID, "om_create: bad device index");
+  h = new OmEngine();
+  h->device = device;
+  h->n = n_instances;
+  int rc = OM_OK;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { rc = set_err(nullptr, OM_E_CUDA, cudaGetErrorString(e)); delete h; return rc; }
+  DevCfg& c = h->c;
+  memset(&c, 0, sizeof(c));
+  c.T = T; c.L = L; c.D = D; c.S = S; c.M = M; c.U = S + M; c.R = L + 2 * L * D; c.NS = L + D;
+  c.NT = cfg->n_truck_types; c.J = cfg->jam_capacity; c.sum_mode = cfg->sum_mode; c.nearest_init = cfg->nearest_init;
+  c.road_lambda = cfg->road_lambda; c.road_mu = cfg->road_mu; c.road_sigma = cfg->road_sigma;
+  c.detour_mu = cfg->detour_mu; c.detour_sigma = cfg->detour_sigma; c.breakdown_mean = cfg->breakdown_mean;
+  c.repair_mu = cfg->repair_mu; c.repair_sigma = cfg->repair_sigma; c.unrepairable_mean = cfg->unrepairable_mean;
+  c.maint_mean = cfg->maint_mean; c.maint_mu = cfg->maint_mu; c.maint_sigma = cfg->maint_sigma;
+  c.jam_sd = cfg->jam_sd; c.jam_scale = cfg->jam_scale;
+#define UP(field, src, count) if (rc == OM_OK) rc = upload(h, cfg->src, (size_t)(count), &c.field)
+  UP(cap, truck_capacity, T); UP(speed, truck_speed, T); UP(ttype, truck_type, T);
+  UP(ubeg, site_unit_begin, L + D + 1); UP(dcycle, dumper_cycle, M); UP(rdist, road_distance, c.R);
+  UP(load_time, load_time, (size_t)c.NT * S); UP(sptf_cost, sptf_cost, (size_t)c.NT * L);
+  UP(jam_chance, jam_chance, T + 1); UP(near_haul, nearest_haul, L); UP(near_back, nearest_back, D);
+  UP(fixed_group, fixed_group, T);
+#undef UP
+  if (rc == OM_OK) {
+    void* d = nullptr;
+    e = cudaMalloc(&d, sizeof(unsigned long long));
+    if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, cudaGetErrorString(e));
+    else { h->counter = (unsigned long long*)d; h->dev_allocs.push_back(d); }
+  }
+  if (rc == OM_OK) {
+    build_layout(c, h->ly);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int maxsm = 0;
+    cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    int limit = maxsm < OM_SMEM_LIMIT ? maxsm : OM_SMEM_LIMIT;
+    int w = limit / (int)h->ly.total_bytes;
+    if (w > OM_MAX_WARPS_PER_CTA) w = OM_MAX_WARPS_PER_CTA;
+    if (w < 1) rc = set_err(h, OM_E_UNSUPPORTED, "om_create: one instance's state does not fit in shared memory");
+    else {
+      h->warps = w; h->block = w * 32; h->smem = w * (int)h->ly.total_bytes;
+      long long ctas = (n_instances + w - 1) / w;
+      h->grid = (int)(ctas < sms ? ctas : sms);
+      const void* fns[3] = {(const void*)om_run_kernel<OM_RNG_DET>, (const void*)om_run_kernel<OM_RNG_PHILOX>,
+                            (const void*)om_run_kernel<OM_RNG_TAPE>};
+      for (int i = 0; i < 3 && rc == OM_OK; ++i) {
+        e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
+        if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+      }
+    }
+  }
+  if (rc != OM_OK) {
+    g_create_err = h->err;
+    for (void* d : h->dev_allocs) cudaFree(d);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return OM_OK;
+}
+
+int om_destroy(OmHandle h) {
+  if (!h) return OM_E_INVALID;
+  cudaSetDevice(h->device);
+  for (void* d : h->dev_allocs) cudaFree(d);
+  delete h;
+  return OM_OK;
+}
+
+int om_state_bytes(OmHandle h, size_t* per_instance) {
+  if (!h || !per_instance) return OM_E_INVALID;
+  *per_instance = h->ly.total_bytes;
+  return OM_OK;
+}
+
+int om_state_layout(OmHandle h, OmStateLayout* out) {
+  if (!h || !out) return OM_E_INVALID;
+  *out = h->ly;
+  return OM_OK;
+}
+
+int om_launch_info(OmHandle h, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* warps_per_cta) {
+  if (!h) return OM_E_INVALID;
+  if (grid) *grid = h->grid;
+  if (block) *block = h->block;
+  if (smem_bytes) *smem_bytes = h->smem;
+  if (warps_per_cta) *warps_per_cta = h->warps;
+  return OM_OK;
+}
+
+int om_reset(OmHandle h, const uint64_t* seeds, const int32_t* dispatcher, int rng_mode, const double* tape_values,
+             const uint8_t* tape_sites, const int64_t* tape_offsets, void* state, void* stream) {
+  if (!h || !seeds || !dispatcher || !state) return set_err(h, OM_E_INVALID, "om_reset: null argument");
+  if (rng_mode < OM_RNG_DET || rng_mode > OM_RNG_TAPE) return set_err(h, OM_E_INVALID, "om_reset: bad rng_mode");
+  if (rng_mode == OM_RNG_TAPE && (!tape_values || !tape_sites || !tape_offsets))
+    return set_err(h, OM_E_INVALID, "om_reset: OM_RNG_TAPE needs tape_values/tape_sites/tape_offsets");
+  CK(cudaSetDevice(h->device));
+  h->rng_mode = rng_mode;
+  h->tape_values = tape_values; h->tape_sites = tape_sites; h->tape_offsets = tape_offsets;
+  const int wpb = 8;
+  long long blocks = (h->n + wpb - 1) / wpb;
+  om_reset_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(h->c, h->ly, (unsigned char*)state, seeds,
+                                                                          dispatcher, h->n);
+  CK(cudaGetLastError());
+  return OM_OK;
+}
+
+int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* stream) {
+  if (!h || !state) return set_err(h, OM_E_INVALID, "om_run: null argument");
+  CK(cudaSetDevice(h->device));
+  RunParams p;
+  memset(&p, 0, sizeof(p));
+  p.c = h->c; p.ly = h->ly;
+  if (outs) p.out = *outs;
+  if (p.out.ticks == nullptr) p.out.tick_capacity = 0;
+  p.state = (unsigned char*)state;
+  p.tape_values = h->tape_values; p.tape_sites = h->tape_sites; p.tape_offsets = h->tape_offsets;
+  p.counter = h->counter; p.n_instances = h->n; p.until = until;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+  switch (h->rng_mode) {
+    case OM_RNG_DET: om_run_kernel<OM_RNG_DET><<<h->grid, h->block, h->smem, st>>>(p); break;
+    case OM_RNG_PHILOX: om_run_kernel<OM_RNG_PHILOX><<<h->grid, h->block, h->smem, st>>>(p); break;
+    default: om_run_kernel<OM_RNG_TAPE><<<h->grid, h->block, h->smem, st>>>(p); break;
+  }
+  CK(cudaGetLastError());
+  return OM_OK;
+}
+
+int om_stats_reduce(OmHandle h, const OmSummary* summary, const int32_t* dispatcher, double* stats_out, void* stream) {
+  if (!h || !summary || !dispatcher || !stats_out) return set_err(h, OM_E_INVALID, "om_stats_reduce: null argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(stats_out, 0, sizeof(double) * 6 * OM_STATS_PER_DISP, st));
+  long long blocks = (h->n + 255) / 256;
+  om_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(summary, dispatcher, h->n, stats_out);
+  CK(cudaGetLastError());
+  return OM_OK;
+}
+
+}  // extern "C"

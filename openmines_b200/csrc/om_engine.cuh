@@ -1,0 +1,1064 @@
+// Device-side engine: one warp simulates one mine instance.
+//
+// The per-instance state is a structure-of-arrays blob (layout: OmStateLayout) that lives in HBM
+// between calls and is staged into shared memory for the duration of om_run.  All "scalar" DES
+// logic (one truck's transition) is executed warp-uniformly -- every lane computes the same values
+// and performs the same shared-memory stores (same value, same address), so no intra-warp
+// synchronisation is needed around it; lane-parallel phases (next-event reduction, status counts,
+// breakdown sampling, wait estimation) are bracketed by __syncwarp().
+//
+// Event ordering reproduces SimPy 4.0.2: every pending entry carries (time fp64, key u32) with
+// key = (priority << 31) | seq, URGENT = 0, NORMAL = 1, seq = per-instance schedule counter
+// (simpy.core.Environment.schedule; call sites listed in SURVEY.md section 2 row 10).  Pending
+// entries: one per truck (a truck waits on exactly one thing), one pending Release per
+// shovel/dumper, one monitor-block entry.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include "../../include/openmines_b200.h"
+#include "om_rng.cuh"
+
+#define OM_FULL 0xffffffffu
+#define OM_NONE16 0xFFFFu
+#define OM_NOLOC 0xFFu
+#define OM_KEY_NORMAL 0x80000000u
+#define OM_KEY_SENTINEL 0xFFFFFFFFu
+
+// truck statuses (truck.py:297-436 string statuses) -- same codes as oracle/trace_format.py
+enum : uint8_t {
+  ST_IDLE = 0, ST_WAIT_INIT, ST_MOVING, ST_WAIT_SHOVEL, ST_LOADING, ST_WAIT_HAUL, ST_WAIT_DUMPER,
+  ST_UNLOADING, ST_WAIT_BACK, ST_REPAIRING, ST_UNREPAIRABLE
+};
+
+// truck continuation points (what happens when the truck's pending entry pops); see SURVEY 3.2
+enum : uint8_t {
+  PH_DEAD = 0,        // Truck.run returned (unrepairable)
+  PH_WAITING,         // in a shovel/dumper FIFO, request not yet granted (no pending entry)
+  PH_RUN_INIT,        // U  Initialize(run)                truck.py:296-317
+  PH_MOVE_BEGIN,      // U  Initialize(move)               truck.py:116-148
+  PH_MOVE_REPAIRED,   //    Timeout(repair_time)           truck.py:149-150
+  PH_MOVE_ARRIVE,     //    Timeout(duration+pre_jam)      truck.py:211-218
+  PH_MOVE_RET,        //    Process(move) -> run resumes   truck.py:319-339 / 404-419
+  PH_LOAD_GRANTED,    //    Request granted                truck.py:342-350
+  PH_LOAD_BEGIN,      // U  Initialize(load)               truck.py:221-228
+  PH_LOAD_DONE,       //    Timeout(load_time)             truck.py:230-235
+  PH_LOAD_RET,        //    Process(load) -> run resumes   truck.py:352-370
+  PH_MAINT_DONE,      //    Timeout(maintenance)           truck.py:372-379
+  PH_DUMP_GRANTED,    //    Request granted                truck.py:422-429
+  PH_DUMP_BEGIN,      // U  Initialize(unload)             truck.py:238-242
+  PH_DUMP_DONE,       //    Timeout(dump_time)             truck.py:243-251
+  PH_DUMP_RET,        //    Process(unload) -> run resumes truck.py:431-453
+  PH_AWAIT_ORDER      //    paused for an external decision (OM_DISP_EXTERNAL)
+};
+
+// trace kinds (include/openmines_b200.h OmTraceRecord; same codes as oracle/trace_format.py)
+enum : uint8_t {
+  K_INIT_ORDER = 0, K_MOVE_INIT, K_MOVE_HAUL, K_MOVE_UNHAUL, K_WAIT_SHOVEL, K_GET_SHOVEL, K_ORDER_HAUL,
+  K_ORDER_BACK, K_WAIT_DUMPER, K_GET_DUMPER, K_BREAKDOWN, K_UNREPAIRABLE, K_JAM, K_ROAD_REPAIR,
+  K_SHOVEL_MAINT_START, K_SHOVEL_MAINT_DONE
+};
+
+// Device view of the packed config (pointers are device pointers owned by the handle).
+struct DevCfg {
+  int T, L, D, S, M, U, R, NS, NT, J, sum_mode, nearest_init;
+  const double* cap;
+  const double* speed;
+  const int32_t* ttype;
+  const int32_t* ubeg;
+  const double* dcycle;
+  const double* rdist;
+  const double* load_time;
+  const double* sptf_cost;
+  const double* jam_chance;
+  const int32_t* near_haul;
+  const int32_t* near_back;
+  const int32_t* fixed_group;
+  double road_lambda, road_mu, road_sigma, detour_mu, detour_sigma;
+  double breakdown_mean, repair_mu, repair_sigma, unrepairable_mean, maint_mean, maint_mu, maint_sigma;
+  double jam_sd, jam_scale;
+};
+
+// Per-instance scalars, first bytes of the state blob.
+struct InstHdr {
+  double now;
+  double tick_time;
+  double reported_tons;
+  uint64_t seed;
+  uint64_t tape_pos;
+  uint32_t seq;
+  uint32_t tick_key;
+  int32_t tick_k;
+  int32_t dispatcher;
+  uint32_t n_events, n_decisions, n_orders, n_hops;
+  uint32_t n_jams, n_road_rep, n_brk, n_unrep;
+  uint32_t jam_count;
+  uint32_t err;
+  uint32_t trace_count;
+  uint32_t order_count;
+  int32_t pending_truck;
+  int32_t pending_kind;
+  uint32_t n_ticks;
+  uint32_t pad;
+};
+static_assert(sizeof(InstHdr) == 120, "InstHdr size");
+#define OM_HDR_BYTES 128
+
+struct RunParams {
+  DevCfg c;
+  OmStateLayout ly;
+  OmOutputs out;
+  unsigned char* state;       // [N * ly.total_bytes]
+  const double* tape_values;
+  const uint8_t* tape_sites;
+  const int64_t* tape_offsets;
+  unsigned long long* counter; // dynamic instance scheduler
+  long long n_instances;
+  double until;
+};
+
+__device__ __forceinline__ double om_inf() { return __longlong_as_double(0x7FF0000000000000LL); }
+
+// CPython >= 3.12 sum() step over exact floats (Neumaier), see oracle/des_oracle.py py_sum
+struct PySum {
+  double s, c;
+  __device__ __forceinline__ void init() { s = 0.0; c = 0.0; }
+  __device__ __forceinline__ void add(double x, bool neumaier) {
+    double t = s + x;
+    if (neumaier) {
+      if (fabs(s) >= fabs(x)) c += (s - t) + x;
+      else c += (x - t) + s;
+    }
+    s = t;
+  }
+  __device__ __forceinline__ double result() const {
+    double r = s;
+    if (c != 0.0 && isfinite(c)) r += c;
+    return r;
+  }
+};
+
+template <int RNG>
+struct Sim {
+  unsigned char* sm;
+  const DevCfg& c;
+  const OmStateLayout& ly;
+  const OmOutputs& out;
+  int lane;
+  long long inst;
+  // hot scalars (registers); mirrored in InstHdr between calls
+  double now, tick_time, reported_tons;
+  uint32_t seq, tick_key;
+  int tick_k, disp;
+  uint32_t k0, k1;
+  uint32_t n_events, n_decisions, n_orders, n_hops, n_jams, n_road_rep, n_brk, n_unrep;
+  uint32_t jam_count, err, trace_count, order_count, n_ticks;
+  unsigned long long tape_pos, tape_end;
+  const double* tape_v;
+  const uint8_t* tape_s;
+
+  __device__ __forceinline__ Sim(unsigned char* sm_, const RunParams& p, int lane_, long long inst_)
+      : sm(sm_), c(p.c), ly(p.ly), out(p.out), lane(lane_), inst(inst_) {}
+
+#define F64(field, i) (((double*)(sm + ly.field))[i])
+#define U32A(field, i) (((uint32_t*)(sm + ly.field))[i])
+#define U16A(field, i) (((uint16_t*)(sm + ly.field))[i])
+#define U8A(field, i) (((uint8_t*)(sm + ly.field))[i])
+
+  // ---------------------------------------------------------------------------------------------
+  // header <-> registers
+  // ---------------------------------------------------------------------------------------------
+  __device__ __forceinline__ void load_hdr(const RunParams& p) {
+    const InstHdr* h = (const InstHdr*)(sm + ly.hdr);
+    now = h->now; tick_time = h->tick_time; reported_tons = h->reported_tons;
+    seq = h->seq; tick_key = h->tick_key; tick_k = h->tick_k; disp = h->dispatcher;
+    k0 = (uint32_t)h->seed; k1 = (uint32_t)(h->seed >> 32);
+    n_events = h->n_events; n_decisions = h->n_decisions; n_orders = h->n_orders; n_hops = h->n_hops;
+    n_jams = h->n_jams; n_road_rep = h->n_road_rep; n_brk = h->n_brk; n_unrep = h->n_unrep;
+    jam_count = h->jam_count; err = h->err; trace_count = h->trace_count; order_count = h->order_count;
+    n_ticks = h->n_ticks;
+    tape_pos = h->tape_pos; tape_end = 0; tape_v = p.tape_values; tape_s = p.tape_sites;
+    if (RNG == OM_RNG_TAPE) {
+      tape_pos += (unsigned long long)p.tape_offsets[inst];   // hdr stores the position relative to the instance's tape
+      tape_end = (unsigned long long)p.tape_offsets[inst + 1];
+    }
+  }
+  __device__ __forceinline__ void store_hdr(const RunParams& p) {
+    InstHdr* h = (InstHdr*)(sm + ly.hdr);
+    h->now = now; h->tick_time = tick_time; h->reported_tons = reported_tons;
+    h->seq = seq; h->tick_key = tick_key; h->tick_k = tick_k;
+    h->n_events = n_events; h->n_decisions = n_decisions; h->n_orders = n_orders; h->n_hops = n_hops;
+    h->n_jams = n_jams; h->n_road_rep = n_road_rep; h->n_brk = n_brk; h->n_unrep = n_unrep;
+    h->jam_count = jam_count; h->err = err; h->trace_count = trace_count; h->order_count = order_count;
+    h->n_ticks = n_ticks;
+    h->tape_pos = (RNG == OM_RNG_TAPE) ? tape_pos - (unsigned long long)p.tape_offsets[inst] : 0ull;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // trace / order log (lane 0 writes to HBM)
+  // ---------------------------------------------------------------------------------------------
+  __device__ __forceinline__ void emit(uint8_t kind, uint32_t truck, uint32_t arg0, uint32_t arg1, double a, double b) {
+    if (kind < 12) n_events++;
+    if (out.trace != nullptr) {
+      if (trace_count < (uint32_t)out.trace_capacity) {
+        if (lane == 0) {
+          OmTraceRecord r;
+          r.time = now; r.a = a; r.b = b; r.truck = (uint16_t)truck; r.kind = kind; r.flags = 0;
+          r.arg0 = (uint16_t)arg0; r.arg1 = (uint16_t)arg1;
+          out.trace[inst * (long long)out.trace_capacity + trace_count] = r;
+        }
+      } else if (err == OM_IERR_NONE) {
+        err = OM_IERR_TRACE_OVERFLOW;
+      }
+      trace_count++;
+    }
+  }
+  __device__ __forceinline__ void log_order(int kind, int site) {
+    if (out.orders != nullptr && order_count < (uint32_t)out.order_capacity && lane == 0)
+      out.orders[inst * (long long)out.order_capacity + order_count] = (int16_t)((kind << 12) | site);
+    order_count++;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // RNG
+  // ---------------------------------------------------------------------------------------------
+  __device__ __forceinline__ double tape_next(int site) {
+    if (tape_pos >= tape_end || tape_s[tape_pos] != (uint8_t)site) {
+      if (err == OM_IERR_NONE || err == OM_IERR_TRACE_OVERFLOW) err = OM_IERR_TAPE;
+      return 0.0;
+    }
+    double v = tape_v[tape_pos];
+    tape_pos++;
+    return v;
+  }
+  __device__ __forceinline__ Philox4 px(uint32_t epoch, uint32_t entity, uint32_t site, uint32_t stream = 0) const {
+    return philox4x32_10(epoch, entity, site, stream, k0, k1);
+  }
+  // exponential with mean `mean` (np.random.exponential(scale) / random.expovariate(1/mean))
+  __device__ __forceinline__ double draw_exp(int site, uint32_t epoch, uint32_t entity, double mean) {
+    if (RNG == OM_RNG_DET) return om_inf();
+    if (RNG == OM_RNG_TAPE) return tape_next(site);
+    return (double)om_exp1(px(epoch, entity, site).x) * mean;
+  }
+  __device__ __forceinline__ double draw_normal(int site, uint32_t epoch, uint32_t entity, double mu, double sigma) {
+    if (RNG == OM_RNG_TAPE) return tape_next(site);
+    Philox4 r = px(epoch, entity, site);
+    return mu + sigma * (double)om_normal(r.x, r.y);
+  }
+  __device__ __forceinline__ double draw_jitter(uint32_t epoch, uint32_t entity) {
+    if (RNG == OM_RNG_DET) return 0.0;
+    if (RNG == OM_RNG_TAPE) return tape_next(OM_S_LOAD_JITTER);
+    return -0.1 + 0.2 * (double)om_u01(px(epoch, entity, OM_S_LOAD_JITTER).x);
+  }
+  __device__ __forceinline__ int draw_randint(uint32_t epoch, uint32_t entity, int n) {
+    if (RNG == OM_RNG_TAPE) return (int)tape_next(OM_S_DISPATCH);
+    return (int)om_randint(px(epoch, entity, OM_S_DISPATCH).x, (uint32_t)n);   // also in DET mode (keyed, exact)
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // scheduling primitives
+  // ---------------------------------------------------------------------------------------------
+  __device__ __forceinline__ void sched_truck(int i, double t, uint32_t prio, uint8_t phase) {
+    F64(t_time, i) = t;
+    U32A(t_key, i) = prio | seq;
+    seq++;
+    U8A(t_phase, i) = phase;
+  }
+  __device__ __forceinline__ void fail(uint32_t code) {
+    if (err == OM_IERR_NONE || err == OM_IERR_TRACE_OVERFLOW) err = code;
+  }
+
+  // FIFO of waiting trucks per unit (simpy Resource.put_queue), linked through t_next
+  __device__ __forceinline__ void q_push(int u, int i) {
+    uint32_t n = U16A(u_qlen, u);
+    U16A(t_next, i) = OM_NONE16;
+    if (n == 0) U16A(u_head, u) = (uint16_t)i;
+    else U16A(t_next, U16A(u_tail, u)) = (uint16_t)i;
+    U16A(u_tail, u) = (uint16_t)i;
+    U16A(u_qlen, u) = (uint16_t)(n + 1);
+  }
+  __device__ __forceinline__ int q_pop(int u) {
+    int h = U16A(u_head, u);
+    uint32_t n = U16A(u_qlen, u) - 1;
+    U16A(u_head, u) = U16A(t_next, h);
+    U16A(u_qlen, u) = (uint16_t)n;
+    if (n == 0) U16A(u_tail, u) = OM_NONE16;
+    return h;
+  }
+  // Resource._trigger_put on the queue head only (simpy/resources/base.py)
+  __device__ __forceinline__ int grant_head(int u) {
+    int h = q_pop(u);
+    U16A(u_user, u) = (uint16_t)h;
+    sched_truck(h, now, OM_KEY_NORMAL, (u < c.S) ? PH_LOAD_GRANTED : PH_DUMP_GRANTED);
+    return h;
+  }
+  // Request.__init__: append, then _trigger_put.  Returns the truck's index in the queue afterwards
+  // as truck.check_queue_position sees it (truck.py:258-273).
+  __device__ __forceinline__ int request(int u, int i) {
+    q_push(u, i);
+    F64(t_time, i) = om_inf();
+    U32A(t_key, i) = OM_KEY_SENTINEL;
+    U8A(t_phase, i) = PH_WAITING;
+    U16A(t_unit, i) = (uint16_t)u;
+    bool me = false;
+    if (U16A(u_user, u) == OM_NONE16) me = (grant_head(u) == i);
+    return me ? 0 : (int)U16A(u_qlen, u) - 1;
+  }
+  // Resource.release: users cleared now, Release event scheduled NORMAL (hand-over happens when it pops)
+  __device__ __forceinline__ void release(int u) {
+    U16A(u_user, u) = OM_NONE16;
+    F64(u_rel_time, u) = now;
+    U32A(u_rel_key, u) = OM_KEY_NORMAL | seq;
+    seq++;
+  }
+
+  // get_available_shovel / get_available_dumper (load_site.py:209-220, dump_site.py:105-116):
+  // first idle unit, else first unit with the shortest queue.  Lane-parallel over the site's units.
+  __device__ __forceinline__ int pick_unit(int site) {
+    int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
+    int u = ub + lane;
+    bool valid = u < ue;
+    bool idle = valid && U16A(u_user, u) == OM_NONE16;
+    unsigned m = __ballot_sync(OM_FULL, idle);
+    if (m) return ub + __ffs(m) - 1;
+    uint32_t v = valid ? (((uint32_t)U16A(u_qlen, u) << 8) | (uint32_t)lane) : 0xFFFFFFFFu;
+    uint32_t best = __reduce_min_sync(OM_FULL, v);
+    return ub + (int)(best & 0xFFu);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // road: distance + repair state (road.py:235-331)
+  // ---------------------------------------------------------------------------------------------
+  __device__ __forceinline__ int road_id(int cur, int tgt) const {
+    if (cur == 0) return tgt - 1;
+    if (cur <= c.L) return c.L + (cur - 1) * c.D + (tgt - c.L - 1);
+    return c.L + c.L * c.D + (cur - c.L - 1) * c.L + (tgt - 1);
+  }
+  __device__ __forceinline__ double get_distance(int i, int cur, int tgt, uint32_t epoch) {
+    int rid = road_id(cur, tgt);
+    double end = F64(r_repair_end, rid);
+    bool in_repair;
+    if (now < end) {
+      in_repair = true;
+    } else {
+      in_repair = false;
+      if (RNG != OM_RNG_DET) {
+        double gap = draw_exp(OM_S_ROAD_GAP, epoch, (uint32_t)i, 1.0 / c.road_lambda);   // expovariate(lambda)
+        if (now >= end + gap) {
+          double d = draw_normal(OM_S_ROAD_DUR, epoch, (uint32_t)i, c.road_mu, c.road_sigma);
+          double dur = (d > 0.0) ? d : 0.0;   // max(0, x)
+          in_repair = true;
+          end = now + dur;
+          F64(r_repair_end, rid) = end;
+          n_road_rep++;
+          emit(K_ROAD_REPAIR, 0xFFFFu, (uint32_t)rid, 0, end, dur);
+        }
+      }
+    }
+    double dist = __ldg(&c.rdist[rid]);
+    if (in_repair) {
+      double p = draw_normal(OM_S_DETOUR, epoch, (uint32_t)i, c.detour_mu, c.detour_sigma);
+      double pun = (p > 0.0) ? p : 0.0;
+      dist = dist * (1.0 + pun);
+    }
+    return dist;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // queue-wait estimation (ParkingLot.update_queue_wait_status, load_site.py:21-68), lane = unit
+  // ---------------------------------------------------------------------------------------------
+  // Writes est per unit of [ub, ue) into scratch[], then returns (on every lane) nothing; callers read
+  // site minima with site_est().
+  __device__ __forceinline__ void unit_est_all(bool load_side) {
+    int ub = load_side ? 0 : c.S, ue = load_side ? c.S : c.U;
+    for (int u = ub + lane; u < ue; u += 32) {
+      double est;
+      int n = U16A(u_qlen, u);
+      if (load_side) {
+        double ls = F64(u_last_start, u), ld = F64(u_last_done, u);
+        double last = (ld > ls) ? ld : ls;               // max(last_service_time, last_service_done_time)
+        double total = 0.0;
+        int t = U16A(u_head, u);
+        for (int q = 0; q < n; ++q) {
+          total += __ldg(&c.load_time[__ldg(&c.ttype[t]) * c.S + u]);
+          t = U16A(t_next, t);
+        }
+        int usr = U16A(u_user, u);
+        if (usr != OM_NONE16) total += __ldg(&c.load_time[__ldg(&c.ttype[usr]) * c.S + u]);
+        double v = (last + total) - now;
+        est = (0.0 > v) ? 0.0 : v;                       // max(v, 0)
+      } else {
+        double cyc = __ldg(&c.dcycle[u - c.S]);
+        double total = 0.0;
+        for (int q = 0; q < n; ++q) total += cyc;
+        double used = now - F64(u_last_start, u);
+        est = (total > used) ? (total - used) : 0.0;
+      }
+      F64(scratch, u) = est;
+    }
+    __syncwarp();
+  }
+  // min over the site's units (call after unit_est_all); lane-local loop
+  __device__ __forceinline__ double site_est(int site) {
+    int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
+    double m = F64(scratch, ub);
+    for (int u = ub + 1; u < ue; ++u) {
+      double v = F64(scratch, u);
+      if (v < m) m = v;
+    }
+    return m;
+  }
+
+  // first-minimum argmin over lanes [0, n) of a double (np.argmin on a list)
+  __device__ __forceinline__ int argmin_lanes(double v, int n) {
+    double best = __shfl_sync(OM_FULL, v, 0);
+    int idx = 0;
+    for (int s = 1; s < n; ++s) {
+      double x = __shfl_sync(OM_FULL, v, s);
+      if (x < best) { best = x; idx = s; }
+    }
+    return idx;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // the six built-in dispatchers as device functions (dispatch_algorithms/*.py) behind
+  // give_init_order / give_haul_order / give_back_order.  Returns the site index, or -1 on error.
+  // ---------------------------------------------------------------------------------------------
+  __device__ __forceinline__ int decide(int kind, int i) {
+    int r = 0;
+    const int L = c.L, D = c.D;
+    switch (disp) {
+      case OM_DISP_NAIVE:
+        r = 0;
+        break;
+      case OM_DISP_RANDOM: {
+        // haul draws over len(load_sites), back over len(dump_sites)  (random_dispatcher.py:21-29)
+        int n = (kind == OM_ORDER_BACK) ? D : L;
+        r = draw_randint(U16A(t_epoch, i), (uint32_t)i, n);
+        break;
+      }
+      case OM_DISP_NEAREST:
+        if (kind == OM_ORDER_INIT) r = c.nearest_init;
+        else if (kind == OM_ORDER_HAUL) r = __ldg(&c.near_haul[U8A(t_cur, i) - 1]);
+        else r = __ldg(&c.near_back[U8A(t_cur, i) - 1 - L]);
+        break;
+      case OM_DISP_FIXEDGROUP:
+        if (kind == OM_ORDER_HAUL) r = __ldg(&c.near_haul[U8A(t_cur, i) - 1]);
+        else r = __ldg(&c.fixed_group[i]);
+        break;
+      case OM_DISP_SPTF: {
+        if (kind == OM_ORDER_HAUL) {
+          // len(coming) + estimated_queue_wait_time   (sptf_dispatcher.py:40-57)
+          unit_est_all(false);
+          double v = om_inf();
+          if (lane < D) {
+            int site = L + lane;
+            int coming = (int)U16A(s_coming, site) - ((U8A(t_tgt, i) == 1 + site) ? 1 : 0);
+            v = (double)coming + site_est(site);
+          }
+          r = argmin_lanes(v, D);
+        } else {
+          // sum(cap/productivity for coming trucks, truck order) + estimated_queue_wait_time (:21-38)
+          unit_est_all(true);
+          double v = om_inf();
+          PySum ps; ps.init();
+          const bool neu = c.sum_mode != 0;
+          int my_site_loc = 1 + lane;
+          for (int o = 0; o < c.T; ++o) {
+            int tg = U8A(t_tgt, o);
+            if (lane < L && o != i && tg == my_site_loc)
+              ps.add(__ldg(&c.sptf_cost[__ldg(&c.ttype[o]) * L + lane]), neu);
+          }
+          if (lane < L) v = ps.result() + site_est(lane);
+          r = argmin_lanes(v, L);
+        }
+        __syncwarp();
+        break;
+      }
+      case OM_DISP_SQ: {
+        // coming trucks + minute-sampled total queue length (sq_dispatcher.py:18-100)
+        int k = (int)now;   // int(env.now)
+        if (k != tick_k) { fail(OM_IERR_SQ_KEYERROR); return -1; }
+        int n = (kind == OM_ORDER_HAUL) ? D : L;
+        int base = (kind == OM_ORDER_HAUL) ? L : 0;
+        uint32_t v = 0xFFFFFFFFu;
+        if (lane < n) {
+          int site = base + lane;
+          uint32_t coming = (uint32_t)U16A(s_coming, site) - ((U8A(t_tgt, i) == 1 + site) ? 1u : 0u);
+          v = ((coming + (uint32_t)U16A(s_qtotal, site)) << 8) | (uint32_t)lane;
+        }
+        r = (int)(__reduce_min_sync(OM_FULL, v) & 0xFFu);
+        break;
+      }
+      default:
+        fail(OM_IERR_BAD_ORDER);
+        return -1;
+    }
+    return r;
+  }
+
+  __device__ __forceinline__ void set_target(int i, int tgt) {
+    int old = U8A(t_tgt, i);
+    if (old != OM_NOLOC && old != 0) U16A(s_coming, old - 1) = (uint16_t)(U16A(s_coming, old - 1) - 1);
+    U16A(s_coming, tgt - 1) = (uint16_t)(U16A(s_coming, tgt - 1) + 1);
+    U8A(t_tgt, i) = (uint8_t)tgt;
+  }
+
+  // wrapper bookkeeping (dispatcher.py:35-89): order counts; SPTF back orders are logged twice
+  __device__ __forceinline__ void count_order(int kind, int site) {
+    n_decisions++;
+    n_orders += (disp == OM_DISP_SPTF && kind == OM_ORDER_BACK) ? 2u : 1u;
+    log_order(kind, site);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // truck transitions
+  // ---------------------------------------------------------------------------------------------
+  // after an order has been decided: truck.py:303-317 (init), 390-402 (haul), 442-453 (back)
+  __device__ __forceinline__ void apply_order(int i, int kind, int site) {
+    const int L = c.L, D = c.D;
+    int nmax = (kind == OM_ORDER_HAUL) ? D : L;
+    if (site < 0 || site >= nmax) { fail(OM_IERR_BAD_ORDER); return; }
+    uint32_t epoch = U16A(t_epoch, i);
+    count_order(kind, site);
+    U16A(t_epoch, i) = (uint16_t)(epoch + 1);
+    double dist;
+    int tgt;
+    if (kind == OM_ORDER_INIT) {
+      U8A(t_status, i) = ST_MOVING;
+      tgt = 1 + site;
+      dist = __ldg(&c.rdist[site]);      // charging_to_load[site]; no road events on this leg (truck.py:308)
+      set_target(i, tgt);
+      emit(K_INIT_ORDER, (uint32_t)i, (uint32_t)site, 0, dist, 0.0);
+    } else if (kind == OM_ORDER_HAUL) {
+      tgt = 1 + L + site;
+      dist = get_distance(i, U8A(t_cur, i), tgt, epoch);
+      set_target(i, tgt);
+      emit(K_ORDER_HAUL, (uint32_t)i, (uint32_t)site, 0, dist, 0.0);
+    } else {
+      tgt = 1 + site;
+      dist = get_distance(i, U8A(t_cur, i), tgt, epoch);
+      set_target(i, tgt);
+      emit(K_ORDER_BACK, (uint32_t)i, (uint32_t)site, 0, dist, 0.0);
+    }
+    F64(t_dist, i) = dist;
+    sched_truck(i, now, 0u, PH_MOVE_BEGIN);   // env.process(move) -> Initialize URGENT
+  }
+
+  // ask for an order; with an external dispatcher the instance pauses here
+  __device__ __forceinline__ bool order(int i, int kind, int* pend_truck, int* pend_kind) {
+    if (disp == OM_DISP_EXTERNAL) {
+      U8A(t_phase, i) = PH_AWAIT_ORDER;
+      F64(t_time, i) = om_inf();
+      U32A(t_key, i) = OM_KEY_SENTINEL;
+      *pend_truck = i; *pend_kind = kind;
+      return false;
+    }
+    int site = decide(kind, i);
+    if (site < 0) return true;
+    apply_order(i, kind, site);
+    return true;
+  }
+
+  // move(): jam scan + departure (truck.py:151-210)
+  __device__ __forceinline__ void move_depart(int i, bool dead) {
+    int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
+    double dist = F64(t_dist, i);
+    double duration = (dist / __ldg(&c.speed[i])) * 60.0;
+    double pre = 0.0;
+    if (RNG != OM_RNG_DET && jam_count > 0) {
+      int rid = road_id(cur, tgt);
+      for (uint32_t base = 0; base < jam_count; base += 32) {
+        uint32_t j = base + lane;
+        bool hit = false;
+        if (j < jam_count)
+          hit = (U16A(j_road, j) == rid) && (F64(j_start, j) <= now) && (F64(j_end, j) >= now);
+        unsigned m = __ballot_sync(OM_FULL, hit);
+        while (m) {
+          int b = __ffs(m) - 1;
+          m &= m - 1;
+          double y = (F64(j_end, base + b) - now) - F64(j_pos, base + b) * duration;
+          pre += (y > 0.0) ? y : 0.0;        // max(0, jam_time - time_to_jam)
+        }
+      }
+      F64(t_prejam, i) = pre;
+    }
+    if (dead) {
+      n_unrep++;
+      emit(K_UNREPAIRABLE, (uint32_t)i, 0, 0, 0.0, 0.0);
+      U8A(t_status, i) = ST_UNREPAIRABLE;
+      U8A(t_phase, i) = PH_DEAD;
+      F64(t_time, i) = om_inf();
+      U32A(t_key, i) = OM_KEY_SENTINEL;
+      return;
+    }
+    uint8_t kind = (cur > c.L) ? K_MOVE_UNHAUL : (cur == 0 ? K_MOVE_INIT : K_MOVE_HAUL);
+    int idx = (tgt <= c.L) ? tgt - 1 : tgt - 1 - c.L;
+    emit(kind, (uint32_t)i, (uint32_t)idx, 0, now + duration + pre, dist);
+    U8A(t_status, i) = ST_MOVING;
+    sched_truck(i, now + (duration + pre), OM_KEY_NORMAL, PH_MOVE_ARRIVE);
+  }
+
+  __device__ __forceinline__ bool after_load(int i, int u, int* pt, int* pk) {
+    release(u);
+    U8A(t_status, i) = ST_WAIT_HAUL;
+    return order(i, OM_ORDER_HAUL, pt, pk);
+  }
+
+  // One truck hop.  Returns false if the instance must pause for an external decision.
+  __device__ __forceinline__ bool truck_hop(int i, int* pt, int* pk) {
+    const uint8_t ph = U8A(t_phase, i);
+    switch (ph) {
+      case PH_RUN_INIT: {
+        U8A(t_cur, i) = 0;
+        U8A(t_status, i) = ST_WAIT_INIT;
+        return order(i, OM_ORDER_INIT, pt, pk);
+      }
+      case PH_MOVE_BEGIN: {
+        F64(t_jstart, i) = now;
+        // check_vehicle_availability (truck.py:538-547)
+        bool dead = false;
+        if (RNG != OM_RNG_DET) {
+          double g = draw_exp(OM_S_UNREPAIRABLE, U16A(t_epoch, i), (uint32_t)i, c.unrepairable_mean);
+          dead = now >= g;
+        }
+        double rep = F64(t_repair, i);
+        if (!dead && rep != 0.0) {
+          n_brk++;
+          emit(K_BREAKDOWN, (uint32_t)i, 0, 0, F64(t_lastbrk, i), rep);
+          U8A(t_status, i) = ST_REPAIRING;
+          sched_truck(i, now + rep, OM_KEY_NORMAL, PH_MOVE_REPAIRED);
+        } else {
+          move_depart(i, dead);
+        }
+        return true;
+      }
+      case PH_MOVE_REPAIRED: {
+        F64(t_repair, i) = 0.0;
+        U8A(t_status, i) = ST_MOVING;
+        move_depart(i, false);
+        return true;
+      }
+      case PH_MOVE_ARRIVE: {
+        U8A(t_cur, i) = U8A(t_tgt, i);
+        F64(t_prejam, i) = 0.0;
+        sched_truck(i, now, OM_KEY_NORMAL, PH_MOVE_RET);
+        return true;
+      }
+      case PH_MOVE_RET: {
+        int cur = U8A(t_cur, i);
+        int u = pick_unit(cur - 1);
+        int qi = request(u, i);
+        if (cur <= c.L) {
+          emit(K_WAIT_SHOVEL, (uint32_t)i, (uint32_t)u, (uint32_t)qi, 0.0, 0.0);
+          U8A(t_status, i) = ST_WAIT_SHOVEL;
+        } else {
+          emit(K_WAIT_DUMPER, (uint32_t)i, (uint32_t)(u - c.S), 0, 0.0, 0.0);
+          U8A(t_status, i) = ST_WAIT_DUMPER;
+        }
+        return true;
+      }
+      case PH_LOAD_GRANTED: {
+        emit(K_GET_SHOVEL, (uint32_t)i, (uint32_t)U16A(t_unit, i), 0, 0.0, 0.0);
+        sched_truck(i, now, 0u, PH_LOAD_BEGIN);
+        return true;
+      }
+      case PH_LOAD_BEGIN: {
+        int u = U16A(t_unit, i);
+        U8A(t_status, i) = ST_LOADING;
+        F64(u_last_start, u) = now;
+        double lt = __ldg(&c.load_time[__ldg(&c.ttype[i]) * c.S + u]);
+        sched_truck(i, now + lt, OM_KEY_NORMAL, PH_LOAD_DONE);
+        return true;
+      }
+      case PH_LOAD_DONE: {
+        int u = U16A(t_unit, i);
+        double load = __ldg(&c.cap[i]) * (1.0 + draw_jitter(U16A(t_epoch, i), (uint32_t)i));
+        F64(t_load, i) = load;
+        F64(u_tons, u) = F64(u_tons, u) + load;
+        U32A(u_svc, u) = U32A(u_svc, u) + 1;
+        F64(u_last_done, u) = now;
+        sched_truck(i, now, OM_KEY_NORMAL, PH_LOAD_RET);
+        return true;
+      }
+      case PH_LOAD_RET: {
+        int u = U16A(t_unit, i);
+        if (RNG != OM_RNG_DET) {
+          double gap = draw_exp(OM_S_MAINT_GAP, U16A(t_epoch, i), (uint32_t)i, c.maint_mean);
+          if (now >= F64(u_lastbrk, u) + gap) {
+            U8A(u_repair, u) = 1;
+            double d = draw_normal(OM_S_MAINT_DUR, U16A(t_epoch, i), (uint32_t)i, c.maint_mu, c.maint_sigma);
+            double dur = (0.0 > d) ? 0.0 : d;    // max(x, 0)
+            emit(K_SHOVEL_MAINT_START, (uint32_t)i, (uint32_t)u, 0, now + dur, 0.0);
+            sched_truck(i, now + dur, OM_KEY_NORMAL, PH_MAINT_DONE);
+            return true;
+          }
+        }
+        return after_load(i, u, pt, pk);
+      }
+      case PH_MAINT_DONE: {
+        int u = U16A(t_unit, i);
+        emit(K_SHOVEL_MAINT_DONE, (uint32_t)i, (uint32_t)u, 0, 0.0, 0.0);
+        F64(u_lastbrk, u) = now;
+        return after_load(i, u, pt, pk);
+      }
+      case PH_DUMP_GRANTED: {
+        emit(K_GET_DUMPER, (uint32_t)i, (uint32_t)(U16A(t_unit, i) - c.S), 0, 0.0, 0.0);
+        sched_truck(i, now, 0u, PH_DUMP_BEGIN);
+        return true;
+      }
+      case PH_DUMP_BEGIN: {
+        int u = U16A(t_unit, i);
+        U8A(t_status, i) = ST_UNLOADING;
+        F64(u_last_start, u) = now;
+        sched_truck(i, now + __ldg(&c.dcycle[u - c.S]), OM_KEY_NORMAL, PH_DUMP_DONE);
+        return true;
+      }
+      case PH_DUMP_DONE: {
+        int u = U16A(t_unit, i);
+        double load = F64(t_load, i);
+        F64(u_tons, u) = F64(u_tons, u) + load;
+        F64(t_total, i) = F64(t_total, i) + load;
+        uint32_t sc = (uint32_t)U16A(t_svc, i) + 1;
+        U16A(t_svc, i) = (uint16_t)sc;
+        F64(t_cycle, i) = (now - 0.0) / (double)sc;     // first_order_time is always 0 (truck.py:304)
+        F64(t_load, i) = 0.0;
+        U32A(u_svc, u) = U32A(u_svc, u) + 1;
+        F64(u_last_done, u) = now;
+        sched_truck(i, now, OM_KEY_NORMAL, PH_DUMP_RET);
+        return true;
+      }
+      case PH_DUMP_RET: {
+        release(U16A(t_unit, i));
+        U8A(t_status, i) = ST_WAIT_BACK;
+        return order(i, OM_ORDER_BACK, pt, pk);
+      }
+      default:
+        return true;
+    }
+  }
+
+  // Release event popped: hand the unit to the queue head (Resource._trigger_put)
+  __device__ __forceinline__ void unit_hop(int u) {
+    F64(u_rel_time, u) = om_inf();
+    U32A(u_rel_key, u) = OM_KEY_SENTINEL;
+    if (U16A(u_user, u) == OM_NONE16 && U16A(u_qlen, u) > 0) grant_head(u);
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // jam pool
+  // ---------------------------------------------------------------------------------------------
+  __device__ __forceinline__ void jam_append(int rid, double pos, double end) {
+    if (jam_count == (uint32_t)c.J) {   // drop expired entries, keep creation order
+      uint32_t w = 0;
+      for (uint32_t j = 0; j < jam_count; ++j) {
+        if (F64(j_end, j) >= now) {
+          if (w != j) {
+            F64(j_pos, w) = F64(j_pos, j); F64(j_start, w) = F64(j_start, j);
+            F64(j_end, w) = F64(j_end, j); U16A(j_road, w) = U16A(j_road, j);
+          }
+          w++;
+        }
+      }
+      jam_count = w;
+    }
+    if (jam_count == (uint32_t)c.J) { fail(OM_IERR_JAM_OVERFLOW); return; }
+    F64(j_pos, jam_count) = pos; F64(j_start, jam_count) = now; F64(j_end, jam_count) = end;
+    U16A(j_road, jam_count) = (uint16_t)rid;
+    jam_count++;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // the per-minute monitor block (mine.py:50-155 + site monitors), atomic
+  // ---------------------------------------------------------------------------------------------
+  __device__ __forceinline__ void tick_block() {
+    const int T = c.T, L = c.L, D = c.D, NS = c.NS;
+    const int k = (int)now;
+    const bool neu = c.sum_mode != 0;
+    // (1) queue totals per site (load_site.py:81-83) and site tons (load_site.py:175, dump_site.py:69)
+    double site_tons = 0.0;
+    uint32_t qtot = 0, site_svc = 0;
+    if (lane < NS) {
+      int ub = __ldg(&c.ubeg[lane]), ue = __ldg(&c.ubeg[lane + 1]);
+      PySum ps; ps.init();
+      for (int u = ub; u < ue; ++u) {
+        qtot += U16A(u_qlen, u);
+        ps.add(F64(u_tons, u), neu);
+        site_svc += U32A(u_svc, u);
+      }
+      site_tons = ps.result();
+      U16A(s_qtotal, lane) = (uint16_t)qtot;
+    }
+    tick_k = k;
+    // (2) mine KPI sample (mine.py:61-119)
+    PySum pm; pm.init();
+    int svc_total = 0;
+    for (int j = 0; j < D; ++j) {
+      pm.add(__shfl_sync(OM_FULL, site_tons, L + j), neu);
+      svc_total += (int)__shfl_sync(OM_FULL, site_svc, L + j);
+    }
+    double produce = pm.result();
+    reported_tons = produce;
+    uint32_t n_work = 0, n_wait = 0, n_lu = 0, n_mov = 0, n_rep = 0;
+    for (int base = 0; base < T; base += 32) {
+      int i = base + lane;
+      uint8_t st = (i < T) ? U8A(t_status, i) : (uint8_t)0xFF;
+      bool valid = i < T;
+      n_work += __popc(__ballot_sync(OM_FULL, valid && st != ST_UNREPAIRABLE));
+      n_wait += __popc(__ballot_sync(OM_FULL, st == ST_WAIT_INIT || st == ST_WAIT_SHOVEL || st == ST_WAIT_HAUL ||
+                                                   st == ST_WAIT_DUMPER || st == ST_WAIT_BACK));
+      n_lu += __popc(__ballot_sync(OM_FULL, st == ST_LOADING || st == ST_UNLOADING));
+      n_mov += __popc(__ballot_sync(OM_FULL, st == ST_MOVING));
+      n_rep += __popc(__ballot_sync(OM_FULL, st == ST_REPAIRING));
+    }
+    if (out.ticks != nullptr && k < out.tick_capacity) {
+      if (lane == 0) {
+        OmTickRecord r;
+        r.produced_tons = produce; r.service_count = svc_total;
+        r.working = (uint16_t)n_work; r.waiting = (uint16_t)n_wait; r.load_unload = (uint16_t)n_lu;
+        r.moving = (uint16_t)n_mov; r.repairing = (uint16_t)n_rep;
+        r.n_jams = (uint16_t)n_jams; r.n_road_repairs = (uint16_t)n_road_rep;
+        r.n_truck_repairs = (uint16_t)n_brk; r.n_unrepairable = (uint16_t)n_unrep; r.pad = 0;
+        out.ticks[inst * (long long)out.tick_capacity + k] = r;
+      }
+      if (lane < NS) {
+        long long o = (inst * (long long)out.tick_capacity + k) * NS + lane;
+        if (out.site_queue_ticks != nullptr) out.site_queue_ticks[o] = (uint16_t)qtot;
+        if (out.site_tons_ticks != nullptr) out.site_tons_ticks[o] = site_tons;
+      }
+    }
+    n_ticks++;
+    if (RNG != OM_RNG_DET) {
+      // (3) truck breakdown sampling (truck.py:522-536), every truck every minute, truck order
+      if (RNG == OM_RNG_TAPE) {
+        for (int i = 0; i < T; ++i) {
+          double gap = tape_next(OM_S_BREAK_GAP);
+          if (now >= F64(t_lastbrk, i) + gap) {
+            double d = tape_next(OM_S_BREAK_DUR);
+            F64(t_repair, i) = (0.0 > d) ? 0.0 : d;
+            F64(t_lastbrk, i) = now;
+          }
+        }
+      } else {
+        for (int i = lane; i < T; i += 32) {
+          Philox4 r = px((uint32_t)k, (uint32_t)i, OM_S_BREAK_GAP);
+          double gap = (double)om_exp1(r.x) * c.breakdown_mean;
+          if (now >= F64(t_lastbrk, i) + gap) {
+            double d = c.repair_mu + c.repair_sigma * (double)om_normal(r.y, r.z);
+            F64(t_repair, i) = (0.0 > d) ? 0.0 : d;
+            F64(t_lastbrk, i) = now;
+          }
+        }
+        __syncwarp();
+      }
+      // (4) jam sampling per road in monitor order (mine.py:138-154, road.py:137-233)
+      if (now >= 2.0) jam_sampling(k);
+    }
+    // re-arm: every monitor generator does `yield env.timeout(1)`; the block's eids are contiguous
+    tick_time = now + 1.0;
+    tick_key = OM_KEY_NORMAL | seq;
+    seq++;
+  }
+
+  __device__ __forceinline__ void jam_sampling(int k) {
+    const int T = c.T, R = c.R;
+    uint32_t* rcnt = (uint32_t*)(sm + ly.scratch);   // scratch is sized >= max(U, R/2 + 1, 32) doubles
+    for (int r = lane; r < R; r += 32) rcnt[r] = 0;
+    __syncwarp();
+    for (int i = lane; i < T; i += 32) {
+      int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
+      if (U8A(t_status, i) == ST_MOVING && cur != tgt) atomicAdd(&rcnt[road_id(cur, tgt)], 1u);
+    }
+    __syncwarp();
+    for (int base = 0; base < R; base += 32) {
+      int r = base + lane;
+      uint32_t n_on = (r < R) ? rcnt[r] : 0u;
+      unsigned m = __ballot_sync(OM_FULL, n_on >= 2u);
+      while (m) {
+        int b = __ffs(m) - 1;
+        m &= m - 1;
+        int rid = base + b;
+        uint32_t n = __shfl_sync(OM_FULL, n_on, b);
+        double chance = __ldg(&c.jam_chance[n]);
+        double coin, pos = 0.0, dur;
+        Philox4 rr;
+        if (RNG == OM_RNG_TAPE) {
+          coin = tape_next(OM_S_JAM_COIN);
+        } else {
+          rr = px((uint32_t)k, (uint32_t)rid, OM_S_JAM_COIN);
+          coin = (double)((float)(rr.x >> 8) * 5.9604644775390625e-08f);   // [0,1)
+        }
+        if (coin >= chance) continue;
+        if (RNG == OM_RNG_TAPE) {
+          pos = tape_next(OM_S_JAM_POS);
+          dur = tape_next(OM_S_JAM_DUR) * c.jam_scale;
+        } else {
+          pos = sample_jam_position(k, rid, rr.y);
+          dur = (double)sqrtf(om_exp1(rr.z)) * c.jam_scale;                // Weibull(shape 2) * scale
+        }
+        double end = now + dur;
+        jam_append(rid, pos, end);
+        n_jams++;
+        emit(K_JAM, 0xFFFFu, (uint32_t)rid, 0, pos, end);
+      }
+    }
+    __syncwarp();
+  }
+
+  // Position of a new jam on road `rid`: the reference draws an index on linspace(0,1,1000) with
+  // p ~ sum_i N(x; coverage_i, sd) (road.py:185-206).  Equivalent two-stage sampler: pick truck i with
+  // probability ~ its grid mass Phi((1+h/2-c_i)/sd) - Phi((-h/2-c_i)/sd), then draw x ~ N(c_i, sd)
+  // truncated to [-h/2, 1+h/2] and round to the grid (mid-point rule; relative error O((h/sd)^2/24)).
+  __device__ __forceinline__ double sample_jam_position(int k, int rid, uint32_t upick) {
+    const int T = c.T;
+    const float sd = (float)c.jam_sd, h = 1.0f / 999.0f;
+    const double base_dist = __ldg(&c.rdist[rid]);
+    float zsum = 0.0f;
+    // pass 1: per-lane mass
+    for (int i = lane; i < T; i += 32) {
+      int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
+      if (U8A(t_status, i) == ST_MOVING && cur != tgt && road_id(cur, tgt) == rid) {
+        float cv = coverage(i, base_dist);
+        zsum += normcdff((1.0f + 0.5f * h - cv) / sd) - normcdff((-0.5f * h - cv) / sd);
+      }
+    }
+    float incl = zsum;
+    for (int o = 1; o < 32; o <<= 1) {
+      float v = __shfl_up_sync(OM_FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    float total = __shfl_sync(OM_FULL, incl, 31);
+    float target = om_u01(upick) * total;
+    unsigned m = __ballot_sync(OM_FULL, incl >= target && zsum > 0.0f);
+    int owner = m ? (__ffs(m) - 1) : 31;
+    float cpick = 0.5f;
+    if (lane == owner) {
+      float acc = incl - zsum;
+      for (int i = lane; i < T; i += 32) {
+        int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
+        if (U8A(t_status, i) == ST_MOVING && cur != tgt && road_id(cur, tgt) == rid) {
+          float cv = coverage(i, base_dist);
+          cpick = cv;
+          acc += normcdff((1.0f + 0.5f * h - cv) / sd) - normcdff((-0.5f * h - cv) / sd);
+          if (acc >= target) break;
+        }
+      }
+    }
+    cpick = __shfl_sync(OM_FULL, cpick, owner);
+    float x = cpick;
+    for (uint32_t it = 0; it < 64; ++it) {   // rejection on the truncation window (acceptance >= 1/2)
+      Philox4 r = px((uint32_t)k, (uint32_t)rid, OM_S_JAM_POS, it);
+      float x0 = cpick + sd * om_normal(r.x, r.y);
+      float x1 = cpick + sd * om_normal(r.z, r.w);
+      bool ok0 = x0 >= -0.5f * h && x0 <= 1.0f + 0.5f * h;
+      bool ok1 = x1 >= -0.5f * h && x1 <= 1.0f + 0.5f * h;
+      if (ok0 || ok1) { x = ok0 ? x0 : x1; break; }
+    }
+    int idx = __float2int_rn(x * 999.0f);
+    idx = idx < 0 ? 0 : (idx > 999 ? 999 : idx);
+    return (double)idx * (1.0 / 999.0);       // np.linspace(0, 1, 1000)[idx]
+  }
+
+  // Truck.get_route_coverage (truck.py:496-520)
+  __device__ __forceinline__ float coverage(int i, double base_dist) {
+    double total = (base_dist / __ldg(&c.speed[i])) * 60.0 + F64(t_prejam, i) + F64(t_repair, i);
+    double cov = (now - F64(t_jstart, i)) / total;
+    if (cov > 1.0) cov = 1.0;
+    return (float)cov;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // main loop: pop (time, key)-minimum entry until `until` (env.run(until), mine.py:391)
+  // ---------------------------------------------------------------------------------------------
+  __device__ __forceinline__ void run(double until) {
+    const int T = c.T, U = c.U;
+    int pend_truck = -1, pend_kind = -1;
+    while (true) {
+      // lane-local minimum over this lane's trucks and units
+      double bt = om_inf();
+      uint32_t bk = OM_KEY_SENTINEL;
+      int bid = -1;
+      for (int i = lane; i < T; i += 32) {
+        double t = F64(t_time, i);
+        uint32_t kk = U32A(t_key, i);
+        if (t < bt || (t == bt && kk < bk)) { bt = t; bk = kk; bid = i; }
+      }
+      for (int u = lane; u < U; u += 32) {
+        double t = F64(u_rel_time, u);
+        uint32_t kk = U32A(u_rel_key, u);
+        if (t < bt || (t == bt && kk < bk)) { bt = t; bk = kk; bid = T + u; }
+      }
+      // warp minimum of the 96-bit key (times are >= 0, so their bit patterns order as unsigned)
+      uint32_t hi = (uint32_t)__double2hiint(bt), lo = (uint32_t)__double2loint(bt);
+      uint32_t mhi = __reduce_min_sync(OM_FULL, hi);
+      uint32_t mlo = __reduce_min_sync(OM_FULL, (hi == mhi) ? lo : 0xFFFFFFFFu);
+      bool cand = (hi == mhi) && (lo == mlo);
+      uint32_t mk = __reduce_min_sync(OM_FULL, cand ? bk : OM_KEY_SENTINEL);
+      unsigned ball = __ballot_sync(OM_FULL, cand && bk == mk);
+      int id = __shfl_sync(OM_FULL, bid, __ffs(ball) - 1);
+      double tmin = __hiloint2double((int)mhi, (int)mlo);
+      bool is_tick = (tick_time < tmin) || (tick_time == tmin && tick_key < mk);
+      if (is_tick) tmin = tick_time;
+      if (!(tmin < until) || (err != OM_IERR_NONE && err != OM_IERR_TRACE_OVERFLOW)) break;
+      now = tmin;
+      n_hops++;
+      if (is_tick) {
+        tick_block();
+      } else if (id < T) {
+        if (!truck_hop(id, &pend_truck, &pend_kind)) break;
+      } else {
+        unit_hop(id - T);
+      }
+    }
+    InstHdr* h = (InstHdr*)(sm + ly.hdr);
+    h->pending_truck = pend_truck;
+    h->pending_kind = pend_kind;
+  }
+
+  // dumped tons at the stop time (sum of dumper tons, plain left-to-right)
+  __device__ __forceinline__ double dumped_tons() {
+    double s = 0.0;
+    for (int u = c.S; u < c.U; ++u) s += F64(u_tons, u);
+    return s;
+  }
+};
+
+// Initial state of one instance at t=0 (Mine.__init__/Truck.__init__/registration order of mine.py:357-389):
+// the monitor block's Initialize events are URGENT at 0 with the smallest eids, then one URGENT
+// Initialize(run) per truck in index order.
+__device__ __forceinline__ void om_init_state(unsigned char* sm, const DevCfg& c, const OmStateLayout& ly, int lane,
+                                              uint64_t seed, int dispatcher) {
+  const double inf = om_inf();
+  // zero everything first
+  for (uint32_t o = lane * 8; o < ly.total_bytes; o += 256) *(unsigned long long*)(sm + o) = 0ull;
+  __syncwarp();
+  for (int i = lane; i < c.T; i += 32) {
+    F64(t_time, i) = 0.0;
+    U32A(t_key, i) = (uint32_t)(1 + i);          // URGENT, after the monitors
+    U8A(t_phase, i) = PH_RUN_INIT;
+    U8A(t_status, i) = ST_IDLE;
+    U8A(t_cur, i) = OM_NOLOC;
+    U8A(t_tgt, i) = OM_NOLOC;
+    U16A(t_next, i) = OM_NONE16;
+    U16A(t_unit, i) = OM_NONE16;
+  }
+  for (int u = lane; u < c.U; u += 32) {
+    F64(u_rel_time, u) = inf;
+    U32A(u_rel_key, u) = OM_KEY_SENTINEL;
+    U16A(u_user, u) = OM_NONE16;
+    U16A(u_head, u) = OM_NONE16;
+    U16A(u_tail, u) = OM_NONE16;
+  }
+  if (lane == 0) {
+    InstHdr* h = (InstHdr*)(sm + ly.hdr);
+    h->now = 0.0;
+    h->tick_time = 0.0;
+    h->tick_key = 0u;                            // URGENT, eid 0
+    h->tick_k = -1;
+    h->seq = (uint32_t)(1 + c.T);
+    h->seed = seed;
+    h->dispatcher = dispatcher;
+    h->pending_truck = -1;
+    h->pending_kind = -1;
+  }
+  __syncwarp();
+}

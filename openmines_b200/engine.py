@@ -1,0 +1,235 @@
+"""``BatchedMine``: host-side driver of the device engine through the C ABI.
+
+It plays the role of ``Mine`` + ``run_dispatch_sim`` (reference mine.py:340-395, cli/run.py:48-112)
+for N independent mine instances at once.  PyTorch is used only to own device memory and
+streams; every simulation step runs in the hand-written CUDA kernels of
+``libopenmines_b200.so`` (there is no CPU or PyTorch fallback).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .config import PackedConfig, pack_config
+from .trace import SUMMARY_DTYPE, TICK_DTYPE, TRACE_DTYPE
+
+RNG_MODES = {"det": 0, "philox": 1, "tape": 2}
+
+DISPATCHER_IDS = {
+    "NaiveDispatcher": 0, "RandomDispatcher": 1, "NearestDispatcher": 2, "FixedGroupDispatcher": 3,
+    "SPTFDispatcher": 4, "SQDispatcher": 5, "external": 255,
+}
+
+
+class OmOutputsStruct(ctypes.Structure):
+    _fields_ = [("summary", ctypes.c_void_p), ("ticks", ctypes.c_void_p), ("tick_capacity", ctypes.c_int32),
+                ("trace_capacity", ctypes.c_int32), ("trace", ctypes.c_void_p), ("site_queue_ticks", ctypes.c_void_p),
+                ("site_tons_ticks", ctypes.c_void_p), ("orders", ctypes.c_void_p), ("order_capacity", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
+_LAYOUT_FIELDS = ["total_bytes", "hdr", "t_time", "t_load", "t_jstart", "t_prejam", "t_lastbrk", "t_repair",
+                  "t_total", "t_cycle", "t_dist", "t_key", "t_svc", "t_epoch", "t_next", "t_unit", "t_phase",
+                  "t_status", "t_cur", "t_tgt", "u_rel_time", "u_last_start", "u_last_done", "u_tons", "u_lastbrk",
+                  "u_rel_key", "u_svc", "u_user", "u_head", "u_tail", "u_qlen", "u_repair", "r_repair_end",
+                  "j_pos", "j_start", "j_end", "j_road", "s_qtotal", "s_coming", "scratch"]
+
+
+class OmStateLayoutStruct(ctypes.Structure):
+    _fields_ = [(f, ctypes.c_uint32) for f in _LAYOUT_FIELDS]
+
+
+def _dispatcher_id(d):
+    if isinstance(d, (int, np.integer)):
+        return int(d)
+    if isinstance(d, str):
+        return DISPATCHER_IDS[d]
+    dev = getattr(d, "device_id", None)      # openmines_b200.dispatcher.BaseDispatcher subclasses
+    if dev is not None:
+        return int(dev)
+    name = getattr(d, "name", d.__class__.__name__)
+    if name in DISPATCHER_IDS:
+        return DISPATCHER_IDS[name]
+    raise ValueError("dispatcher %r has no device implementation; use the external-decision mode" % (d,))
+
+
+class RunResult:
+    """Device tensors produced by one ``BatchedMine.run`` call (numpy views via the helpers)."""
+
+    def __init__(self):
+        self.summary = self.ticks = self.trace = self.site_queue_ticks = self.site_tons_ticks = self.orders = None
+        self.tick_capacity = self.trace_capacity = self.order_capacity = 0
+
+    def summary_np(self):
+        return self.summary.cpu().numpy().view(SUMMARY_DTYPE).reshape(-1)
+
+    def ticks_np(self):
+        return self.ticks.cpu().numpy().view(TICK_DTYPE).reshape(-1, self.tick_capacity)
+
+    def trace_np(self, inst):
+        s = self.summary_np()
+        tr = self.trace[inst].cpu().numpy().view(TRACE_DTYPE).reshape(-1)
+        return tr, s[inst]
+
+    def orders_np(self):
+        return self.orders.cpu().numpy()
+
+
+class BatchedMine:
+    """N independent instances of one mine config on one GPU."""
+
+    def __init__(self, config, n_instances, device=0, jam_capacity=64, sum_mode="neumaier"):
+        import torch
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("openmines_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.pc = config if isinstance(config, PackedConfig) else pack_config(config, jam_capacity, sum_mode)
+        self.n = int(n_instances)
+        self.device = torch.device("cuda", device)
+        self._cstruct = self.pc.c_struct()
+        h = ctypes.c_void_p()
+        rc = self.lib.om_create(ctypes.byref(self._cstruct), self.n, device, ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError("om_create failed (%d): %s" % (rc, self.lib.om_last_error(None).decode()))
+        self.h = h
+        sb = ctypes.c_size_t()
+        self._ck(self.lib.om_state_bytes(self.h, ctypes.byref(sb)))
+        self.state_bytes = int(sb.value)
+        self.layout = OmStateLayoutStruct()
+        self._ck(self.lib.om_state_layout(self.h, ctypes.byref(self.layout)))
+        self.state = torch.empty((self.n, self.state_bytes), dtype=torch.uint8, device=self.device)
+        self.dispatcher_ids = None
+        self.seeds = None
+        self._tape = None
+        self.sim_time = self.pc.sim_time
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError("openmines_b200 call failed (%d): %s" % (rc, self.lib.om_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.om_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launch_info(self):
+        g, b, s, w = (ctypes.c_int32() for _ in range(4))
+        self._ck(self.lib.om_launch_info(self.h, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s), ctypes.byref(w)))
+        return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "warps_per_cta": w.value}
+
+    # ------------------------------------------------------------------------------------------
+    def reset(self, dispatchers, seeds=None, rng_mode="philox", tapes=None):
+        """Write the t=0 state of every instance.
+
+        dispatchers: one dispatcher (name / id / BaseDispatcher object) or a sequence of N of them.
+        seeds:       uint64 per instance (default: instance index).
+        tapes:       for rng_mode="tape": list of N (sites uint8[], values float64[]) tuples.
+        """
+        torch = self.torch
+        if isinstance(dispatchers, (str, int, np.integer)) or not hasattr(dispatchers, "__len__"):
+            ids = np.full(self.n, _dispatcher_id(dispatchers), dtype=np.int32)
+        elif isinstance(dispatchers, np.ndarray) and dispatchers.dtype.kind in "iu":
+            ids = dispatchers.astype(np.int32)
+        else:
+            ids = np.array([_dispatcher_id(d) for d in dispatchers], dtype=np.int32)
+        assert ids.shape == (self.n,)
+        if seeds is None:
+            seeds = np.arange(self.n, dtype=np.uint64)
+        seeds = np.asarray(seeds, dtype=np.uint64)
+        assert seeds.shape == (self.n,)
+        self.dispatcher_ids = torch.from_numpy(ids).to(self.device)
+        self.seeds = torch.from_numpy(seeds.view(np.int64)).to(self.device)
+        mode = RNG_MODES[rng_mode]
+        tv = ts = to = None
+        if mode == 2:
+            assert tapes is not None and len(tapes) == self.n
+            offs = np.zeros(self.n + 1, dtype=np.int64)
+            for i, (s, v) in enumerate(tapes):
+                offs[i + 1] = offs[i] + len(v)
+            sites = np.concatenate([np.asarray(s, dtype=np.uint8) for s, _ in tapes]) if offs[-1] else np.zeros(1, np.uint8)
+            vals = np.concatenate([np.asarray(v, dtype=np.float64) for _, v in tapes]) if offs[-1] else np.zeros(1)
+            tv = torch.from_numpy(vals).to(self.device)
+            ts = torch.from_numpy(sites).to(self.device)
+            to = torch.from_numpy(offs).to(self.device)
+            self._tape = (tv, ts, to)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        self._ck(self.lib.om_reset(self.h, ptr(self.seeds), ptr(self.dispatcher_ids), mode, ptr(tv), ptr(ts), ptr(to),
+                                   ptr(self.state), self._stream()))
+        return self
+
+    def run(self, until=None, ticks=True, trace_capacity=0, site_ticks=False, order_capacity=0, result=None):
+        """Advance every instance to simulated time ``until`` (default: the config's sim_time)."""
+        torch = self.torch
+        until = float(self.sim_time if until is None else until)
+        r = result if result is not None else RunResult()
+        if r.summary is None:
+            r.summary = torch.zeros((self.n, 64), dtype=torch.uint8, device=self.device)
+        tick_cap = int(np.ceil(self.sim_time)) if ticks else 0
+        ns = self.pc.L + self.pc.D
+        if ticks and r.ticks is None:
+            r.ticks = torch.zeros((self.n, tick_cap, 32), dtype=torch.uint8, device=self.device)
+            r.tick_capacity = tick_cap
+        if site_ticks and r.site_queue_ticks is None:
+            r.site_queue_ticks = torch.zeros((self.n, tick_cap, ns), dtype=torch.int16, device=self.device)
+            r.site_tons_ticks = torch.zeros((self.n, tick_cap, ns), dtype=torch.float64, device=self.device)
+        if trace_capacity and r.trace is None:
+            r.trace = torch.zeros((self.n, trace_capacity, 32), dtype=torch.uint8, device=self.device)
+            r.trace_capacity = int(trace_capacity)
+        if order_capacity and r.orders is None:
+            r.orders = torch.full((self.n, order_capacity), -1, dtype=torch.int16, device=self.device)
+            r.order_capacity = int(order_capacity)
+        o = OmOutputsStruct()
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        o.summary, o.ticks, o.trace = ptr(r.summary), ptr(r.ticks), ptr(r.trace)
+        o.tick_capacity, o.trace_capacity = r.tick_capacity, r.trace_capacity
+        o.site_queue_ticks, o.site_tons_ticks = ptr(r.site_queue_ticks), ptr(r.site_tons_ticks)
+        o.orders, o.order_capacity = ptr(r.orders), r.order_capacity
+        self._ck(self.lib.om_run(self.h, until, ctypes.c_void_p(self.state.data_ptr()), ctypes.byref(o), self._stream()))
+        return r
+
+    def stats(self, result):
+        """Per-dispatcher partial sums [6, 16] (float64 device tensor) for the cross-GPU all-reduce."""
+        torch = self.torch
+        out = torch.zeros((6, 16), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.om_stats_reduce(self.h, ctypes.c_void_p(result.summary.data_ptr()),
+                                          ctypes.c_void_p(self.dispatcher_ids.data_ptr()),
+                                          ctypes.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def state_arrays(self, inst):
+        """Decode one instance's state blob into named numpy arrays (used by the parity tests)."""
+        blob = self.state[inst].cpu().numpy()
+        ly, pc = self.layout, self.pc
+        T, U, S = pc.T, pc.S + pc.M, pc.S
+
+        def arr(field, dtype, count):
+            off = getattr(ly, field)
+            return np.frombuffer(blob.tobytes(), dtype=dtype, count=count, offset=off).copy()
+        out = {}
+        for f in ("t_time", "t_load", "t_jstart", "t_prejam", "t_lastbrk", "t_repair", "t_total", "t_cycle", "t_dist"):
+            out[f] = arr(f, np.float64, T)
+        out["t_key"] = arr("t_key", np.uint32, T)
+        for f in ("t_svc", "t_epoch", "t_next", "t_unit"):
+            out[f] = arr(f, np.uint16, T)
+        for f in ("t_phase", "t_status", "t_cur", "t_tgt"):
+            out[f] = arr(f, np.uint8, T)
+        for f in ("u_rel_time", "u_last_start", "u_last_done", "u_tons"):
+            out[f] = arr(f, np.float64, U)
+        out["u_lastbrk"] = arr("u_lastbrk", np.float64, S)
+        out["u_svc"] = arr("u_svc", np.uint32, U)
+        for f in ("u_user", "u_head", "u_tail", "u_qlen"):
+            out[f] = arr(f, np.uint16, U)
+        out["u_repair"] = arr("u_repair", np.uint8, S)
+        out["r_repair_end"] = arr("r_repair_end", np.float64, pc.R)
+        return out

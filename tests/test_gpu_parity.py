@@ -1,0 +1,120 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the oracle and the golden
+vectors recorded from the unmodified reference.  Integer / index / event-sequence work is compared
+bit-exact; fp64 times and tonnages are compared bit-exact too (tolerance 0), which is stricter
+than the 1e-9 relative bound of BASELINE.json's north_star.
+"""
+import numpy as np
+import pytest
+
+from helpers import DISPATCHERS, Golden, engine_vs_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _mine(cfg, n, **kw):
+    import openmines_b200 as om
+    return om.BatchedMine(cfg, n, **kw)
+
+
+@pytest.mark.parametrize("cfg_name", ["north_pit_mine", "north_pit_mine_short"])
+def test_det_all_dispatchers_vs_golden(cfg_name, north_pit, short_mine):
+    """det mode: event sequence, tick arrays, final tonnage bit-exact vs the reference goldens."""
+    cfg = north_pit if cfg_name == "north_pit_mine" else short_mine
+    cases = [(d, 0) for d in DISPATCHERS] + [("RandomDispatcher", 7)]
+    mine = _mine(cfg, len(cases))
+    mine.reset([d for d, _ in cases], seeds=[s for _, s in cases], rng_mode="det")
+    res = mine.run(trace_capacity=4096, site_ticks=True, order_capacity=2048)
+    for i, (d, seed) in enumerate(cases):
+        g = Golden("det_%s_%s_s%d" % (cfg_name, d, seed))
+        diffs = engine_vs_ref(g, mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s seed %d: %s" % (d, seed, diffs[:5])
+
+
+def test_tape_replay_vs_golden(north_pit):
+    """tape mode: the engine consumes the reference's recorded draws -> trajectories bit-exact."""
+    goldens = [Golden("live_north_pit_mine_%s_s11" % d) for d in DISPATCHERS]
+    mine = _mine(north_pit, len(DISPATCHERS))
+    mine.reset(DISPATCHERS, rng_mode="tape", tapes=[g.tape for g in goldens])
+    res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=2048)
+    for i, d in enumerate(DISPATCHERS):
+        diffs = engine_vs_ref(goldens[i], mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s: %s" % (d, diffs[:5])
+        s = res.summary_np()[i]
+        assert s["err"] == 0
+
+
+def test_tape_replay_short(short_mine):
+    names = ["RandomDispatcher", "SQDispatcher"]
+    goldens = [Golden("live_north_pit_mine_short_%s_s3" % d) for d in names]
+    mine = _mine(short_mine, 2)
+    mine.reset(names, rng_mode="tape", tapes=[g.tape for g in goldens])
+    res = mine.run(trace_capacity=1024, site_ticks=True, order_capacity=256)
+    for i, d in enumerate(names):
+        diffs = engine_vs_ref(goldens[i], mine, res, i)
+        assert not diffs, "%s: %s" % (d, diffs[:5])
+
+
+def test_det_vs_oracle_seeds(north_pit):
+    """det mode on seeds the goldens do not cover: RandomDispatcher (keyed Philox) vs the CPU oracle."""
+    from oracle import des_oracle as do
+    seeds = [1, 2, 3, 1000003, 2 ** 40 + 5]
+    mine = _mine(north_pit, len(seeds))
+    mine.reset("RandomDispatcher", seeds=seeds, rng_mode="det")
+    res = mine.run(trace_capacity=4096, site_ticks=True, order_capacity=2048)
+    for i, seed in enumerate(seeds):
+        o = do.run_oracle(north_pit, "RandomDispatcher", "det", seed=seed)
+        diffs = engine_vs_ref(o, mine, res, i)
+        assert not diffs, "seed %d: %s" % (seed, diffs[:5])
+
+
+def test_tape_replay_vs_oracle_fresh_seeds(north_pit):
+    """live oracle runs on fresh seeds -> tape -> engine replay, all six dispatchers."""
+    from oracle import des_oracle as do
+    cases = [(d, 100 + k) for k, d in enumerate(DISPATCHERS)]
+    oracles = [do.run_oracle(north_pit, d, "live", seed=s) for d, s in cases]
+    mine = _mine(north_pit, len(cases))
+    mine.reset([d for d, _ in cases], rng_mode="tape", tapes=[o.tape for o in oracles])
+    res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=2048)
+    for i, (d, s) in enumerate(cases):
+        diffs = engine_vs_ref(oracles[i], mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s seed %d: %s" % (d, s, diffs[:5])
+
+
+def test_c2_shape_identical_trajectories(north_pit):
+    """BASELINE config 2 property: for the five seed-independent dispatchers every seed gives the
+    identical det trajectory (same events, tons); checked on 6 x 64 instances."""
+    n_seeds = 64
+    names = [d for d in DISPATCHERS for _ in range(n_seeds)]
+    seeds = [s for _ in DISPATCHERS for s in range(n_seeds)]
+    mine = _mine(north_pit, len(names))
+    mine.reset(names, seeds=seeds, rng_mode="det")
+    res = mine.run()
+    s = res.summary_np().reshape(len(DISPATCHERS), n_seeds)
+    ticks = res.ticks_np().reshape(len(DISPATCHERS), n_seeds, -1)
+    for k, d in enumerate(DISPATCHERS):
+        assert (s[k]["err"] == 0).all()
+        if d == "RandomDispatcher":
+            assert len(np.unique(s[k]["reported_tons"])) > 8
+            continue
+        g = Golden("det_north_pit_mine_%s_s0" % d)
+        assert (s[k]["reported_tons"] == g.reported_tons).all(), d
+        assert (s[k]["n_truck_events"] == g.n_truck_events).all(), d
+        assert (ticks[k]["produced_tons"][:, :g.n_ticks] == g.tick["produced_tons"][None, :]).all(), d
+
+
+def test_resume_equals_single_run(north_pit):
+    """om_run(until=a) then om_run(until=b) == om_run(until=b): state round-trips HBM exactly."""
+    mine = _mine(north_pit, 6)
+    mine.reset(DISPATCHERS, rng_mode="philox", seeds=np.arange(6) + 50)
+    r1 = mine.run(trace_capacity=8192)
+    a = r1.summary_np().copy()
+    t1 = [r1.trace_np(i)[0].copy() for i in range(6)]
+    mine.reset(DISPATCHERS, rng_mode="philox", seeds=np.arange(6) + 50)
+    r2 = mine.run(until=77.5, trace_capacity=8192)
+    r2 = mine.run(until=150.0, result=r2)
+    r2 = mine.run(result=r2)
+    b = r2.summary_np()
+    for f in ("reported_tons", "dumped_tons", "n_truck_events", "n_decisions", "n_jams", "n_truck_repairs", "err"):
+        assert np.array_equal(a[f], b[f]), f
+    for i in range(6):
+        assert np.array_equal(t1[i], r2.trace_np(i)[0])

@@ -1,0 +1,99 @@
+"""CPU tests (no GPU) of the host side: config packer anchors, dispatcher surface, C-ABI exports."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import openmines_b200 as om
+from openmines_b200 import _lib, config as cfgmod
+
+
+def test_packer_static_anchors(north_pit):
+    """SURVEY.md Appendix D anchors, recomputed with the reference's arithmetic."""
+    pc = om.pack_config(north_pit)
+    assert (pc.T, pc.L, pc.D, pc.S, pc.M, pc.R) == (71, 5, 5, 20, 37, 55)
+    mins = (pc.road_distance[:5] / 25) * 60
+    assert list(mins) == [7.199999999999999, 10.319999999999999, 7.536000000000001, 5.4239999999999995, 5.04]
+    lt = pc.load_time.reshape(pc.n_types, pc.S)
+    assert lt[0, 0] == 34.22222222222222 and lt[0, 5] == 5.684055118110236
+    assert lt[1, 0] == 15.555555555555555 and lt[1, 5] == 2.5836614173228347
+    assert lt[2, 0] == 24.444444444444443 and lt[2, 5] == 4.060039370078741
+    assert pc.load_site_productivity == [11.25, 22.546666666666667, 18.046666666666667, 22.546666666666667,
+                                         27.093333333333334]
+    assert pc.nearest_init == 4
+    assert list(pc.nearest_haul) == [4, 4, 4, 1, 0] and list(pc.nearest_back) == [2, 2, 2, 3, 3]
+    assert list(np.bincount(pc.fixed_group)) == [6, 19, 17, 15, 14]
+    assert list(pc.site_unit_begin) == [0, 5, 10, 13, 18, 20, 25, 33, 41, 49, 57]
+    # dump j -> load i uses d2l[i][j] (road.py:314-316)
+    d2l = np.array(north_pit["road"]["d2l_road_matrix"])
+    assert pc.road_distance[5 + 25 + 4 * 5 + 0] == d2l[0][4] == 34.26
+
+
+def test_packer_rejects_duplicate_truck_names(north_pit):
+    cfg = {**north_pit, "charging_site": {**north_pit["charging_site"], "trucks": [
+        {"type": "A", "count": 2, "capacity": 10, "speed": 20}, {"type": "A", "count": 1, "capacity": 20, "speed": 20}]}}
+    with pytest.raises(NotImplementedError):
+        om.pack_config(cfg)
+
+
+def test_dispatcher_surface():
+    d = om.by_name("SQDispatcher")
+    assert isinstance(d, om.BaseDispatcher) and d.name == "SQDispatcher" and d.device_id == 5
+    assert d.total_order_count == 0 and d.init_orders == []
+    with pytest.raises(RuntimeError):
+        d.give_init_order(None, None)
+    d = om.SPTFDispatcher()
+    d.record_orders([(0 << 12) | 3, (1 << 12) | 2, (2 << 12) | 1, -1], sptf_double_log=True)
+    assert d.init_orders == [3, 1] and d.haul_orders == [2] and d.back_orders == [1] and d.total_order_count == 4
+
+    class Mine(om.BaseDispatcher):
+        pass
+    assert Mine().device_id == 255
+    with pytest.raises(NotImplementedError):
+        Mine().give_haul_order(None, None)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports what include/openmines_b200.h declares."""
+    _lib.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    header = open(os.path.join(_lib.INCLUDE, "openmines_b200.h")).read()
+    import re
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(om_[a-z_]+)\s*\(", header, re.M))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_struct_sizes_match_header():
+    from openmines_b200.engine import OmOutputsStruct, OmStateLayoutStruct
+    from openmines_b200.trace import SUMMARY_DTYPE, TICK_DTYPE, TRACE_DTYPE
+    assert ctypes.sizeof(OmOutputsStruct) == 64
+    assert ctypes.sizeof(OmStateLayoutStruct) == 4 * 40
+    assert ctypes.sizeof(cfgmod.OmConfigStruct) == 12 * 4 + 12 * 8 + 14 * 8
+    assert (TRACE_DTYPE.itemsize, TICK_DTYPE.itemsize, SUMMARY_DTYPE.itemsize) == (32, 32, 64)
+
+
+def test_create_fails_loudly_without_gpu(north_pit):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        om.BatchedMine(north_pit, 4)
+    lib = _lib.load()
+    pc = om.pack_config(north_pit)
+    s = pc.c_struct()
+    h = ctypes.c_void_p()
+    rc = lib.om_create(ctypes.byref(s), 4, 0, ctypes.byref(h))
+    assert rc == -2 and b"no CPU fallback" in lib.om_last_error(None)
+
+
+def test_product_never_imports_oracle():
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "openmines_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f

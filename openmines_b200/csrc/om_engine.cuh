@@ -1014,11 +1014,12 @@ struct Sim {
     h->pending_kind = pend_kind;
   }
 
-  // dumped tons at the stop time (sum of dumper tons, plain left-to-right)
+  // dumped tons at the stop time: sum() of the dumper tons in dumper order (same flavour as the monitors)
   __device__ __forceinline__ double dumped_tons() {
-    double s = 0.0;
-    for (int u = c.S; u < c.U; ++u) s += F64(u_tons, u);
-    return s;
+    PySum ps; ps.init();
+    const bool neu = c.sum_mode != 0;
+    for (int u = c.S; u < c.U; ++u) ps.add(F64(u_tons, u), neu);
+    return ps.result();
   }
 };
 

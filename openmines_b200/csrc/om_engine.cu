@@ -24,7 +24,7 @@ __global__ void om_reset_kernel(DevCfg c, OmStateLayout ly, unsigned char* state
   om_init_state(state + (size_t)inst * ly.total_bytes, c, ly, threadIdx.x & 31, seeds[inst], dispatcher[inst]);
 }
 
-template <int RNG>
+template <int RNG, bool TRACE>
 __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(const __grid_constant__ RunParams p) {
   extern __shared__ __align__(16) unsigned char om_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -40,10 +40,11 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
     {
       const uint4* src = (const uint4*)g;
       uint4* dst = (uint4*)sm;
+#pragma unroll 2
       for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
     }
     __syncwarp();
-    Sim<RNG> s(sm, p, lane, (long long)inst);
+    Sim<RNG, TRACE> s(sm, p, lane, (long long)inst);
     s.load_hdr(p);
     s.run(p.until);
     s.store_hdr(p);
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
     {
       uint4* dst = (uint4*)g;
       const uint4* src = (const uint4*)sm;
+#pragma unroll 2
       for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
     }
     __syncwarp();
@@ -229,9 +231,10 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
       h->warps = w; h->block = w * 32; h->smem = w * (int)h->ly.total_bytes;
       long long ctas = (n_instances + w - 1) / w;
       h->grid = (int)(ctas < sms ? ctas : sms);
-      const void* fns[3] = {(const void*)om_run_kernel<OM_RNG_DET>, (const void*)om_run_kernel<OM_RNG_PHILOX>,
-                            (const void*)om_run_kernel<OM_RNG_TAPE>};
-      for (int i = 0; i < 3 && rc == OM_OK; ++i) {
+      const void* fns[6] = {(const void*)om_run_kernel<OM_RNG_DET, false>, (const void*)om_run_kernel<OM_RNG_PHILOX, false>,
+                            (const void*)om_run_kernel<OM_RNG_TAPE, false>, (const void*)om_run_kernel<OM_RNG_DET, true>,
+                            (const void*)om_run_kernel<OM_RNG_PHILOX, true>, (const void*)om_run_kernel<OM_RNG_TAPE, true>};
+      for (int i = 0; i < 6 && rc == OM_OK; ++i) {
         e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
         if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
       }
@@ -306,11 +309,18 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
   p.counter = h->counter; p.n_instances = h->n; p.until = until;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+  const bool trace = p.out.trace != nullptr || p.out.orders != nullptr;   // event-trace / order-log variant
+#define OM_LAUNCH(MODE)                                                                     \
+  do {                                                                                      \
+    if (trace) om_run_kernel<MODE, true><<<h->grid, h->block, h->smem, st>>>(p);            \
+    else om_run_kernel<MODE, false><<<h->grid, h->block, h->smem, st>>>(p);                 \
+  } while (0)
   switch (h->rng_mode) {
-    case OM_RNG_DET: om_run_kernel<OM_RNG_DET><<<h->grid, h->block, h->smem, st>>>(p); break;
-    case OM_RNG_PHILOX: om_run_kernel<OM_RNG_PHILOX><<<h->grid, h->block, h->smem, st>>>(p); break;
-    default: om_run_kernel<OM_RNG_TAPE><<<h->grid, h->block, h->smem, st>>>(p); break;
+    case OM_RNG_DET: OM_LAUNCH(OM_RNG_DET); break;
+    case OM_RNG_PHILOX: OM_LAUNCH(OM_RNG_PHILOX); break;
+    default: OM_LAUNCH(OM_RNG_TAPE); break;
   }
+#undef OM_LAUNCH
   CK(cudaGetLastError());
   return OM_OK;
 }

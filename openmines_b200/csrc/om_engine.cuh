@@ -118,6 +118,13 @@ struct RunParams {
 
 __device__ __forceinline__ double om_inf() { return __longlong_as_double(0x7FF0000000000000LL); }
 
+// Out-of-line helpers: the hot loop must stay small enough for the instruction caches (profiles/r1_a),
+// so the 10-round Philox and the fp64 division (a ~35-instruction Newton sequence) exist once.
+__device__ __noinline__ Philox4 om_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  return philox4x32_10(c0, c1, c2, c3, k0, k1);
+}
+__device__ __noinline__ double om_ddiv(double a, double b) { return a / b; }
+
 // CPython >= 3.12 sum() step over exact floats (Neumaier), see oracle/des_oracle.py py_sum
 struct PySum {
   double s, c;
@@ -137,7 +144,7 @@ struct PySum {
   }
 };
 
-template <int RNG>
+template <int RNG, bool TRACE>
 struct Sim {
   unsigned char* sm;
   const DevCfg& c;
@@ -198,7 +205,7 @@ struct Sim {
   // ---------------------------------------------------------------------------------------------
   __device__ __forceinline__ void emit(uint8_t kind, uint32_t truck, uint32_t arg0, uint32_t arg1, double a, double b) {
     if (kind < 12) n_events++;
-    if (out.trace != nullptr) {
+    if (TRACE && out.trace != nullptr) {
       if (trace_count < (uint32_t)out.trace_capacity) {
         if (lane == 0) {
           OmTraceRecord r;
@@ -213,7 +220,7 @@ struct Sim {
     }
   }
   __device__ __forceinline__ void log_order(int kind, int site) {
-    if (out.orders != nullptr && order_count < (uint32_t)out.order_capacity && lane == 0)
+    if (TRACE && out.orders != nullptr && order_count < (uint32_t)out.order_capacity && lane == 0)
       out.orders[inst * (long long)out.order_capacity + order_count] = (int16_t)((kind << 12) | site);
     order_count++;
   }
@@ -231,7 +238,7 @@ struct Sim {
     return v;
   }
   __device__ __forceinline__ Philox4 px(uint32_t epoch, uint32_t entity, uint32_t site, uint32_t stream = 0) const {
-    return philox4x32_10(epoch, entity, site, stream, k0, k1);
+    return om_philox(epoch, entity, site, stream, k0, k1);
   }
   // exponential with mean `mean` (np.random.exponential(scale) / random.expovariate(1/mean))
   __device__ __forceinline__ double draw_exp(int site, uint32_t epoch, uint32_t entity, double mean) {
@@ -283,25 +290,6 @@ struct Sim {
     U16A(u_qlen, u) = (uint16_t)n;
     if (n == 0) U16A(u_tail, u) = OM_NONE16;
     return h;
-  }
-  // Resource._trigger_put on the queue head only (simpy/resources/base.py)
-  __device__ __forceinline__ int grant_head(int u) {
-    int h = q_pop(u);
-    U16A(u_user, u) = (uint16_t)h;
-    sched_truck(h, now, OM_KEY_NORMAL, (u < c.S) ? PH_LOAD_GRANTED : PH_DUMP_GRANTED);
-    return h;
-  }
-  // Request.__init__: append, then _trigger_put.  Returns the truck's index in the queue afterwards
-  // as truck.check_queue_position sees it (truck.py:258-273).
-  __device__ __forceinline__ int request(int u, int i) {
-    q_push(u, i);
-    F64(t_time, i) = om_inf();
-    U32A(t_key, i) = OM_KEY_SENTINEL;
-    U8A(t_phase, i) = PH_WAITING;
-    U16A(t_unit, i) = (uint16_t)u;
-    bool me = false;
-    if (U16A(u_user, u) == OM_NONE16) me = (grant_head(u) == i);
-    return me ? 0 : (int)U16A(u_qlen, u) - 1;
   }
   // Resource.release: users cleared now, Release event scheduled NORMAL (hand-over happens when it pops)
   __device__ __forceinline__ void release(int u) {
@@ -370,6 +358,7 @@ struct Sim {
   // site minima with site_est().
   __device__ __forceinline__ void unit_est_all(bool load_side) {
     int ub = load_side ? 0 : c.S, ue = load_side ? c.S : c.U;
+    #pragma unroll 1
     for (int u = ub + lane; u < ue; u += 32) {
       double est;
       int n = U16A(u_qlen, u);
@@ -378,6 +367,7 @@ struct Sim {
         double last = (ld > ls) ? ld : ls;               // max(last_service_time, last_service_done_time)
         double total = 0.0;
         int t = U16A(u_head, u);
+        #pragma unroll 1
         for (int q = 0; q < n; ++q) {
           total += __ldg(&c.load_time[__ldg(&c.ttype[t]) * c.S + u]);
           t = U16A(t_next, t);
@@ -389,6 +379,7 @@ struct Sim {
       } else {
         double cyc = __ldg(&c.dcycle[u - c.S]);
         double total = 0.0;
+        #pragma unroll 1
         for (int q = 0; q < n; ++q) total += cyc;
         double used = now - F64(u_last_start, u);
         est = (total > used) ? (total - used) : 0.0;
@@ -401,6 +392,7 @@ struct Sim {
   __device__ __forceinline__ double site_est(int site) {
     int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
     double m = F64(scratch, ub);
+    #pragma unroll 1
     for (int u = ub + 1; u < ue; ++u) {
       double v = F64(scratch, u);
       if (v < m) m = v;
@@ -412,6 +404,7 @@ struct Sim {
   __device__ __forceinline__ int argmin_lanes(double v, int n) {
     double best = __shfl_sync(OM_FULL, v, 0);
     int idx = 0;
+    #pragma unroll 1
     for (int s = 1; s < n; ++s) {
       double x = __shfl_sync(OM_FULL, v, s);
       if (x < best) { best = x; idx = s; }
@@ -462,11 +455,22 @@ struct Sim {
           double v = om_inf();
           PySum ps; ps.init();
           const bool neu = c.sum_mode != 0;
-          int my_site_loc = 1 + lane;
-          for (int o = 0; o < c.T; ++o) {
-            int tg = U8A(t_tgt, o);
-            if (lane < L && o != i && tg == my_site_loc)
-              ps.add(__ldg(&c.sptf_cost[__ldg(&c.ttype[o]) * L + lane]), neu);
+          #pragma unroll 1
+          for (int base = 0; base < c.T; base += 32) {
+            int o = base + lane;
+            int tg = (o < c.T && o != i) ? (int)U8A(t_tgt, o) : 0;
+            unsigned mine_mask = 0;
+            #pragma unroll 1
+            for (int s = 0; s < L; ++s) {
+              unsigned m = __ballot_sync(OM_FULL, tg == 1 + s);
+              if (lane == s) mine_mask = m;
+            }
+            #pragma unroll 1
+            while (mine_mask) {                      // lane s walks the trucks coming to site s, in truck order
+              int b = __ffs(mine_mask) - 1;
+              mine_mask &= mine_mask - 1;
+              ps.add(__ldg(&c.sptf_cost[__ldg(&c.ttype[base + b]) * L + lane]), neu);
+            }
           }
           if (lane < L) v = ps.result() + site_est(lane);
           r = argmin_lanes(v, L);
@@ -515,9 +519,7 @@ struct Sim {
   // ---------------------------------------------------------------------------------------------
   // after an order has been decided: truck.py:303-317 (init), 390-402 (haul), 442-453 (back)
   __device__ __forceinline__ void apply_order(int i, int kind, int site) {
-    const int L = c.L, D = c.D;
-    int nmax = (kind == OM_ORDER_HAUL) ? D : L;
-    if (site < 0 || site >= nmax) { fail(OM_IERR_BAD_ORDER); return; }
+    const int L = c.L;
     uint32_t epoch = U16A(t_epoch, i);
     count_order(kind, site);
     U16A(t_epoch, i) = (uint16_t)(epoch + 1);
@@ -541,38 +543,24 @@ struct Sim {
       emit(K_ORDER_BACK, (uint32_t)i, (uint32_t)site, 0, dist, 0.0);
     }
     F64(t_dist, i) = dist;
-    sched_truck(i, now, 0u, PH_MOVE_BEGIN);   // env.process(move) -> Initialize URGENT
-  }
-
-  // ask for an order; with an external dispatcher the instance pauses here
-  __device__ __forceinline__ bool order(int i, int kind, int* pend_truck, int* pend_kind) {
-    if (disp == OM_DISP_EXTERNAL) {
-      U8A(t_phase, i) = PH_AWAIT_ORDER;
-      F64(t_time, i) = om_inf();
-      U32A(t_key, i) = OM_KEY_SENTINEL;
-      *pend_truck = i; *pend_kind = kind;
-      return false;
-    }
-    int site = decide(kind, i);
-    if (site < 0) return true;
-    apply_order(i, kind, site);
-    return true;
   }
 
   // move(): jam scan + departure (truck.py:151-210)
   __device__ __forceinline__ void move_depart(int i, bool dead) {
     int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
     double dist = F64(t_dist, i);
-    double duration = (dist / __ldg(&c.speed[i])) * 60.0;
+    double duration = om_ddiv(dist, __ldg(&c.speed[i])) * 60.0;
     double pre = 0.0;
     if (RNG != OM_RNG_DET && jam_count > 0) {
       int rid = road_id(cur, tgt);
+      #pragma unroll 1
       for (uint32_t base = 0; base < jam_count; base += 32) {
         uint32_t j = base + lane;
         bool hit = false;
         if (j < jam_count)
           hit = (U16A(j_road, j) == rid) && (F64(j_start, j) <= now) && (F64(j_end, j) >= now);
         unsigned m = __ballot_sync(OM_FULL, hit);
+        #pragma unroll 1
         while (m) {
           int b = __ffs(m) - 1;
           m &= m - 1;
@@ -598,158 +586,13 @@ struct Sim {
     sched_truck(i, now + (duration + pre), OM_KEY_NORMAL, PH_MOVE_ARRIVE);
   }
 
-  __device__ __forceinline__ bool after_load(int i, int u, int* pt, int* pk) {
-    release(u);
-    U8A(t_status, i) = ST_WAIT_HAUL;
-    return order(i, OM_ORDER_HAUL, pt, pk);
-  }
-
-  // One truck hop.  Returns false if the instance must pause for an external decision.
-  __device__ __forceinline__ bool truck_hop(int i, int* pt, int* pk) {
-    const uint8_t ph = U8A(t_phase, i);
-    switch (ph) {
-      case PH_RUN_INIT: {
-        U8A(t_cur, i) = 0;
-        U8A(t_status, i) = ST_WAIT_INIT;
-        return order(i, OM_ORDER_INIT, pt, pk);
-      }
-      case PH_MOVE_BEGIN: {
-        F64(t_jstart, i) = now;
-        // check_vehicle_availability (truck.py:538-547)
-        bool dead = false;
-        if (RNG != OM_RNG_DET) {
-          double g = draw_exp(OM_S_UNREPAIRABLE, U16A(t_epoch, i), (uint32_t)i, c.unrepairable_mean);
-          dead = now >= g;
-        }
-        double rep = F64(t_repair, i);
-        if (!dead && rep != 0.0) {
-          n_brk++;
-          emit(K_BREAKDOWN, (uint32_t)i, 0, 0, F64(t_lastbrk, i), rep);
-          U8A(t_status, i) = ST_REPAIRING;
-          sched_truck(i, now + rep, OM_KEY_NORMAL, PH_MOVE_REPAIRED);
-        } else {
-          move_depart(i, dead);
-        }
-        return true;
-      }
-      case PH_MOVE_REPAIRED: {
-        F64(t_repair, i) = 0.0;
-        U8A(t_status, i) = ST_MOVING;
-        move_depart(i, false);
-        return true;
-      }
-      case PH_MOVE_ARRIVE: {
-        U8A(t_cur, i) = U8A(t_tgt, i);
-        F64(t_prejam, i) = 0.0;
-        sched_truck(i, now, OM_KEY_NORMAL, PH_MOVE_RET);
-        return true;
-      }
-      case PH_MOVE_RET: {
-        int cur = U8A(t_cur, i);
-        int u = pick_unit(cur - 1);
-        int qi = request(u, i);
-        if (cur <= c.L) {
-          emit(K_WAIT_SHOVEL, (uint32_t)i, (uint32_t)u, (uint32_t)qi, 0.0, 0.0);
-          U8A(t_status, i) = ST_WAIT_SHOVEL;
-        } else {
-          emit(K_WAIT_DUMPER, (uint32_t)i, (uint32_t)(u - c.S), 0, 0.0, 0.0);
-          U8A(t_status, i) = ST_WAIT_DUMPER;
-        }
-        return true;
-      }
-      case PH_LOAD_GRANTED: {
-        emit(K_GET_SHOVEL, (uint32_t)i, (uint32_t)U16A(t_unit, i), 0, 0.0, 0.0);
-        sched_truck(i, now, 0u, PH_LOAD_BEGIN);
-        return true;
-      }
-      case PH_LOAD_BEGIN: {
-        int u = U16A(t_unit, i);
-        U8A(t_status, i) = ST_LOADING;
-        F64(u_last_start, u) = now;
-        double lt = __ldg(&c.load_time[__ldg(&c.ttype[i]) * c.S + u]);
-        sched_truck(i, now + lt, OM_KEY_NORMAL, PH_LOAD_DONE);
-        return true;
-      }
-      case PH_LOAD_DONE: {
-        int u = U16A(t_unit, i);
-        double load = __ldg(&c.cap[i]) * (1.0 + draw_jitter(U16A(t_epoch, i), (uint32_t)i));
-        F64(t_load, i) = load;
-        F64(u_tons, u) = F64(u_tons, u) + load;
-        U32A(u_svc, u) = U32A(u_svc, u) + 1;
-        F64(u_last_done, u) = now;
-        sched_truck(i, now, OM_KEY_NORMAL, PH_LOAD_RET);
-        return true;
-      }
-      case PH_LOAD_RET: {
-        int u = U16A(t_unit, i);
-        if (RNG != OM_RNG_DET) {
-          double gap = draw_exp(OM_S_MAINT_GAP, U16A(t_epoch, i), (uint32_t)i, c.maint_mean);
-          if (now >= F64(u_lastbrk, u) + gap) {
-            U8A(u_repair, u) = 1;
-            double d = draw_normal(OM_S_MAINT_DUR, U16A(t_epoch, i), (uint32_t)i, c.maint_mu, c.maint_sigma);
-            double dur = (0.0 > d) ? 0.0 : d;    // max(x, 0)
-            emit(K_SHOVEL_MAINT_START, (uint32_t)i, (uint32_t)u, 0, now + dur, 0.0);
-            sched_truck(i, now + dur, OM_KEY_NORMAL, PH_MAINT_DONE);
-            return true;
-          }
-        }
-        return after_load(i, u, pt, pk);
-      }
-      case PH_MAINT_DONE: {
-        int u = U16A(t_unit, i);
-        emit(K_SHOVEL_MAINT_DONE, (uint32_t)i, (uint32_t)u, 0, 0.0, 0.0);
-        F64(u_lastbrk, u) = now;
-        return after_load(i, u, pt, pk);
-      }
-      case PH_DUMP_GRANTED: {
-        emit(K_GET_DUMPER, (uint32_t)i, (uint32_t)(U16A(t_unit, i) - c.S), 0, 0.0, 0.0);
-        sched_truck(i, now, 0u, PH_DUMP_BEGIN);
-        return true;
-      }
-      case PH_DUMP_BEGIN: {
-        int u = U16A(t_unit, i);
-        U8A(t_status, i) = ST_UNLOADING;
-        F64(u_last_start, u) = now;
-        sched_truck(i, now + __ldg(&c.dcycle[u - c.S]), OM_KEY_NORMAL, PH_DUMP_DONE);
-        return true;
-      }
-      case PH_DUMP_DONE: {
-        int u = U16A(t_unit, i);
-        double load = F64(t_load, i);
-        F64(u_tons, u) = F64(u_tons, u) + load;
-        F64(t_total, i) = F64(t_total, i) + load;
-        uint32_t sc = (uint32_t)U16A(t_svc, i) + 1;
-        U16A(t_svc, i) = (uint16_t)sc;
-        F64(t_cycle, i) = (now - 0.0) / (double)sc;     // first_order_time is always 0 (truck.py:304)
-        F64(t_load, i) = 0.0;
-        U32A(u_svc, u) = U32A(u_svc, u) + 1;
-        F64(u_last_done, u) = now;
-        sched_truck(i, now, OM_KEY_NORMAL, PH_DUMP_RET);
-        return true;
-      }
-      case PH_DUMP_RET: {
-        release(U16A(t_unit, i));
-        U8A(t_status, i) = ST_WAIT_BACK;
-        return order(i, OM_ORDER_BACK, pt, pk);
-      }
-      default:
-        return true;
-    }
-  }
-
-  // Release event popped: hand the unit to the queue head (Resource._trigger_put)
-  __device__ __forceinline__ void unit_hop(int u) {
-    F64(u_rel_time, u) = om_inf();
-    U32A(u_rel_key, u) = OM_KEY_SENTINEL;
-    if (U16A(u_user, u) == OM_NONE16 && U16A(u_qlen, u) > 0) grant_head(u);
-  }
-
   // ---------------------------------------------------------------------------------------------
   // jam pool
   // ---------------------------------------------------------------------------------------------
   __device__ __forceinline__ void jam_append(int rid, double pos, double end) {
     if (jam_count == (uint32_t)c.J) {   // drop expired entries, keep creation order
       uint32_t w = 0;
+      #pragma unroll 1
       for (uint32_t j = 0; j < jam_count; ++j) {
         if (F64(j_end, j) >= now) {
           if (w != j) {
@@ -780,6 +623,7 @@ struct Sim {
     if (lane < NS) {
       int ub = __ldg(&c.ubeg[lane]), ue = __ldg(&c.ubeg[lane + 1]);
       PySum ps; ps.init();
+      #pragma unroll 1
       for (int u = ub; u < ue; ++u) {
         qtot += U16A(u_qlen, u);
         ps.add(F64(u_tons, u), neu);
@@ -792,6 +636,7 @@ struct Sim {
     // (2) mine KPI sample (mine.py:61-119)
     PySum pm; pm.init();
     int svc_total = 0;
+    #pragma unroll 1
     for (int j = 0; j < D; ++j) {
       pm.add(__shfl_sync(OM_FULL, site_tons, L + j), neu);
       svc_total += (int)__shfl_sync(OM_FULL, site_svc, L + j);
@@ -799,6 +644,7 @@ struct Sim {
     double produce = pm.result();
     reported_tons = produce;
     uint32_t n_work = 0, n_wait = 0, n_lu = 0, n_mov = 0, n_rep = 0;
+    #pragma unroll 1
     for (int base = 0; base < T; base += 32) {
       int i = base + lane;
       uint8_t st = (i < T) ? U8A(t_status, i) : (uint8_t)0xFF;
@@ -830,6 +676,7 @@ struct Sim {
     if (RNG != OM_RNG_DET) {
       // (3) truck breakdown sampling (truck.py:522-536), every truck every minute, truck order
       if (RNG == OM_RNG_TAPE) {
+        #pragma unroll 1
         for (int i = 0; i < T; ++i) {
           double gap = tape_next(OM_S_BREAK_GAP);
           if (now >= F64(t_lastbrk, i) + gap) {
@@ -839,13 +686,25 @@ struct Sim {
           }
         }
       } else {
-        for (int i = lane; i < T; i += 32) {
-          Philox4 r = px((uint32_t)k, (uint32_t)i, OM_S_BREAK_GAP);
-          double gap = (double)om_exp1(r.x) * c.breakdown_mean;
-          if (now >= F64(t_lastbrk, i) + gap) {
-            double d = c.repair_mu + c.repair_sigma * (double)om_normal(r.y, r.z);
-            F64(t_repair, i) = (0.0 > d) ? 0.0 : d;
-            F64(t_lastbrk, i) = now;
+        // one Philox call serves four trucks (words x,y,z,w -> trucks q, q+C, q+2C, q+3C); the rare
+        // repair-time normal draws its own call
+        const int C = (T + 3) >> 2;
+        #pragma unroll 1
+        for (int q = lane; q < C; q += 32) {
+          Philox4 r = px((uint32_t)k, (uint32_t)q, OM_S_BREAK_GAP);
+          uint32_t w4[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            int i = q + w * C;
+            if (i < T) {
+              double gap = (double)om_exp1(w4[w]) * c.breakdown_mean;
+              if (now >= F64(t_lastbrk, i) + gap) {
+                Philox4 r2 = px((uint32_t)k, (uint32_t)i, OM_S_BREAK_DUR);
+                double d = c.repair_mu + c.repair_sigma * (double)om_normal(r2.x, r2.y);
+                F64(t_repair, i) = (0.0 > d) ? 0.0 : d;
+                F64(t_lastbrk, i) = now;
+              }
+            }
           }
         }
         __syncwarp();
@@ -862,38 +721,48 @@ struct Sim {
   __device__ __forceinline__ void jam_sampling(int k) {
     const int T = c.T, R = c.R;
     uint32_t* rcnt = (uint32_t*)(sm + ly.scratch);   // scratch is sized >= max(U, R/2 + 1, 32) doubles
+    #pragma unroll 1
     for (int r = lane; r < R; r += 32) rcnt[r] = 0;
     __syncwarp();
+    #pragma unroll 1
     for (int i = lane; i < T; i += 32) {
       int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
       if (U8A(t_status, i) == ST_MOVING && cur != tgt) atomicAdd(&rcnt[road_id(cur, tgt)], 1u);
     }
     __syncwarp();
+    #pragma unroll 1
     for (int base = 0; base < R; base += 32) {
       int r = base + lane;
       uint32_t n_on = (r < R) ? rcnt[r] : 0u;
-      unsigned m = __ballot_sync(OM_FULL, n_on >= 2u);
+      bool candidate = n_on >= 2u;                          // road.py:148-176: >= 2 moving trucks
+      Philox4 rr;
+      rr.x = rr.y = rr.z = rr.w = 0u;
+      bool hit = candidate;
+      if (RNG == OM_RNG_PHILOX) {
+        // every candidate road flips its own keyed coin in parallel (road.py:179)
+        if (__any_sync(OM_FULL, candidate)) {
+          rr = px((uint32_t)k, (uint32_t)r, OM_S_JAM_COIN);
+          double coin = (double)((float)(rr.x >> 8) * 5.9604644775390625e-08f);   // [0,1)
+          hit = candidate && coin < __ldg(&c.jam_chance[candidate ? n_on : 0u]);
+        }
+      }
+      unsigned m = __ballot_sync(OM_FULL, hit);
+      #pragma unroll 1
       while (m) {
         int b = __ffs(m) - 1;
         m &= m - 1;
         int rid = base + b;
-        uint32_t n = __shfl_sync(OM_FULL, n_on, b);
-        double chance = __ldg(&c.jam_chance[n]);
-        double coin, pos = 0.0, dur;
-        Philox4 rr;
+        double pos, dur;
         if (RNG == OM_RNG_TAPE) {
-          coin = tape_next(OM_S_JAM_COIN);
-        } else {
-          rr = px((uint32_t)k, (uint32_t)rid, OM_S_JAM_COIN);
-          coin = (double)((float)(rr.x >> 8) * 5.9604644775390625e-08f);   // [0,1)
-        }
-        if (coin >= chance) continue;
-        if (RNG == OM_RNG_TAPE) {
+          uint32_t n = __shfl_sync(OM_FULL, n_on, b);
+          double coin = tape_next(OM_S_JAM_COIN);
+          if (coin >= __ldg(&c.jam_chance[n])) continue;
           pos = tape_next(OM_S_JAM_POS);
           dur = tape_next(OM_S_JAM_DUR) * c.jam_scale;
         } else {
-          pos = sample_jam_position(k, rid, rr.y);
-          dur = (double)sqrtf(om_exp1(rr.z)) * c.jam_scale;                // Weibull(shape 2) * scale
+          uint32_t wy = __shfl_sync(OM_FULL, rr.y, b), wz = __shfl_sync(OM_FULL, rr.z, b);
+          pos = sample_jam_position(k, rid, wy);
+          dur = (double)sqrtf(om_exp1(wz)) * c.jam_scale;                         // Weibull(shape 2) * scale
         }
         double end = now + dur;
         jam_append(rid, pos, end);
@@ -914,14 +783,16 @@ struct Sim {
     const double base_dist = __ldg(&c.rdist[rid]);
     float zsum = 0.0f;
     // pass 1: per-lane mass
+    #pragma unroll 1
     for (int i = lane; i < T; i += 32) {
       int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
       if (U8A(t_status, i) == ST_MOVING && cur != tgt && road_id(cur, tgt) == rid) {
         float cv = coverage(i, base_dist);
-        zsum += normcdff((1.0f + 0.5f * h - cv) / sd) - normcdff((-0.5f * h - cv) / sd);
+        zsum += om_normcdf((1.0f + 0.5f * h - cv) / sd) - om_normcdf((-0.5f * h - cv) / sd);
       }
     }
     float incl = zsum;
+    #pragma unroll 1
     for (int o = 1; o < 32; o <<= 1) {
       float v = __shfl_up_sync(OM_FULL, incl, o);
       if (lane >= o) incl += v;
@@ -933,18 +804,20 @@ struct Sim {
     float cpick = 0.5f;
     if (lane == owner) {
       float acc = incl - zsum;
+      #pragma unroll 1
       for (int i = lane; i < T; i += 32) {
         int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
         if (U8A(t_status, i) == ST_MOVING && cur != tgt && road_id(cur, tgt) == rid) {
           float cv = coverage(i, base_dist);
           cpick = cv;
-          acc += normcdff((1.0f + 0.5f * h - cv) / sd) - normcdff((-0.5f * h - cv) / sd);
+          acc += om_normcdf((1.0f + 0.5f * h - cv) / sd) - om_normcdf((-0.5f * h - cv) / sd);
           if (acc >= target) break;
         }
       }
     }
     cpick = __shfl_sync(OM_FULL, cpick, owner);
     float x = cpick;
+    #pragma unroll 1
     for (uint32_t it = 0; it < 64; ++it) {   // rejection on the truncation window (acceptance >= 1/2)
       Philox4 r = px((uint32_t)k, (uint32_t)rid, OM_S_JAM_POS, it);
       float x0 = cpick + sd * om_normal(r.x, r.y);
@@ -960,54 +833,314 @@ struct Sim {
 
   // Truck.get_route_coverage (truck.py:496-520)
   __device__ __forceinline__ float coverage(int i, double base_dist) {
-    double total = (base_dist / __ldg(&c.speed[i])) * 60.0 + F64(t_prejam, i) + F64(t_repair, i);
-    double cov = (now - F64(t_jstart, i)) / total;
+    double total = om_ddiv(base_dist, __ldg(&c.speed[i])) * 60.0 + F64(t_prejam, i) + F64(t_repair, i);
+    double cov = om_ddiv(now - F64(t_jstart, i), total);
     if (cov > 1.0) cov = 1.0;
     return (float)cov;
   }
 
   // ---------------------------------------------------------------------------------------------
-  // main loop: pop (time, key)-minimum entry until `until` (env.run(until), mine.py:391)
+  // main loop: pop the (time, key)-minimum entry until `until` (env.run(until), mine.py:391) and run the
+  // popped continuation.
+  //
+  // Exact hop fusion.  SimPy needs 16 truck hops + 2 Release hops per truck cycle, but most of them
+  // are forced: (1) an URGENT Initialize scheduled at t > 0 is always the very next pop (no other URGENT
+  // entry can be pending), so MOVE_BEGIN / LOAD_BEGIN / DUMP_BEGIN run inline; (2) when the
+  // popped entry is the ONLY pending entry with time == now (trucks, Releases and the monitor block
+  // included), every same-time successor it creates is again the unique minimum, so the whole chain
+  //   ARRIVE -> RET -> (grant) -> GRANTED -> BEGIN      and
+  //   DONE -> RET -> Release/order -> MOVE_BEGIN -> Release pops -> grant head -> GRANTED -> BEGIN
+  // runs back to back in SimPy's order without returning to the reduction.  With ties present every hop
+  // goes through the reduction exactly as SimPy's heap would order it.  `seq` advances identically in
+  // both modes, so the state is the same whichever path ran.
   // ---------------------------------------------------------------------------------------------
+  enum : uint32_t { XP_ORDER = 32, XP_DEPART, XP_AFTER_LOAD, XP_AFTER_DEPART, XP_DONE, XP_PAUSE };
+
   __device__ __forceinline__ void run(double until) {
-    const int T = c.T, U = c.U;
+    const int T = c.T, U = c.U, L = c.L, D = c.D, S = c.S;
     int pend_truck = -1, pend_kind = -1;
-    while (true) {
-      // lane-local minimum over this lane's trucks and units
-      double bt = om_inf();
-      uint32_t bk = OM_KEY_SENTINEL;
+    for (;;) {
+      // ---- lane-local minimum over this lane's trucks and units (times are >= 0: compare bit patterns)
+      uint32_t bhi = 0x7FF00000u, blo = 0u, bk = OM_KEY_SENTINEL;
       int bid = -1;
+      bool dup = false;
+      #pragma unroll 1
       for (int i = lane; i < T; i += 32) {
-        double t = F64(t_time, i);
+        uint2 tv = *(const uint2*)&F64(t_time, i);
         uint32_t kk = U32A(t_key, i);
-        if (t < bt || (t == bt && kk < bk)) { bt = t; bk = kk; bid = i; }
+        bool teq = (tv.y == bhi) && (tv.x == blo);
+        bool tlt = (tv.y < bhi) || (tv.y == bhi && tv.x < blo);
+        if (teq) dup = true;
+        if (tlt) dup = false;
+        if (tlt || (teq && kk < bk)) { bhi = tv.y; blo = tv.x; bk = kk; bid = i; }
       }
+      #pragma unroll 1
       for (int u = lane; u < U; u += 32) {
-        double t = F64(u_rel_time, u);
+        uint2 tv = *(const uint2*)&F64(u_rel_time, u);
         uint32_t kk = U32A(u_rel_key, u);
-        if (t < bt || (t == bt && kk < bk)) { bt = t; bk = kk; bid = T + u; }
+        bool teq = (tv.y == bhi) && (tv.x == blo);
+        bool tlt = (tv.y < bhi) || (tv.y == bhi && tv.x < blo);
+        if (teq) dup = true;
+        if (tlt) dup = false;
+        if (tlt || (teq && kk < bk)) { bhi = tv.y; blo = tv.x; bk = kk; bid = T + u; }
       }
-      // warp minimum of the 96-bit key (times are >= 0, so their bit patterns order as unsigned)
-      uint32_t hi = (uint32_t)__double2hiint(bt), lo = (uint32_t)__double2loint(bt);
-      uint32_t mhi = __reduce_min_sync(OM_FULL, hi);
-      uint32_t mlo = __reduce_min_sync(OM_FULL, (hi == mhi) ? lo : 0xFFFFFFFFu);
-      bool cand = (hi == mhi) && (lo == mlo);
+      uint32_t mhi = __reduce_min_sync(OM_FULL, bhi);
+      uint32_t mlo = __reduce_min_sync(OM_FULL, (bhi == mhi) ? blo : 0xFFFFFFFFu);
+      bool cand = (bhi == mhi) && (blo == mlo);
       uint32_t mk = __reduce_min_sync(OM_FULL, cand ? bk : OM_KEY_SENTINEL);
+      unsigned cands = __ballot_sync(OM_FULL, cand);
       unsigned ball = __ballot_sync(OM_FULL, cand && bk == mk);
-      int id = __shfl_sync(OM_FULL, bid, __ffs(ball) - 1);
+      int winner = __ffs(ball) - 1;
+      int id = __shfl_sync(OM_FULL, bid, winner);
+      bool wdup = __shfl_sync(OM_FULL, (int)dup, winner) != 0;
       double tmin = __hiloint2double((int)mhi, (int)mlo);
       bool is_tick = (tick_time < tmin) || (tick_time == tmin && tick_key < mk);
+      bool unique = (__popc(cands) == 1) && !wdup && (tick_time != tmin);
       if (is_tick) tmin = tick_time;
       if (!(tmin < until) || (err != OM_IERR_NONE && err != OM_IERR_TRACE_OVERFLOW)) break;
       now = tmin;
       n_hops++;
-      if (is_tick) {
-        tick_block();
-      } else if (id < T) {
-        if (!truck_hop(id, &pend_truck, &pend_kind)) break;
+      if (is_tick) { tick_block(); continue; }
+
+      const bool inl = now > 0.0;            // URGENT successors run inline
+      const bool chain = unique && inl;      // same-time NORMAL successors run inline
+      int i = id;
+      int rel_u = -1;                        // Release created in this chain, not yet popped
+      int kind = 0;
+      bool dead = false;
+      uint32_t ph;
+      if (id >= T) {
+        // Release event popped: Resource._trigger_put hands the unit to the queue head
+        int u = id - T;
+        F64(u_rel_time, u) = om_inf();
+        U32A(u_rel_key, u) = OM_KEY_SENTINEL;
+        if (U16A(u_user, u) != OM_NONE16 || U16A(u_qlen, u) == 0) continue;
+        i = q_pop(u);
+        U16A(u_user, u) = (uint16_t)i;
+        ph = (u < S) ? PH_LOAD_GRANTED : PH_DUMP_GRANTED;
+        if (!chain) { sched_truck(i, now, OM_KEY_NORMAL, (uint8_t)ph); continue; }
+        seq++;
       } else {
-        unit_hop(id - T);
+        ph = U8A(t_phase, i);
       }
+
+      for (;;) {
+        switch (ph) {
+          case PH_RUN_INIT:                                            // truck.py:296-302
+            U8A(t_cur, i) = 0;
+            U8A(t_status, i) = ST_WAIT_INIT;
+            kind = OM_ORDER_INIT;
+            ph = XP_ORDER;
+            break;
+          case XP_ORDER: {                                             // dispatcher.py:35-89 + truck.py:303-317,389-402,441-453
+            if (disp == OM_DISP_EXTERNAL) {
+              U8A(t_phase, i) = PH_AWAIT_ORDER;
+              F64(t_time, i) = om_inf();
+              U32A(t_key, i) = OM_KEY_SENTINEL;
+              pend_truck = i; pend_kind = kind;
+              ph = XP_PAUSE;
+              break;
+            }
+            int site = decide(kind, i);
+            int nmax = (kind == OM_ORDER_HAUL) ? D : L;
+            if (site < 0 || site >= nmax) { fail(OM_IERR_BAD_ORDER); ph = XP_DONE; break; }
+            apply_order(i, kind, site);
+            seq++;                                                     // env.process(move): Initialize URGENT
+            if (inl) { ph = PH_MOVE_BEGIN; break; }
+            F64(t_time, i) = now; U32A(t_key, i) = seq - 1; U8A(t_phase, i) = PH_MOVE_BEGIN;
+            ph = XP_AFTER_DEPART;
+            break;
+          }
+          case PH_MOVE_BEGIN: {                                        // truck.py:116-150
+            F64(t_jstart, i) = now;
+            dead = false;
+            if (RNG != OM_RNG_DET) {
+              double g = draw_exp(OM_S_UNREPAIRABLE, U16A(t_epoch, i), (uint32_t)i, c.unrepairable_mean);
+              dead = now >= g;                                         // check_vehicle_availability, truck.py:538-547
+            }
+            double rep = F64(t_repair, i);
+            if (!dead && rep != 0.0) {
+              n_brk++;
+              emit(K_BREAKDOWN, (uint32_t)i, 0, 0, F64(t_lastbrk, i), rep);
+              U8A(t_status, i) = ST_REPAIRING;
+              sched_truck(i, now + rep, OM_KEY_NORMAL, PH_MOVE_REPAIRED);
+              ph = XP_AFTER_DEPART;
+            } else {
+              ph = XP_DEPART;
+            }
+            break;
+          }
+          case PH_MOVE_REPAIRED:
+            F64(t_repair, i) = 0.0;
+            U8A(t_status, i) = ST_MOVING;
+            dead = false;
+            ph = XP_DEPART;
+            break;
+          case XP_DEPART:                                              // truck.py:151-210
+            move_depart(i, dead);
+            ph = XP_AFTER_DEPART;
+            break;
+          case XP_AFTER_DEPART: {
+            // the Release issued earlier in this chain is now the unique minimum: pop it
+            ph = XP_DONE;
+            if (rel_u >= 0) {
+              int u = rel_u;
+              rel_u = -1;
+              F64(u_rel_time, u) = om_inf();
+              U32A(u_rel_key, u) = OM_KEY_SENTINEL;
+              n_hops++;
+              if (U16A(u_user, u) == OM_NONE16 && U16A(u_qlen, u) > 0) {
+                i = q_pop(u);
+                U16A(u_user, u) = (uint16_t)i;
+                seq++;                                                 // Request.succeed()
+                ph = (u < S) ? PH_LOAD_GRANTED : PH_DUMP_GRANTED;
+              }
+            }
+            break;
+          }
+          case PH_MOVE_ARRIVE:                                         // truck.py:211-218
+            U8A(t_cur, i) = U8A(t_tgt, i);
+            F64(t_prejam, i) = 0.0;
+            if (chain) { seq++; ph = PH_MOVE_RET; break; }             // Process(move) event
+            sched_truck(i, now, OM_KEY_NORMAL, PH_MOVE_RET);
+            ph = XP_DONE;
+            break;
+          case PH_MOVE_RET: {                                          // truck.py:324-339 / 409-419
+            int cur = U8A(t_cur, i);
+            int u = pick_unit(cur - 1);
+            q_push(u, i);
+            U16A(t_unit, i) = (uint16_t)u;
+            bool me = false;
+            ph = XP_DONE;
+            if (U16A(u_user, u) == OM_NONE16) {                        // head-only _trigger_put
+              int h = q_pop(u);
+              U16A(u_user, u) = (uint16_t)h;
+              uint8_t gph = (u < S) ? PH_LOAD_GRANTED : PH_DUMP_GRANTED;
+              me = (h == i);
+              if (me && chain) { seq++; ph = gph; }
+              else sched_truck(h, now, OM_KEY_NORMAL, gph);
+            }
+            if (!me) {
+              F64(t_time, i) = om_inf();
+              U32A(t_key, i) = OM_KEY_SENTINEL;
+              U8A(t_phase, i) = PH_WAITING;
+            }
+            int qi = me ? 0 : (int)U16A(u_qlen, u) - 1;
+            if (cur <= L) {
+              emit(K_WAIT_SHOVEL, (uint32_t)i, (uint32_t)u, (uint32_t)qi, 0.0, 0.0);
+              U8A(t_status, i) = ST_WAIT_SHOVEL;
+            } else {
+              emit(K_WAIT_DUMPER, (uint32_t)i, (uint32_t)(u - S), 0, 0.0, 0.0);
+              U8A(t_status, i) = ST_WAIT_DUMPER;
+            }
+            break;
+          }
+          case PH_LOAD_GRANTED:                                        // truck.py:342-350
+            emit(K_GET_SHOVEL, (uint32_t)i, (uint32_t)U16A(t_unit, i), 0, 0.0, 0.0);
+            seq++;                                                     // env.process(load): Initialize URGENT
+            if (inl) { ph = PH_LOAD_BEGIN; break; }
+            F64(t_time, i) = now; U32A(t_key, i) = seq - 1; U8A(t_phase, i) = PH_LOAD_BEGIN;
+            ph = XP_DONE;
+            break;
+          case PH_LOAD_BEGIN: {                                        // truck.py:221-228
+            int u = U16A(t_unit, i);
+            U8A(t_status, i) = ST_LOADING;
+            F64(u_last_start, u) = now;
+            sched_truck(i, now + __ldg(&c.load_time[__ldg(&c.ttype[i]) * S + u]), OM_KEY_NORMAL, PH_LOAD_DONE);
+            ph = XP_DONE;
+            break;
+          }
+          case PH_LOAD_DONE: {                                         // truck.py:230-235
+            int u = U16A(t_unit, i);
+            double load = __ldg(&c.cap[i]) * (1.0 + draw_jitter(U16A(t_epoch, i), (uint32_t)i));
+            F64(t_load, i) = load;
+            F64(u_tons, u) = F64(u_tons, u) + load;
+            U32A(u_svc, u) = U32A(u_svc, u) + 1;
+            F64(u_last_done, u) = now;
+            if (chain) { seq++; ph = PH_LOAD_RET; break; }             // Process(load) event
+            sched_truck(i, now, OM_KEY_NORMAL, PH_LOAD_RET);
+            ph = XP_DONE;
+            break;
+          }
+          case PH_LOAD_RET: {                                          // truck.py:352-370
+            ph = XP_AFTER_LOAD;
+            if (RNG != OM_RNG_DET) {
+              int u = U16A(t_unit, i);
+              double gap = draw_exp(OM_S_MAINT_GAP, U16A(t_epoch, i), (uint32_t)i, c.maint_mean);
+              if (now >= F64(u_lastbrk, u) + gap) {
+                U8A(u_repair, u) = 1;
+                double dn = draw_normal(OM_S_MAINT_DUR, U16A(t_epoch, i), (uint32_t)i, c.maint_mu, c.maint_sigma);
+                double dur = (0.0 > dn) ? 0.0 : dn;                    // max(x, 0)
+                emit(K_SHOVEL_MAINT_START, (uint32_t)i, (uint32_t)u, 0, now + dur, 0.0);
+                sched_truck(i, now + dur, OM_KEY_NORMAL, PH_MAINT_DONE);
+                ph = XP_DONE;
+              }
+            }
+            break;
+          }
+          case PH_MAINT_DONE: {                                        // truck.py:372-379
+            int u = U16A(t_unit, i);
+            emit(K_SHOVEL_MAINT_DONE, (uint32_t)i, (uint32_t)u, 0, 0.0, 0.0);
+            F64(u_lastbrk, u) = now;
+            ph = XP_AFTER_LOAD;
+            break;
+          }
+          case XP_AFTER_LOAD: {                                        // leave `with req:` -> release; truck.py:383-389
+            int u = U16A(t_unit, i);
+            release(u);
+            if (chain) rel_u = u;
+            U8A(t_status, i) = ST_WAIT_HAUL;
+            kind = OM_ORDER_HAUL;
+            ph = XP_ORDER;
+            break;
+          }
+          case PH_DUMP_GRANTED:                                        // truck.py:422-429
+            emit(K_GET_DUMPER, (uint32_t)i, (uint32_t)(U16A(t_unit, i) - S), 0, 0.0, 0.0);
+            seq++;
+            if (inl) { ph = PH_DUMP_BEGIN; break; }
+            F64(t_time, i) = now; U32A(t_key, i) = seq - 1; U8A(t_phase, i) = PH_DUMP_BEGIN;
+            ph = XP_DONE;
+            break;
+          case PH_DUMP_BEGIN: {                                        // truck.py:238-242
+            int u = U16A(t_unit, i);
+            U8A(t_status, i) = ST_UNLOADING;
+            F64(u_last_start, u) = now;
+            sched_truck(i, now + __ldg(&c.dcycle[u - S]), OM_KEY_NORMAL, PH_DUMP_DONE);
+            ph = XP_DONE;
+            break;
+          }
+          case PH_DUMP_DONE: {                                         // truck.py:243-251
+            int u = U16A(t_unit, i);
+            double load = F64(t_load, i);
+            F64(u_tons, u) = F64(u_tons, u) + load;
+            F64(t_total, i) = F64(t_total, i) + load;
+            uint32_t sc = (uint32_t)U16A(t_svc, i) + 1;
+            U16A(t_svc, i) = (uint16_t)sc;
+            F64(t_cycle, i) = om_ddiv(now - 0.0, (double)sc);          // first_order_time is always 0 (truck.py:304)
+            F64(t_load, i) = 0.0;
+            U32A(u_svc, u) = U32A(u_svc, u) + 1;
+            F64(u_last_done, u) = now;
+            if (chain) { seq++; ph = PH_DUMP_RET; break; }             // Process(unload) event
+            sched_truck(i, now, OM_KEY_NORMAL, PH_DUMP_RET);
+            ph = XP_DONE;
+            break;
+          }
+          case PH_DUMP_RET: {                                          // truck.py:431-441
+            int u = U16A(t_unit, i);
+            release(u);
+            if (chain) rel_u = u;
+            U8A(t_status, i) = ST_WAIT_BACK;
+            kind = OM_ORDER_BACK;
+            ph = XP_ORDER;
+            break;
+          }
+          default:
+            ph = XP_DONE;
+            break;
+        }
+        if (ph >= XP_DONE) break;
+      }
+      if (ph == XP_PAUSE) break;
     }
     InstHdr* h = (InstHdr*)(sm + ly.hdr);
     h->pending_truck = pend_truck;
@@ -1018,6 +1151,7 @@ struct Sim {
   __device__ __forceinline__ double dumped_tons() {
     PySum ps; ps.init();
     const bool neu = c.sum_mode != 0;
+    #pragma unroll 1
     for (int u = c.S; u < c.U; ++u) ps.add(F64(u_tons, u), neu);
     return ps.result();
   }
@@ -1030,8 +1164,10 @@ __device__ __forceinline__ void om_init_state(unsigned char* sm, const DevCfg& c
                                               uint64_t seed, int dispatcher) {
   const double inf = om_inf();
   // zero everything first
+  #pragma unroll 1
   for (uint32_t o = lane * 8; o < ly.total_bytes; o += 256) *(unsigned long long*)(sm + o) = 0ull;
   __syncwarp();
+  #pragma unroll 1
   for (int i = lane; i < c.T; i += 32) {
     F64(t_time, i) = 0.0;
     U32A(t_key, i) = (uint32_t)(1 + i);          // URGENT, after the monitors
@@ -1042,6 +1178,7 @@ __device__ __forceinline__ void om_init_state(unsigned char* sm, const DevCfg& c
     U16A(t_next, i) = OM_NONE16;
     U16A(t_unit, i) = OM_NONE16;
   }
+  #pragma unroll 1
   for (int u = lane; u < c.U; u += 32) {
     F64(u_rel_time, u) = inf;
     U32A(u_rel_key, u) = OM_KEY_SENTINEL;

@@ -48,10 +48,13 @@ __device__ __forceinline__ float om_u01(uint32_t x) { return (float)((x >> 8) + 
 __device__ __forceinline__ float om_exp1(uint32_t x) { return -__logf(om_u01(x)); }
 
 // standard normal from two 32-bit words (Box-Muller, accurate libm flavours: draws are rare)
-__device__ __forceinline__ float om_normal(uint32_t a, uint32_t b) {
+__device__ __noinline__ float om_normal(uint32_t a, uint32_t b) {
   float r = sqrtf(-2.0f * logf(om_u01(a)));
   return r * cospif(2.0f * om_u01(b));
 }
 
 // bounded integer in [0, n): Lemire multiply-shift (no rejection); mirrored by oracle/philox.py
 __device__ __forceinline__ uint32_t om_randint(uint32_t x, uint32_t n) { return __umulhi(x, n); }
+
+// standard normal CDF, out of line (used only when a jam is created)
+__device__ __noinline__ float om_normcdf(float x) { return normcdff(x); }

@@ -165,7 +165,7 @@ typedef struct OmStateLayout {
   uint32_t total_bytes;
   uint32_t hdr;
   uint32_t t_time, t_load, t_jstart, t_prejam, t_lastbrk, t_repair, t_total, t_cycle, t_dist; /* f64 */
-  uint32_t t_key;                                                                            /* u32 */
+  uint32_t t_key, t_rng;                                                                     /* u32 */
   uint32_t t_svc, t_epoch, t_next, t_unit;                                                   /* u16 */
   uint32_t t_phase, t_status, t_cur, t_tgt;                                                  /* u8  */
   uint32_t u_rel_time, u_last_start, u_last_done, u_tons, u_lastbrk;                         /* f64 */

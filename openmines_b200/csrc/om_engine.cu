@@ -158,7 +158,7 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly) {
   if (nscr < (R + 1) / 2) nscr = (R + 1) / 2;
   if (nscr < 32) nscr = 32;
   ly.scratch = take(off, 8, nscr);
-  ly.t_key = take(off, 4, T); ly.u_rel_key = take(off, 4, U); ly.u_svc = take(off, 4, U);
+  ly.t_key = take(off, 4, T); ly.t_rng = take(off, 4, T); ly.u_rel_key = take(off, 4, U); ly.u_svc = take(off, 4, U);
   ly.t_svc = take(off, 2, T); ly.t_epoch = take(off, 2, T); ly.t_next = take(off, 2, T); ly.t_unit = take(off, 2, T);
   ly.u_user = take(off, 2, U); ly.u_head = take(off, 2, U); ly.u_tail = take(off, 2, U); ly.u_qlen = take(off, 2, U);
   ly.j_road = take(off, 2, J); ly.s_qtotal = take(off, 2, NS); ly.s_coming = take(off, 2, NS);

@@ -98,7 +98,7 @@ struct InstHdr {
   int32_t pending_truck;
   int32_t pending_kind;
   uint32_t n_ticks;
-  uint32_t pad;
+  uint32_t n_rel;       // pending Release entries in the unit table
 };
 static_assert(sizeof(InstHdr) == 120, "InstHdr size");
 #define OM_HDR_BYTES 128
@@ -158,10 +158,11 @@ struct Sim {
   int tick_k, disp;
   uint32_t k0, k1;
   uint32_t n_events, n_decisions, n_orders, n_hops, n_jams, n_road_rep, n_brk, n_unrep;
-  uint32_t jam_count, err, trace_count, order_count, n_ticks;
+  uint32_t jam_count, err, trace_count, order_count, n_ticks, n_rel;
   unsigned long long tape_pos, tape_end;
   const double* tape_v;
   const uint8_t* tape_s;
+  Philox4 ordw;   // words of the current order's Philox call (PHILOX mode)
 
   __device__ __forceinline__ Sim(unsigned char* sm_, const RunParams& p, int lane_, long long inst_)
       : sm(sm_), c(p.c), ly(p.ly), out(p.out), lane(lane_), inst(inst_) {}
@@ -182,7 +183,7 @@ struct Sim {
     n_events = h->n_events; n_decisions = h->n_decisions; n_orders = h->n_orders; n_hops = h->n_hops;
     n_jams = h->n_jams; n_road_rep = h->n_road_rep; n_brk = h->n_brk; n_unrep = h->n_unrep;
     jam_count = h->jam_count; err = h->err; trace_count = h->trace_count; order_count = h->order_count;
-    n_ticks = h->n_ticks;
+    n_ticks = h->n_ticks; n_rel = h->n_rel;
     tape_pos = h->tape_pos; tape_end = 0; tape_v = p.tape_values; tape_s = p.tape_sites;
     if (RNG == OM_RNG_TAPE) {
       tape_pos += (unsigned long long)p.tape_offsets[inst];   // hdr stores the position relative to the instance's tape
@@ -196,7 +197,7 @@ struct Sim {
     h->n_events = n_events; h->n_decisions = n_decisions; h->n_orders = n_orders; h->n_hops = n_hops;
     h->n_jams = n_jams; h->n_road_rep = n_road_rep; h->n_brk = n_brk; h->n_unrep = n_unrep;
     h->jam_count = jam_count; h->err = err; h->trace_count = trace_count; h->order_count = order_count;
-    h->n_ticks = n_ticks;
+    h->n_ticks = n_ticks; h->n_rel = n_rel;
     h->tape_pos = (RNG == OM_RNG_TAPE) ? tape_pos - (unsigned long long)p.tape_offsets[inst] : 0ull;
   }
 
@@ -291,12 +292,18 @@ struct Sim {
     if (n == 0) U16A(u_tail, u) = OM_NONE16;
     return h;
   }
-  // Resource.release: users cleared now, Release event scheduled NORMAL (hand-over happens when it pops)
-  __device__ __forceinline__ void release(int u) {
+  // Resource.release: users cleared now, Release event scheduled NORMAL (hand-over happens when it pops).
+  // Returns the Release's key; the caller either keeps it in registers (fused chain) or files it.
+  __device__ __forceinline__ uint32_t release(int u) {
     U16A(u_user, u) = OM_NONE16;
-    F64(u_rel_time, u) = now;
-    U32A(u_rel_key, u) = OM_KEY_NORMAL | seq;
+    uint32_t key = OM_KEY_NORMAL | seq;
     seq++;
+    return key;
+  }
+  __device__ __forceinline__ void file_release(int u, uint32_t key) {
+    F64(u_rel_time, u) = now;
+    U32A(u_rel_key, u) = key;
+    n_rel++;
   }
 
   // get_available_shovel / get_available_dumper (load_site.py:209-220, dump_site.py:105-116):
@@ -330,7 +337,8 @@ struct Sim {
     } else {
       in_repair = false;
       if (RNG != OM_RNG_DET) {
-        double gap = draw_exp(OM_S_ROAD_GAP, epoch, (uint32_t)i, 1.0 / c.road_lambda);   // expovariate(lambda)
+        double gap = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(ordw.x) / c.road_lambda
+                                            : draw_exp(OM_S_ROAD_GAP, epoch, (uint32_t)i, 1.0 / c.road_lambda);   // expovariate(lambda)
         if (now >= end + gap) {
           double d = draw_normal(OM_S_ROAD_DUR, epoch, (uint32_t)i, c.road_mu, c.road_sigma);
           double dur = (d > 0.0) ? d : 0.0;   // max(0, x)
@@ -521,6 +529,11 @@ struct Sim {
   __device__ __forceinline__ void apply_order(int i, int kind, int site) {
     const int L = c.L;
     uint32_t epoch = U16A(t_epoch, i);
+    if (RNG == OM_RNG_PHILOX) {
+      // one call per order: x -> road-repair gap (haul/back), y -> unrepairable gap of the move that follows
+      ordw = px(epoch, (uint32_t)i, OM_S_ROAD_GAP);
+      U32A(t_rng, i) = ordw.y;
+    }
     count_order(kind, site);
     U16A(t_epoch, i) = (uint16_t)(epoch + 1);
     double dist;
@@ -760,8 +773,8 @@ struct Sim {
           pos = tape_next(OM_S_JAM_POS);
           dur = tape_next(OM_S_JAM_DUR) * c.jam_scale;
         } else {
-          uint32_t wy = __shfl_sync(OM_FULL, rr.y, b), wz = __shfl_sync(OM_FULL, rr.z, b);
-          pos = sample_jam_position(k, rid, wy);
+          uint32_t wz = __shfl_sync(OM_FULL, rr.z, b);
+          pos = sample_jam_position(k, rid, __shfl_sync(OM_FULL, n_on, b));
           dur = (double)sqrtf(om_exp1(wz)) * c.jam_scale;                         // Weibull(shape 2) * scale
         }
         double end = now + dur;
@@ -774,57 +787,44 @@ struct Sim {
   }
 
   // Position of a new jam on road `rid`: the reference draws an index on linspace(0,1,1000) with
-  // p ~ sum_i N(x; coverage_i, sd) (road.py:185-206).  Equivalent two-stage sampler: pick truck i with
-  // probability ~ its grid mass Phi((1+h/2-c_i)/sd) - Phi((-h/2-c_i)/sd), then draw x ~ N(c_i, sd)
-  // truncated to [-h/2, 1+h/2] and round to the grid (mid-point rule; relative error O((h/sd)^2/24)).
-  __device__ __forceinline__ double sample_jam_position(int k, int rid, uint32_t upick) {
+  // p ~ sum_i N(x; coverage_i, sd) over the trucks on the road (road.py:185-206).  Equivalent rejection
+  // sampler: pick one of the N trucks uniformly, draw x ~ N(coverage_i, sd), accept iff x falls in the
+  // grid window [-h/2, 1+h/2] (else pick again), round to the grid.  Accepted x has density
+  // ~ sum_i N(x; c_i, sd) on the window, i.e. the reference's categorical up to the mid-point rule
+  // (relative error O((h/sd)^2/24) = 4e-6).  Acceptance >= 1/2 per attempt.
+  __device__ __forceinline__ double sample_jam_position(int k, int rid, uint32_t n_on) {
     const int T = c.T;
     const float sd = (float)c.jam_sd, h = 1.0f / 999.0f;
     const double base_dist = __ldg(&c.rdist[rid]);
-    float zsum = 0.0f;
-    // pass 1: per-lane mass
-    #pragma unroll 1
-    for (int i = lane; i < T; i += 32) {
-      int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
-      if (U8A(t_status, i) == ST_MOVING && cur != tgt && road_id(cur, tgt) == rid) {
-        float cv = coverage(i, base_dist);
-        zsum += om_normcdf((1.0f + 0.5f * h - cv) / sd) - om_normcdf((-0.5f * h - cv) / sd);
-      }
-    }
-    float incl = zsum;
-    #pragma unroll 1
-    for (int o = 1; o < 32; o <<= 1) {
-      float v = __shfl_up_sync(OM_FULL, incl, o);
-      if (lane >= o) incl += v;
-    }
-    float total = __shfl_sync(OM_FULL, incl, 31);
-    float target = om_u01(upick) * total;
-    unsigned m = __ballot_sync(OM_FULL, incl >= target && zsum > 0.0f);
-    int owner = m ? (__ffs(m) - 1) : 31;
-    float cpick = 0.5f;
-    if (lane == owner) {
-      float acc = incl - zsum;
-      #pragma unroll 1
-      for (int i = lane; i < T; i += 32) {
-        int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
-        if (U8A(t_status, i) == ST_MOVING && cur != tgt && road_id(cur, tgt) == rid) {
-          float cv = coverage(i, base_dist);
-          cpick = cv;
-          acc += om_normcdf((1.0f + 0.5f * h - cv) / sd) - om_normcdf((-0.5f * h - cv) / sd);
-          if (acc >= target) break;
+    float x = 0.5f;
+#pragma unroll 1
+    for (uint32_t it = 0; it < 64; ++it) {
+      Philox4 r = px((uint32_t)k, (uint32_t)rid, OM_S_JAM_POS, it);
+      int pick = (int)om_randint(r.x, n_on);               // pick-th truck on this road, truck order
+      int found = -1;
+#pragma unroll 1
+      for (int base = 0; base < T && found < 0; base += 32) {
+        int i = base + lane;
+        bool on = false;
+        if (i < T) {
+          int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
+          on = U8A(t_status, i) == ST_MOVING && cur != tgt && road_id(cur, tgt) == rid;
+        }
+        unsigned m = __ballot_sync(OM_FULL, on);
+        int cnt = __popc(m);
+        if (pick < cnt) {
+          // position of the pick-th set bit
+#pragma unroll 1
+          for (int q = 0; q < pick; ++q) m &= m - 1;
+          found = base + __ffs(m) - 1;
+        } else {
+          pick -= cnt;
         }
       }
-    }
-    cpick = __shfl_sync(OM_FULL, cpick, owner);
-    float x = cpick;
-    #pragma unroll 1
-    for (uint32_t it = 0; it < 64; ++it) {   // rejection on the truncation window (acceptance >= 1/2)
-      Philox4 r = px((uint32_t)k, (uint32_t)rid, OM_S_JAM_POS, it);
-      float x0 = cpick + sd * om_normal(r.x, r.y);
-      float x1 = cpick + sd * om_normal(r.z, r.w);
-      bool ok0 = x0 >= -0.5f * h && x0 <= 1.0f + 0.5f * h;
-      bool ok1 = x1 >= -0.5f * h && x1 <= 1.0f + 0.5f * h;
-      if (ok0 || ok1) { x = ok0 ? x0 : x1; break; }
+      if (found < 0) break;                                 // cannot happen: n_on trucks are on the road
+      float cv = coverage(found, base_dist);
+      float xx = cv + sd * om_normal(r.y, r.z);
+      if (xx >= -0.5f * h && xx <= 1.0f + 0.5f * h) { x = xx; break; }
     }
     int idx = __float2int_rn(x * 999.0f);
     idx = idx < 0 ? 0 : (idx > 999 ? 999 : idx);
@@ -874,7 +874,8 @@ struct Sim {
         if (tlt) dup = false;
         if (tlt || (teq && kk < bk)) { bhi = tv.y; blo = tv.x; bk = kk; bid = i; }
       }
-      #pragma unroll 1
+            if (n_rel != 0)
+#pragma unroll 1
       for (int u = lane; u < U; u += 32) {
         uint2 tv = *(const uint2*)&F64(u_rel_time, u);
         uint32_t kk = U32A(u_rel_key, u);
@@ -905,7 +906,8 @@ struct Sim {
       const bool inl = now > 0.0;            // URGENT successors run inline
       const bool chain = unique && inl;      // same-time NORMAL successors run inline
       int i = id;
-      int rel_u = -1;                        // Release created in this chain, not yet popped
+      int rel_u = -1;                        // Release created in this chain, not yet popped (kept in registers)
+      uint32_t rel_key = 0;
       int kind = 0;
       bool dead = false;
       uint32_t ph;
@@ -914,6 +916,7 @@ struct Sim {
         int u = id - T;
         F64(u_rel_time, u) = om_inf();
         U32A(u_rel_key, u) = OM_KEY_SENTINEL;
+        n_rel--;
         if (U16A(u_user, u) != OM_NONE16 || U16A(u_qlen, u) == 0) continue;
         i = q_pop(u);
         U16A(u_user, u) = (uint16_t)i;
@@ -938,12 +941,18 @@ struct Sim {
               F64(t_time, i) = om_inf();
               U32A(t_key, i) = OM_KEY_SENTINEL;
               pend_truck = i; pend_kind = kind;
+              if (rel_u >= 0) { file_release(rel_u, rel_key); rel_u = -1; }
               ph = XP_PAUSE;
               break;
             }
             int site = decide(kind, i);
             int nmax = (kind == OM_ORDER_HAUL) ? D : L;
-            if (site < 0 || site >= nmax) { fail(OM_IERR_BAD_ORDER); ph = XP_DONE; break; }
+            if (site < 0 || site >= nmax) {
+              fail(OM_IERR_BAD_ORDER);
+              if (rel_u >= 0) { file_release(rel_u, rel_key); rel_u = -1; }
+              ph = XP_DONE;
+              break;
+            }
             apply_order(i, kind, site);
             seq++;                                                     // env.process(move): Initialize URGENT
             if (inl) { ph = PH_MOVE_BEGIN; break; }
@@ -955,7 +964,8 @@ struct Sim {
             F64(t_jstart, i) = now;
             dead = false;
             if (RNG != OM_RNG_DET) {
-              double g = draw_exp(OM_S_UNREPAIRABLE, U16A(t_epoch, i), (uint32_t)i, c.unrepairable_mean);
+              double g = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(U32A(t_rng, i)) * c.unrepairable_mean
+                                                : draw_exp(OM_S_UNREPAIRABLE, U16A(t_epoch, i), (uint32_t)i, c.unrepairable_mean);
               dead = now >= g;                                         // check_vehicle_availability, truck.py:538-547
             }
             double rep = F64(t_repair, i);
@@ -986,9 +996,6 @@ struct Sim {
             if (rel_u >= 0) {
               int u = rel_u;
               rel_u = -1;
-              F64(u_rel_time, u) = om_inf();
-              U32A(u_rel_key, u) = OM_KEY_SENTINEL;
-              n_hops++;
               if (U16A(u_user, u) == OM_NONE16 && U16A(u_qlen, u) > 0) {
                 i = q_pop(u);
                 U16A(u_user, u) = (uint16_t)i;
@@ -1052,7 +1059,16 @@ struct Sim {
           }
           case PH_LOAD_DONE: {                                         // truck.py:230-235
             int u = U16A(t_unit, i);
-            double load = __ldg(&c.cap[i]) * (1.0 + draw_jitter(U16A(t_epoch, i), (uint32_t)i));
+            double jit;
+            if (RNG == OM_RNG_PHILOX) {
+              // one call per load: x -> load jitter, y -> shovel-maintenance gap (read at LOAD_RET)
+              Philox4 r = px(U16A(t_epoch, i), (uint32_t)i, OM_S_LOAD_JITTER);
+              jit = -0.1 + 0.2 * (double)om_u01(r.x);
+              U32A(t_rng, i) = r.y;
+            } else {
+              jit = draw_jitter(U16A(t_epoch, i), (uint32_t)i);
+            }
+            double load = __ldg(&c.cap[i]) * (1.0 + jit);
             F64(t_load, i) = load;
             F64(u_tons, u) = F64(u_tons, u) + load;
             U32A(u_svc, u) = U32A(u_svc, u) + 1;
@@ -1066,7 +1082,8 @@ struct Sim {
             ph = XP_AFTER_LOAD;
             if (RNG != OM_RNG_DET) {
               int u = U16A(t_unit, i);
-              double gap = draw_exp(OM_S_MAINT_GAP, U16A(t_epoch, i), (uint32_t)i, c.maint_mean);
+              double gap = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(U32A(t_rng, i)) * c.maint_mean
+                                                  : draw_exp(OM_S_MAINT_GAP, U16A(t_epoch, i), (uint32_t)i, c.maint_mean);
               if (now >= F64(u_lastbrk, u) + gap) {
                 U8A(u_repair, u) = 1;
                 double dn = draw_normal(OM_S_MAINT_DUR, U16A(t_epoch, i), (uint32_t)i, c.maint_mu, c.maint_sigma);
@@ -1087,8 +1104,8 @@ struct Sim {
           }
           case XP_AFTER_LOAD: {                                        // leave `with req:` -> release; truck.py:383-389
             int u = U16A(t_unit, i);
-            release(u);
-            if (chain) rel_u = u;
+            rel_key = release(u);
+            if (chain) rel_u = u; else file_release(u, rel_key);
             U8A(t_status, i) = ST_WAIT_HAUL;
             kind = OM_ORDER_HAUL;
             ph = XP_ORDER;
@@ -1127,8 +1144,8 @@ struct Sim {
           }
           case PH_DUMP_RET: {                                          // truck.py:431-441
             int u = U16A(t_unit, i);
-            release(u);
-            if (chain) rel_u = u;
+            rel_key = release(u);
+            if (chain) rel_u = u; else file_release(u, rel_key);
             U8A(t_status, i) = ST_WAIT_BACK;
             kind = OM_ORDER_BACK;
             ph = XP_ORDER;

@@ -29,7 +29,7 @@ class OmOutputsStruct(ctypes.Structure):
 
 
 _LAYOUT_FIELDS = ["total_bytes", "hdr", "t_time", "t_load", "t_jstart", "t_prejam", "t_lastbrk", "t_repair",
-                  "t_total", "t_cycle", "t_dist", "t_key", "t_svc", "t_epoch", "t_next", "t_unit", "t_phase",
+                  "t_total", "t_cycle", "t_dist", "t_key", "t_rng", "t_svc", "t_epoch", "t_next", "t_unit", "t_phase",
                   "t_status", "t_cur", "t_tgt", "u_rel_time", "u_last_start", "u_last_done", "u_tons", "u_lastbrk",
                   "u_rel_key", "u_svc", "u_user", "u_head", "u_tail", "u_qlen", "u_repair", "r_repair_end",
                   "j_pos", "j_start", "j_end", "j_road", "s_qtotal", "s_coming", "scratch"]

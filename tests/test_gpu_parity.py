@@ -118,3 +118,34 @@ def test_resume_equals_single_run(north_pit):
         assert np.array_equal(a[f], b[f]), f
     for i in range(6):
         assert np.array_equal(t1[i], r2.trace_np(i)[0])
+
+
+def test_live_distribution_vs_reference(north_pit):
+    """live RNG (Philox): per-instance reported tons, truck events and jam counts must agree in
+    distribution with the reference's own stochastic runs (48 seeds per dispatcher, recorded in
+    tests/golden/live_distribution_north_pit_mine.npz).  Bounds: Welch z-test on the mean at
+    |z| < 4.0 (two-sided p ~ 6e-5 per check, 18 checks) and two-sample KS p > 1e-4 on tons."""
+    import os
+    from scipy import stats
+    from helpers import GOLDEN
+    ref = np.load(os.path.join(GOLDEN, "live_distribution_north_pit_mine.npz"))
+    n_seeds = 2048
+    names = [d for d in DISPATCHERS for _ in range(n_seeds)]
+    seeds = np.tile(np.arange(n_seeds, dtype=np.uint64) + 10_000, len(DISPATCHERS))
+    mine = _mine(north_pit, len(names))
+    mine.reset(names, seeds=seeds, rng_mode="philox")
+    res = mine.run()
+    s = res.summary_np().reshape(len(DISPATCHERS), n_seeds)
+    assert (s["err"] == 0).all()
+    report = []
+    for k, d in enumerate(DISPATCHERS):
+        for field, key in (("reported_tons", "tons"), ("n_truck_events", "events"), ("n_jams", "jams")):
+            a = s[k][field].astype(np.float64)
+            b = ref["%s_%s" % (d, key)].astype(np.float64)
+            z = (a.mean() - b.mean()) / np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+            report.append((d, key, a.mean(), b.mean(), z))
+            assert abs(z) < 4.0, "%s %s: engine mean %.1f vs reference %.1f (z=%.2f)" % (d, key, a.mean(), b.mean(), z)
+        ks = stats.ks_2samp(s[k]["reported_tons"], ref[d + "_tons"])
+        assert ks.pvalue > 1e-4, "%s tons KS p=%.2e" % (d, ks.pvalue)
+    for r in report:
+        print("%-22s %-7s engine %10.2f  reference %10.2f  z=%+.2f" % r)

@@ -149,3 +149,18 @@ def test_live_distribution_vs_reference(north_pit):
         assert ks.pvalue > 1e-4, "%s tons KS p=%.2e" % (d, ks.pvalue)
     for r in report:
         print("%-22s %-7s engine %10.2f  reference %10.2f  z=%+.2f" % r)
+
+
+def test_stats_kernel_matches_host_mirror(north_pit):
+    """om_stats_reduce (the partial sums fed to the NCCL all-reduce) == the numpy mirror."""
+    from openmines_b200 import parallel
+    n = 600
+    ids = np.arange(n) % 6
+    mine = _mine(north_pit, n)
+    mine.reset(ids.astype(np.int32), seeds=np.arange(n) + 7, rng_mode="philox")
+    res = mine.run(until=90.0)
+    got = mine.stats(res).cpu().numpy()
+    want = parallel.stats_from_summaries(res.summary_np(), ids)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    rows = parallel.describe(got)
+    assert set(rows) == set(DISPATCHERS) and all(r["instances"] == 100 for r in rows.values())

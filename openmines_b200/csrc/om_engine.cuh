@@ -948,6 +948,7 @@ struct Sim {
             int site = decide(kind, i);
             int nmax = (kind == OM_ORDER_HAUL) ? D : L;
             if (site < 0 || site >= nmax) {
+              if (site >= 0) count_order(kind, site);   // the wrapper logs the order before truck.py indexes the site list
               fail(OM_IERR_BAD_ORDER);
               if (rel_u >= 0) { file_release(rel_u, rel_key); rel_u = -1; }
               ph = XP_DONE;

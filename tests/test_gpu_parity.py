@@ -164,3 +164,25 @@ def test_stats_kernel_matches_host_mirror(north_pit):
     assert np.allclose(got, want, rtol=1e-12, atol=0)
     rows = parallel.describe(got)
     assert set(rows) == set(DISPATCHERS) and all(r["instances"] == 100 for r in rows.values())
+
+
+def test_scaled_mine_c5_vs_oracle():
+    """BASELINE configs[4] shape (500 trucks, 20 load sites, 10 dump sites, 420 roads): det SQ / SPTF /
+    Random bit-exact vs the oracle, and a tape replay of a live SQ oracle run."""
+    from oracle import des_oracle as do
+    from openmines_b200.synthetic import scaled_mine
+    cfg = scaled_mine()
+    cases = [("SQDispatcher", "det", 0), ("SPTFDispatcher", "det", 0), ("RandomDispatcher", "det", 5)]
+    oracles = [do.run_oracle(cfg, d, m, seed=s) for d, m, s in cases]
+    mine = _mine(cfg, len(cases), jam_capacity=512)
+    mine.reset([d for d, _, _ in cases], seeds=[s for _, _, s in cases], rng_mode="det")
+    res = mine.run(trace_capacity=16384, site_ticks=True, order_capacity=8192)
+    for i, (d, m, s) in enumerate(cases):
+        diffs = engine_vs_ref(oracles[i], mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s: %s" % (d, diffs[:5])
+    live = do.run_oracle(cfg, "SQDispatcher", "live", seed=1)
+    mine = _mine(cfg, 1, jam_capacity=512)
+    mine.reset("SQDispatcher", rng_mode="tape", tapes=[live.tape])
+    res = mine.run(trace_capacity=32768, site_ticks=True, order_capacity=8192)
+    diffs = engine_vs_ref(live, mine, res, 0)
+    assert not diffs, diffs[:5]

@@ -490,3 +490,72 @@ def load_config(path):
     import json
     with open(path, "r", encoding="utf-8") as fh:
         return json.load(fh)
+
+
+# ----------------------------------------------------------------------------------------
+# RL surface of the unmodified reference (RLDispatcher + Mine.start_rl + preprocess_observation)
+# ----------------------------------------------------------------------------------------
+def run_reference_rl(config, policy, mode="det", seed=0, tape=None, teacher="ShortestTripDispatcher",
+                     sim_time=None, ref_root=REF_ROOT_DEFAULT):
+    """Drive the reference's own RL loop: ``prepare_env`` (utils/rl_env.py:29-104) runs in a thread exactly
+    as ``ThreadMineEnv.reset`` starts it (mine_env.py:302-316); this thread plays the agent.
+    policy(step_index, kind_code, obs194, n_choices) -> int.  Returns the per-step log."""
+    import queue
+    import threading
+    load_reference(ref_root)
+    for name in ("asyncore", "docutils", "docutils.nodes"):      # stale imports at rl_dispatch.py:6,11
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except ImportError:
+                sys.modules[name] = mock.MagicMock(name=name)
+    import openmines.src.utils.rl_env as rl_env
+    from openmines.src.utils.feature_processing import preprocess_observation
+    cfg = dict(config)
+    if sim_time is not None:
+        cfg["sim_time"] = sim_time
+    cfg["sug_dispatcher"] = teacher
+    rng = RngControl(mode, seed, tape)
+    obs_q, act_q = queue.Queue(), queue.Queue()
+    err = {}
+
+    def target():
+        try:
+            rl_env.prepare_env(obs_q, act_q, cfg, "dense", cfg["sim_time"], False, False, None)
+        except BaseException as e:   # surface crashes of the simulation thread
+            err["e"] = e
+            obs_q.put(None)
+
+    log = []
+    kinds = {"init": 0, "haul": 1, "unhaul": 2}
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="om_ref_rl_")
+    os.chdir(tmp)
+    try:
+        with rng, contextlib.redirect_stdout(open(os.devnull, "w")):
+            th = threading.Thread(target=target, daemon=True)
+            th.start()
+            while True:
+                out = obs_q.get(timeout=120)
+                if out is None:
+                    raise err["e"]
+                ob = out["ob"]
+                obs = preprocess_observation(ob, cfg["sim_time"])
+                done = bool(out["done"])
+                kind = kinds[ob["event_name"]]
+                n = len(cfg["dump_sites"]) if kind == 1 else len(cfg["load_sites"])
+                rec = {"obs": obs, "reward": float(out["reward"]), "done": done,
+                       "kind": -1 if done else kind, "sug_action": -1 if done else int(out["info"]["sug_action"]),
+                       "time": float(out["info"]["time"]), "produce_tons": float(out["info"]["produce_tons"])}
+                if done:
+                    rec["action"] = -1
+                    log.append(rec)
+                    break
+                action = int(policy(len(log), kind, obs, n))
+                rec["action"] = action
+                log.append(rec)
+                act_q.put(action)
+            th.join(timeout=60)
+    finally:
+        os.chdir(cwd)
+    return log, rng.tape()

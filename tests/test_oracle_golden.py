@@ -156,3 +156,29 @@ def test_oracle_sq_keyerror_is_reported(short_mine):
     cfg = {**cfg, "road": {**cfg["road"], "charging_to_load_road_matrix": [1.25, 1.25, 1.25]}}   # 3.0 min legs
     o = do.run_oracle(cfg, "SQDispatcher", "det")
     assert o.error is None or "KeyError" in o.error
+
+
+@pytest.mark.parametrize("name", ["rl_north_pit_mine_det_s0_ShortestTripDispatcher_p1",
+                                  "rl_north_pit_mine_live_s21_ShortestTripDispatcher_p2",
+                                  "rl_north_pit_mine_live_s22_SQDispatcher_p3"])
+def test_rl_oracle_matches_reference_golden(name, north_pit):
+    """The RL restatement (observation float32[194], dense reward, teacher suggestion, final step) is
+    bit-identical to the reference's RLDispatcher / start_rl / preprocess_observation."""
+    import os
+    from helpers import GOLDEN
+    from oracle import rl_oracle as ro
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    mode, seed, teacher, pseed = str(z["mode"]), int(z["seed"]), str(z["teacher"]), int(z["policy_seed"])
+    if mode == "live":   # replay the reference's own draws
+        r = ro.run_rl_oracle(north_pit, ro.keyed_policy(pseed), "replay", tape=(z["tape_sites"], z["tape_values"]),
+                             teacher=teacher)
+    else:
+        r = ro.run_rl_oracle(north_pit, ro.keyed_policy(pseed), mode, seed=seed, teacher=teacher)
+    log = r.rl_log
+    assert len(log) == len(z["reward"])
+    assert np.array_equal(np.stack([x["obs"] for x in log]), z["obs"])
+    assert np.array_equal(np.array([x["reward"] for x in log]), z["reward"])
+    assert np.array_equal(np.array([x["kind"] for x in log]), z["kind"])
+    assert np.array_equal(np.array([x["sug_action"] for x in log]), z["sug_action"])
+    assert np.array_equal(np.array([x["action"] for x in log]), z["action"])
+    assert np.array_equal(np.array([x["done"] for x in log]), z["done"])

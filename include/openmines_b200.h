@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OM_ABI_VERSION 1
+#define OM_ABI_VERSION 2
 
 /* error codes */
 #define OM_OK 0
@@ -42,6 +42,7 @@ extern "C" {
 #define OM_DISP_FIXEDGROUP 3  /* fixed_group_dispatcher.py:21-110 */
 #define OM_DISP_SPTF 4        /* sptf_dispatcher.py:21-61 */
 #define OM_DISP_SQ 5          /* sq_dispatcher.py:18-100 */
+#define OM_DISP_SHORTESTTRIP 6 /* shortest_trip_dispatcher.py:12-84 (default teacher of the gym env) */
 #define OM_DISP_EXTERNAL 255  /* decisions supplied by the host through om_step (rl_dispatch.py:58-123) */
 
 /* RNG modes */
@@ -93,6 +94,8 @@ typedef struct OmConfig {
   const int32_t* nearest_haul;    /* [L]  argmin l2d[i,:], nearest_dispatcher.py:42-45 */
   const int32_t* nearest_back;    /* [D]  argmin d2l[:,j], nearest_dispatcher.py:64-66 */
   const int32_t* fixed_group;     /* [T]  fixed_group_dispatcher.py:21-56 (0 when unassigned) */
+  const double* shovel_rate;      /* [S]  shovel_tons / cycle_time, load_site.py:182-185 */
+  const double* site_productivity; /* [L] sum of shovel_rate per load site, load_site.py:182-184 */
   /* stochastic-event parameters (reference defaults are hard-coded where cited) */
   double road_lambda;        /* road.py:38 / config road_event_params */
   double road_mu;            /* road.py:39 */
@@ -164,7 +167,7 @@ typedef struct OmOutputs {
 typedef struct OmStateLayout {
   uint32_t total_bytes;
   uint32_t hdr;
-  uint32_t t_time, t_load, t_jstart, t_prejam, t_lastbrk, t_repair, t_total, t_cycle, t_dist; /* f64 */
+  uint32_t t_time, t_load, t_jstart, t_prejam, t_lastbrk, t_repair, t_total, t_cycle, t_dist, t_since; /* f64 */
   uint32_t t_key, t_rng;                                                                     /* u32 */
   uint32_t t_svc, t_epoch, t_next, t_unit;                                                   /* u16 */
   uint32_t t_phase, t_status, t_cur, t_tgt;                                                  /* u8  */
@@ -176,6 +179,7 @@ typedef struct OmStateLayout {
   uint32_t j_pos, j_start, j_end;                                                            /* f64 [jam_capacity] */
   uint32_t j_road;                                                                           /* u16 [jam_capacity] */
   uint32_t s_qtotal, s_coming;                                                               /* u16 [L+D] */
+  uint32_t s_tons, s_cap, s_ability;                                                         /* f64 [L+D] minute-sampled */
   uint32_t scratch;                                                                          /* f64 [max(U, 32)] */
 } OmStateLayout;
 
@@ -209,6 +213,28 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
  * sum decisions, sum jams, sum road repairs, sum truck repairs, sum unrepairable, n_err, ...}. */
 int om_stats_reduce(OmHandle h, const OmSummary* summary, const int32_t* dispatcher,
                     double* stats_out, void* stream);
+
+/* Batched gym-style step (replaces RLDispatcher._step + Mine.start_rl + preprocess_observation:
+ * rl_dispatch.py:58-123,194-509, mine.py:397-476, utils/feature_processing.py:3-75).  Instances reset with
+ * OM_DISP_EXTERNAL pause at every dispatch decision.  One call = apply `actions[n]` to instance n's pending
+ * order (ignored when none is pending: first call after om_reset), advance to the next decision point (or to
+ * `until`), and emit that decision's observation / the reward of the previous decision.  All device pointers;
+ * obs rows are written only when a new decision is pending (on the final step the reference re-sends the
+ * previous observation, so the row is left untouched). */
+typedef struct OmStepIO {
+  const int32_t* actions; /* [N] in */
+  float* obs;             /* [N * obs_dim] */
+  double* reward;         /* [N] dense reward (rl_dispatch.py:194-308), final bonus on the last step */
+  uint8_t* done;          /* [N] 1 on the final step and afterwards */
+  int32_t* order_kind;    /* [N] OM_ORDER_* of the pending decision, -1 when done */
+  int32_t* truck;         /* [N] truck asking, -1 when done */
+  int32_t* sug_action;    /* [N] teacher's decision (info["sug_action"]), -1 when done / no teacher */
+  double* info;           /* [N * 4] produce_tons, time, delta_time, reserved */
+  int32_t teacher;        /* OM_DISP_* of the teacher (0..6), or -1 */
+  int32_t reserved;
+} OmStepIO;
+int om_obs_dim(OmHandle h, int32_t* dim);
+int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* stream);
 
 /* Kernel launch geometry actually used by om_run (for bench.py's launch accounting). */
 int om_launch_info(OmHandle h, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* warps_per_cta);

@@ -65,12 +65,14 @@ def load():
     lib.om_reset.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp]
     lib.om_run.argtypes = [vp, dbl, vp, vp, vp]
     lib.om_stats_reduce.argtypes = [vp, vp, vp, vp, vp]
+    lib.om_obs_dim.argtypes = [vp, ctypes.POINTER(i32)]
+    lib.om_step.argtypes = [vp, dbl, vp, vp, vp]
     for f in ("om_create", "om_destroy", "om_state_bytes", "om_state_layout", "om_launch_info", "om_reset",
-              "om_run", "om_stats_reduce"):
+              "om_run", "om_stats_reduce", "om_obs_dim", "om_step"):
         getattr(lib, f).restype = ctypes.c_int
     _lib = lib
     return lib
 
 
 EXPORTED_SYMBOLS = ["om_create", "om_destroy", "om_last_error", "om_state_bytes", "om_state_layout", "om_reset",
-                    "om_run", "om_stats_reduce", "om_launch_info"]
+                    "om_run", "om_stats_reduce", "om_launch_info", "om_obs_dim", "om_step"]

@@ -21,7 +21,7 @@ import math
 
 import numpy as np
 
-OM_ABI_VERSION = 1
+OM_ABI_VERSION = 2
 
 ROAD_EVENT_DEFAULTS = {            # road.py:37-43
     "lambda_repair": 1 / (60 * 2),
@@ -65,6 +65,7 @@ class OmConfigStruct(ctypes.Structure):
         ("truck_capacity", _dp), ("truck_speed", _dp), ("truck_type", _ip), ("site_unit_begin", _ip),
         ("dumper_cycle", _dp), ("road_distance", _dp), ("load_time", _dp), ("sptf_cost", _dp),
         ("jam_chance", _dp), ("nearest_haul", _ip), ("nearest_back", _ip), ("fixed_group", _ip),
+        ("shovel_rate", _dp), ("site_productivity", _dp),
         ("road_lambda", ctypes.c_double), ("road_mu", ctypes.c_double), ("road_sigma", ctypes.c_double),
         ("detour_mu", ctypes.c_double), ("detour_sigma", ctypes.c_double), ("breakdown_mean", ctypes.c_double),
         ("repair_mu", ctypes.c_double), ("repair_sigma", ctypes.c_double), ("unrepairable_mean", ctypes.c_double),
@@ -86,7 +87,7 @@ class PackedConfig:
         s.nearest_init = int(self.nearest_init)
         dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
         for name in ("truck_capacity", "truck_speed", "dumper_cycle", "road_distance", "load_time", "sptf_cost",
-                     "jam_chance"):
+                     "jam_chance", "shovel_rate", "site_productivity"):
             a = np.ascontiguousarray(getattr(self, name), dtype=np.float64)
             setattr(self, name, a)
             setattr(s, name, a.ctypes.data_as(dp))
@@ -196,6 +197,8 @@ def pack_config(config, jam_capacity=64, sum_mode="neumaier"):
     for s in range(L):
         prod.append(py_sum([sh_tons[u] / sh_cycle[u] for u in range(ubeg[s], ubeg[s + 1])], sum_mode))
     pc.load_site_productivity = prod
+    pc.site_productivity = np.array(prod, dtype=np.float64)
+    pc.shovel_rate = np.array([sh_tons[u] / sh_cycle[u] for u in range(pc.S)], dtype=np.float64)
     sc = np.zeros((pc.n_types, L), dtype=np.float64)
     for k, cap in enumerate(type_keys):
         for s in range(L):

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
       for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
     }
     __syncwarp();
-    Sim<RNG, TRACE> s(sm, p, lane, (long long)inst);
+    Sim<RNG, TRACE, false> s(sm, p, lane, (long long)inst);
     s.load_hdr(p);
     s.run(p.until);
     s.store_hdr(p);
@@ -59,6 +59,42 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
         p.out.summary[inst] = r;
       }
     }
+    __syncwarp();
+    {
+      uint4* dst = (uint4*)g;
+      const uint4* src = (const uint4*)sm;
+#pragma unroll 2
+      for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
+    }
+    __syncwarp();
+  }
+}
+
+// Batched gym-style step: one warp per env; the state blob round-trips HBM every step (this kernel IS
+// HBM-bound: 2 * S_state + obs row per env step).
+template <int RNG>
+__global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_step_kernel(const __grid_constant__ RunParams p) {
+  extern __shared__ __align__(16) unsigned char om_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* sm = om_smem + (size_t)warp * p.ly.total_bytes;
+  const uint32_t n16 = p.ly.total_bytes >> 4;
+  while (true) {
+    unsigned long long inst = 0;
+    if (lane == 0) inst = atomicAdd(p.counter, 1ull);
+    inst = __shfl_sync(OM_FULL, inst, 0);
+    if (inst >= (unsigned long long)p.n_instances) break;
+    unsigned char* g = p.state + (size_t)inst * p.ly.total_bytes;
+    {
+      const uint4* src = (const uint4*)g;
+      uint4* dst = (uint4*)sm;
+#pragma unroll 2
+      for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
+    }
+    __syncwarp();
+    Sim<RNG, false, true> s(sm, p, lane, (long long)inst);
+    s.load_hdr(p);
+    s.rl_step(p);
+    s.store_hdr(p);
     __syncwarp();
     {
       uint4* dst = (uint4*)g;
@@ -150,9 +186,11 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly) {
   ly.t_time = take(off, 8, T); ly.t_load = take(off, 8, T); ly.t_jstart = take(off, 8, T);
   ly.t_prejam = take(off, 8, T); ly.t_lastbrk = take(off, 8, T); ly.t_repair = take(off, 8, T);
   ly.t_total = take(off, 8, T); ly.t_cycle = take(off, 8, T); ly.t_dist = take(off, 8, T);
+  ly.t_since = take(off, 8, T);
   ly.u_rel_time = take(off, 8, U); ly.u_last_start = take(off, 8, U); ly.u_last_done = take(off, 8, U);
   ly.u_tons = take(off, 8, U); ly.u_lastbrk = take(off, 8, S);
   ly.r_repair_end = take(off, 8, R);
+  ly.s_tons = take(off, 8, NS); ly.s_cap = take(off, 8, NS); ly.s_ability = take(off, 8, NS);
   ly.j_pos = take(off, 8, J); ly.j_start = take(off, 8, J); ly.j_end = take(off, 8, J);
   size_t nscr = U;
   if (nscr < (R + 1) / 2) nscr = (R + 1) / 2;
@@ -209,7 +247,7 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
   UP(ubeg, site_unit_begin, L + D + 1); UP(dcycle, dumper_cycle, M); UP(rdist, road_distance, c.R);
   UP(load_time, load_time, (size_t)c.NT * S); UP(sptf_cost, sptf_cost, (size_t)c.NT * L);
   UP(jam_chance, jam_chance, T + 1); UP(near_haul, nearest_haul, L); UP(near_back, nearest_back, D);
-  UP(fixed_group, fixed_group, T);
+  UP(fixed_group, fixed_group, T); UP(shovel_rate, shovel_rate, S); UP(site_prod, site_productivity, L);
 #undef UP
   if (rc == OM_OK) {
     void* d = nullptr;
@@ -236,6 +274,12 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
                             (const void*)om_run_kernel<OM_RNG_PHILOX, true>, (const void*)om_run_kernel<OM_RNG_TAPE, true>};
       for (int i = 0; i < 6 && rc == OM_OK; ++i) {
         e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
+        if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+      }
+      const void* sfns[3] = {(const void*)om_step_kernel<OM_RNG_DET>, (const void*)om_step_kernel<OM_RNG_PHILOX>,
+                             (const void*)om_step_kernel<OM_RNG_TAPE>};
+      for (int i = 0; i < 3 && rc == OM_OK; ++i) {
+        e = cudaFuncSetAttribute(sfns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
         if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
       }
     }
@@ -321,6 +365,37 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
     default: OM_LAUNCH(OM_RNG_TAPE); break;
   }
 #undef OM_LAUNCH
+  CK(cudaGetLastError());
+  return OM_OK;
+}
+
+int om_obs_dim(OmHandle h, int32_t* dim) {
+  if (!h || !dim) return OM_E_INVALID;
+  const DevCfg& c = h->c;
+  int C = c.L > c.D ? c.L : c.D;
+  *dim = 6 + (1 + c.NS) + 2 + 3 * C + 2 * c.R + 5 * c.NS;
+  return OM_OK;
+}
+
+int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* stream) {
+  if (!h || !state || !io || !io->obs) return set_err(h, OM_E_INVALID, "om_step: null argument");
+  CK(cudaSetDevice(h->device));
+  RunParams p;
+  memset(&p, 0, sizeof(p));
+  p.c = h->c; p.ly = h->ly;
+  p.c.sim_time = until;
+  p.io = *io;
+  om_obs_dim(h, &p.obs_dim);
+  p.state = (unsigned char*)state;
+  p.tape_values = h->tape_values; p.tape_sites = h->tape_sites; p.tape_offsets = h->tape_offsets;
+  p.counter = h->counter; p.n_instances = h->n; p.until = until;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+  switch (h->rng_mode) {
+    case OM_RNG_DET: om_step_kernel<OM_RNG_DET><<<h->grid, h->block, h->smem, st>>>(p); break;
+    case OM_RNG_PHILOX: om_step_kernel<OM_RNG_PHILOX><<<h->grid, h->block, h->smem, st>>>(p); break;
+    default: om_step_kernel<OM_RNG_TAPE><<<h->grid, h->block, h->smem, st>>>(p); break;
+  }
   CK(cudaGetLastError());
   return OM_OK;
 }

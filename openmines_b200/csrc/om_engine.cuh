@@ -73,6 +73,9 @@ struct DevCfg {
   const int32_t* near_haul;
   const int32_t* near_back;
   const int32_t* fixed_group;
+  const double* shovel_rate;
+  const double* site_prod;
+  double sim_time;
   double road_lambda, road_mu, road_sigma, detour_mu, detour_sigma;
   double breakdown_mean, repair_mu, repair_sigma, unrepairable_mean, maint_mean, maint_mu, maint_sigma;
   double jam_sd, jam_scale;
@@ -99,9 +102,15 @@ struct InstHdr {
   int32_t pending_kind;
   uint32_t n_ticks;
   uint32_t n_rel;       // pending Release entries in the unit table
+  // RL step surface (rl_dispatch.py): window start, last sampled production, closed-interval accumulators
+  double rl_last_time;
+  double rl_last_prod;
+  double acc_wait, acc_shovel, acc_dumper, acc_move, acc_jam;
+  uint32_t finished;
+  uint32_t rl_steps;
 };
-static_assert(sizeof(InstHdr) == 120, "InstHdr size");
-#define OM_HDR_BYTES 128
+static_assert(sizeof(InstHdr) == 184, "InstHdr size");
+#define OM_HDR_BYTES 192
 
 struct RunParams {
   DevCfg c;
@@ -114,6 +123,8 @@ struct RunParams {
   unsigned long long* counter; // dynamic instance scheduler
   long long n_instances;
   double until;
+  OmStepIO io;      // om_step only
+  int obs_dim;
 };
 
 __device__ __forceinline__ double om_inf() { return __longlong_as_double(0x7FF0000000000000LL); }
@@ -144,7 +155,7 @@ struct PySum {
   }
 };
 
-template <int RNG, bool TRACE>
+template <int RNG, bool TRACE, bool RL>
 struct Sim {
   unsigned char* sm;
   const DevCfg& c;
@@ -163,6 +174,7 @@ struct Sim {
   const double* tape_v;
   const uint8_t* tape_s;
   Philox4 ordw;   // words of the current order's Philox call (PHILOX mode)
+  double rl_last, rl_last_prod, acc_wait, acc_shovel, acc_dumper, acc_move, acc_jam;   // RL only
 
   __device__ __forceinline__ Sim(unsigned char* sm_, const RunParams& p, int lane_, long long inst_)
       : sm(sm_), c(p.c), ly(p.ly), out(p.out), lane(lane_), inst(inst_) {}
@@ -184,6 +196,10 @@ struct Sim {
     n_jams = h->n_jams; n_road_rep = h->n_road_rep; n_brk = h->n_brk; n_unrep = h->n_unrep;
     jam_count = h->jam_count; err = h->err; trace_count = h->trace_count; order_count = h->order_count;
     n_ticks = h->n_ticks; n_rel = h->n_rel;
+    if (RL) {
+      rl_last = h->rl_last_time; rl_last_prod = h->rl_last_prod; acc_wait = h->acc_wait; acc_shovel = h->acc_shovel;
+      acc_dumper = h->acc_dumper; acc_move = h->acc_move; acc_jam = h->acc_jam;
+    }
     tape_pos = h->tape_pos; tape_end = 0; tape_v = p.tape_values; tape_s = p.tape_sites;
     if (RNG == OM_RNG_TAPE) {
       tape_pos += (unsigned long long)p.tape_offsets[inst];   // hdr stores the position relative to the instance's tape
@@ -198,6 +214,10 @@ struct Sim {
     h->n_jams = n_jams; h->n_road_rep = n_road_rep; h->n_brk = n_brk; h->n_unrep = n_unrep;
     h->jam_count = jam_count; h->err = err; h->trace_count = trace_count; h->order_count = order_count;
     h->n_ticks = n_ticks; h->n_rel = n_rel;
+    if (RL) {
+      h->rl_last_time = rl_last; h->rl_last_prod = rl_last_prod; h->acc_wait = acc_wait; h->acc_shovel = acc_shovel;
+      h->acc_dumper = acc_dumper; h->acc_move = acc_move; h->acc_jam = acc_jam;
+    }
     h->tape_pos = (RNG == OM_RNG_TAPE) ? tape_pos - (unsigned long long)p.tape_offsets[inst] : 0ull;
   }
 
@@ -270,6 +290,15 @@ struct Sim {
     U32A(t_key, i) = prio | seq;
     seq++;
     U8A(t_phase, i) = phase;
+  }
+  // RL reward bookkeeping: a truck leaves a timed state (wait shovel / get shovel / get dumper / move record);
+  // add the part of [t_since, now] that lies in the current reward window (rl_dispatch.py:221-273)
+  __device__ __forceinline__ void rl_close(double& acc, int i) {
+    if (RL) {
+      double st = F64(t_since, i);
+      double lo = (st > rl_last) ? st : rl_last;
+      if (lo < now) acc += now - lo;
+    }
   }
   __device__ __forceinline__ void fail(uint32_t code) {
     if (err == OM_IERR_NONE || err == OM_IERR_TRACE_OVERFLOW) err = code;
@@ -501,6 +530,49 @@ struct Sim {
         r = (int)(__reduce_min_sync(OM_FULL, v) & 0xFFu);
         break;
       }
+      case OM_DISP_SHORTESTTRIP: {
+        // shortest_trip_dispatcher.py:12-84: earliest expected finish of (travel | queue + on-road trucks) + service
+        const double v = __ldg(&c.speed[i]);
+        const int cur = U8A(t_cur, i);
+        double val = om_inf();
+        if (kind == OM_ORDER_HAUL) {
+          unit_est_all(false);
+          if (lane < D) {
+            int site = L + lane, tgt = 1 + site;
+            int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
+            double dt0 = __ldg(&c.dcycle[ub - c.S]);
+            int cnt = 0;
+#pragma unroll 1
+            for (int o = 0; o < c.T; ++o)
+              cnt += (U8A(t_status, o) == ST_MOVING && U8A(t_cur, o) == cur && U8A(t_tgt, o) == tgt) ? 1 : 0;
+            double reach = now + om_ddiv(60.0 * __ldg(&c.rdist[road_id(cur, tgt)]), v);
+            double avail = (now + site_est(site)) + om_ddiv((double)cnt, (double)(ue - ub)) * dt0;
+            double service = (avail > reach) ? avail : reach;      // np.maximum
+            val = (service + dt0) - now;
+          }
+          r = argmin_lanes(val, D);
+        } else {
+          unit_est_all(true);
+          if (lane < L) {
+            int tgt = 1 + lane;
+            int ub = __ldg(&c.ubeg[lane]), ue = __ldg(&c.ubeg[lane + 1]);
+            double capsum = 0.0;                                   // trucks on the charging-site road, also for back orders (:71)
+#pragma unroll 1
+            for (int o = 0; o < c.T; ++o)
+              if (U8A(t_status, o) == ST_MOVING && U8A(t_cur, o) == 0 && U8A(t_tgt, o) == tgt) capsum += __ldg(&c.cap[o]);
+            double prod = __ldg(&c.site_prod[lane]);
+            double dist = __ldg(&c.rdist[road_id(cur, tgt)]);
+            double reach = now + om_ddiv(60.0 * dist, v);
+            double avail = (now + site_est(lane)) + om_ddiv(capsum, prod);
+            double service = (avail > reach) ? avail : reach;
+            double loading = om_ddiv(__ldg(&c.cap[i]), om_ddiv(prod, (double)(ue - ub)));
+            val = (service + loading) - now;
+          }
+          r = argmin_lanes(val, L);
+        }
+        __syncwarp();
+        break;
+      }
       default:
         fail(OM_IERR_BAD_ORDER);
         return -1;
@@ -595,6 +667,7 @@ struct Sim {
     uint8_t kind = (cur > c.L) ? K_MOVE_UNHAUL : (cur == 0 ? K_MOVE_INIT : K_MOVE_HAUL);
     int idx = (tgt <= c.L) ? tgt - 1 : tgt - 1 - c.L;
     emit(kind, (uint32_t)i, (uint32_t)idx, 0, now + duration + pre, dist);
+    if (RL) F64(t_since, i) = now;
     U8A(t_status, i) = ST_MOVING;
     sched_truck(i, now + (duration + pre), OM_KEY_NORMAL, PH_MOVE_ARRIVE);
   }
@@ -607,6 +680,10 @@ struct Sim {
       uint32_t w = 0;
       #pragma unroll 1
       for (uint32_t j = 0; j < jam_count; ++j) {
+        if (RL && !(F64(j_end, j) >= now)) {
+          double st = F64(j_start, j), lo = (st > rl_last) ? st : rl_last;
+          if (lo < F64(j_end, j)) acc_jam += F64(j_end, j) - lo;
+        }
         if (F64(j_end, j) >= now) {
           if (w != j) {
             F64(j_pos, w) = F64(j_pos, j); F64(j_start, w) = F64(j_start, j);
@@ -644,6 +721,24 @@ struct Sim {
       }
       site_tons = ps.result();
       U16A(s_qtotal, lane) = (uint16_t)qtot;
+      if (RL) {
+        // minute-sampled values the observation reads (load_site.py:175-185, dump_site.py:69-78)
+        F64(s_tons, lane) = site_tons;
+        if (lane < L) {
+          PySum pa; pa.init();
+#pragma unroll 1
+          for (int u = ub; u < ue; ++u) pa.add(__ldg(&c.shovel_rate[u]) * (U8A(u_repair, u) ? 0.0 : 1.0), neu);
+          double prod = __ldg(&c.site_prod[lane]);
+          F64(s_cap, lane) = prod;
+          F64(s_ability, lane) = om_ddiv(pa.result(), prod);
+        } else {
+          PySum pd; pd.init();
+#pragma unroll 1
+          for (int u = ub; u < ue; ++u) pd.add(om_ddiv(F64(u_tons, u), __ldg(&c.dcycle[u - c.S])), neu);
+          F64(s_cap, lane) = pd.result();
+          F64(s_ability, lane) = 1.0;
+        }
+      }
     }
     tick_k = k;
     // (2) mine KPI sample (mine.py:61-119)
@@ -1007,6 +1102,7 @@ struct Sim {
             break;
           }
           case PH_MOVE_ARRIVE:                                         // truck.py:211-218
+            rl_close(acc_move, i);
             U8A(t_cur, i) = U8A(t_tgt, i);
             F64(t_prejam, i) = 0.0;
             if (chain) { seq++; ph = PH_MOVE_RET; break; }             // Process(move) event
@@ -1036,6 +1132,7 @@ struct Sim {
             int qi = me ? 0 : (int)U16A(u_qlen, u) - 1;
             if (cur <= L) {
               emit(K_WAIT_SHOVEL, (uint32_t)i, (uint32_t)u, (uint32_t)qi, 0.0, 0.0);
+              if (RL) F64(t_since, i) = now;
               U8A(t_status, i) = ST_WAIT_SHOVEL;
             } else {
               emit(K_WAIT_DUMPER, (uint32_t)i, (uint32_t)(u - S), 0, 0.0, 0.0);
@@ -1044,6 +1141,8 @@ struct Sim {
             break;
           }
           case PH_LOAD_GRANTED:                                        // truck.py:342-350
+            rl_close(acc_wait, i);
+            if (RL) F64(t_since, i) = now;
             emit(K_GET_SHOVEL, (uint32_t)i, (uint32_t)U16A(t_unit, i), 0, 0.0, 0.0);
             seq++;                                                     // env.process(load): Initialize URGENT
             if (inl) { ph = PH_LOAD_BEGIN; break; }
@@ -1080,6 +1179,7 @@ struct Sim {
             break;
           }
           case PH_LOAD_RET: {                                          // truck.py:352-370
+            rl_close(acc_shovel, i);
             ph = XP_AFTER_LOAD;
             if (RNG != OM_RNG_DET) {
               int u = U16A(t_unit, i);
@@ -1113,6 +1213,7 @@ struct Sim {
             break;
           }
           case PH_DUMP_GRANTED:                                        // truck.py:422-429
+            if (RL) F64(t_since, i) = now;
             emit(K_GET_DUMPER, (uint32_t)i, (uint32_t)(U16A(t_unit, i) - S), 0, 0.0, 0.0);
             seq++;
             if (inl) { ph = PH_DUMP_BEGIN; break; }
@@ -1144,6 +1245,7 @@ struct Sim {
             break;
           }
           case PH_DUMP_RET: {                                          // truck.py:431-441
+            rl_close(acc_dumper, i);
             int u = U16A(t_unit, i);
             rel_key = release(u);
             if (chain) rel_u = u; else file_release(u, rel_key);
@@ -1163,6 +1265,204 @@ struct Sim {
     InstHdr* h = (InstHdr*)(sm + ly.hdr);
     h->pending_truck = pend_truck;
     h->pending_kind = pend_kind;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // RL step surface: dense reward (rl_dispatch.py:194-308), observation float32[obs_dim]
+  // (rl_dispatch.py:309-509 + utils/feature_processing.py:3-75), teacher suggestion (:169-184)
+  // ---------------------------------------------------------------------------------------------
+  __device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(OM_FULL, v, o);
+    return v;
+  }
+
+  __device__ __forceinline__ double rl_reward(bool final_step) {
+    const int T = c.T;
+    double w = 0.0, sh = 0.0, du = 0.0, mv = 0.0, jm = 0.0;
+#pragma unroll 1
+    for (int i = lane; i < T; i += 32) {           // intervals still open at this decision
+      int ph = U8A(t_phase, i), cur = U8A(t_cur, i);
+      double st = F64(t_since, i);
+      double lo = (st > rl_last) ? st : rl_last;
+      double part = (lo < now) ? (now - lo) : 0.0;
+      if ((ph == PH_WAITING || ph == PH_LOAD_GRANTED) && cur >= 1 && cur <= c.L) w += part;
+      else if (ph == PH_LOAD_BEGIN || ph == PH_LOAD_DONE || ph == PH_LOAD_RET) sh += part;
+      else if (ph == PH_DUMP_BEGIN || ph == PH_DUMP_DONE || ph == PH_DUMP_RET) du += part;
+      else if (ph == PH_MOVE_ARRIVE) mv += part;
+    }
+#pragma unroll 1
+    for (uint32_t j = lane; j < jam_count; j += 32) {
+      double st = F64(j_start, j), en = F64(j_end, j);
+      double lo = (st > rl_last) ? st : rl_last, hi = (en < now) ? en : now;
+      if (lo < hi) jm += hi - lo;
+    }
+    w = acc_wait + warp_sum(w);
+    double service = (acc_shovel + warp_sum(sh)) + (acc_dumper + warp_sum(du));
+    mv = acc_move + warp_sum(mv);
+    jm = acc_jam + warp_sum(jm);
+    double final_reward = 0.0;
+    if (final_step && now != 0.0) {
+      double ft = rl_last_prod - 10000.0;
+      if (ft > 0.0) final_reward = 0.5 * ft;
+    }
+    double delta = reported_tons - rl_last_prod;   // mine.produce_tons is the minute-sampled value
+    rl_last_prod = reported_tons;
+    double reward = -0.1 * w + -0.05 * service + -0.05 * jm + -0.01 * mv + 5.0 * log(delta + 1.0) + final_reward;
+    double dt = now - rl_last;
+    if (dt > 0.0) reward += 0.1 * om_ddiv(delta, dt + 1e-6);
+    acc_wait = acc_shovel = acc_dumper = acc_move = acc_jam = 0.0;
+    return reward;
+  }
+
+  // Observation of the pending decision (truck i, order kind).  Layout generalises the reference's
+  // L = D = 5 vector: C = max(L, D) candidate slots (zero padded), NS = L + D, R roads.
+  __device__ __forceinline__ void rl_observation(int i, int kind, float* ob) {
+    const int T = c.T, L = c.L, D = c.D, NS = c.NS, R = c.R;
+    const int C = L > D ? L : D;
+    const int o1 = 6, o2 = o1 + 1 + NS, o3 = o2 + 2, o4 = o3 + C, o5 = o4 + C, o6 = o5 + R, o7 = o6 + R,
+              o8 = o7 + C, o9 = o8 + NS, o10 = o9 + NS, o11 = o10 + NS, o12 = o11 + NS;
+    const int cur = U8A(t_cur, i);
+    const double tn = (double)T + 1e-8;
+    unit_est_all(true);                             // dispatcher.update_mine (dispatcher.py:24-33)
+    unit_est_all(false);
+    if (lane == 0) {
+      ob[0] = kind == OM_ORDER_INIT ? 1.f : 0.f; ob[1] = kind == OM_ORDER_HAUL ? 1.f : 0.f;
+      ob[2] = kind == OM_ORDER_BACK ? 1.f : 0.f;
+      ob[3] = (float)(now - rl_last);
+      double time_now = om_ddiv(now, c.sim_time);
+      ob[4] = (float)time_now; ob[5] = (float)(1.0 - time_now);
+      ob[o2] = (float)log(F64(t_load, i) + 1.0);
+      ob[o2 + 1] = (float)log(F64(t_cycle, i) + 1.0);
+    }
+#pragma unroll 1
+    for (int q = lane; q < 1 + NS; q += 32) ob[o1 + q] = (q == cur) ? 1.f : 0.f;
+    // candidate roads from the current location
+    const int ncand = (kind == OM_ORDER_HAUL) ? D : L;
+#pragma unroll 1
+    for (int q = lane; q < C; q += 32) {
+      float tt = 0.f, tc = 0.f, sw = 0.f;
+      if (q < ncand) {
+        int tgt = (kind == OM_ORDER_HAUL) ? 1 + L + q : 1 + q;
+        int site = tgt - 1;
+        int pair_cnt = 0, on_cnt = 0;
+        double capsum = 0.0;
+#pragma unroll 1
+        for (int o = 0; o < T; ++o) {
+          if (U8A(t_cur, o) == cur && U8A(t_tgt, o) == tgt) {          // mine.update_road_status pair counts
+            pair_cnt++;
+            if (U8A(t_status, o) == ST_MOVING) { on_cnt++; capsum += __ldg(&c.cap[o]); }   // Road.truck_on_road
+          }
+        }
+        double dist = __ldg(&c.rdist[road_id(cur, tgt)]);
+        tt = (float)om_ddiv(dist * 60.0, 25.0);                        // speed is hard-coded (feature_processing.py:43)
+        tc = (float)om_ddiv((double)pair_cnt, tn);
+        double extra;
+        if (kind == OM_ORDER_HAUL) {
+          int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
+          extra = om_ddiv((double)on_cnt, (double)(ue - ub)) * __ldg(&c.dcycle[ub - c.S]);
+        } else {
+          extra = om_ddiv(capsum, __ldg(&c.site_prod[q]));
+        }
+        sw = (float)log((site_est(site) + extra) + 1.0);
+      }
+      ob[o3 + q] = tt; ob[o4 + q] = tc; ob[o7 + q] = sw;
+    }
+    // all roads: distance and active-jam count
+#pragma unroll 1
+    for (int r = lane; r < R; r += 32) {
+      int cnt = 0;
+#pragma unroll 1
+      for (uint32_t j = 0; j < jam_count; ++j)
+        cnt += (U16A(j_road, j) == r && F64(j_start, j) <= now && F64(j_end, j) >= now) ? 1 : 0;
+      ob[o5 + r] = (float)__ldg(&c.rdist[r]);
+      ob[o6 + r] = (float)cnt;
+    }
+    // per-site blocks
+#pragma unroll 1
+    for (int s = lane; s < NS; s += 32) {
+      ob[o8 + s] = (float)log(site_est(s) + 1.0);
+      ob[o9 + s] = (float)om_ddiv((double)U16A(s_qtotal, s), tn);
+      ob[o10 + s] = (float)log(F64(s_cap, s) + 1.0);
+      ob[o11 + s] = (float)F64(s_ability, s);
+      ob[o12 + s] = (float)log(F64(s_tons, s) + 1.0);
+    }
+    __syncwarp();
+  }
+
+  // One env step of this instance (called by om_step_kernel after the state blob is staged).
+  __device__ __forceinline__ void rl_step(const RunParams& p) {
+    InstHdr* h = (InstHdr*)(sm + ly.hdr);
+    const OmStepIO& io = p.io;
+    if (h->finished) {
+      if (lane == 0) {
+        if (io.reward) io.reward[inst] = 0.0;
+        if (io.done) io.done[inst] = 1;
+        if (io.order_kind) io.order_kind[inst] = -1;
+        if (io.truck) io.truck[inst] = -1;
+        if (io.sug_action) io.sug_action[inst] = -1;
+      }
+      return;
+    }
+    int pt = h->pending_truck, pk = h->pending_kind;
+    if (pt >= 0) {
+      // the agent's action arrives: RLDispatcher._step returns, truck.py:303-317 / 390-402 / 442-453 continue
+      int a = io.actions ? io.actions[inst] : 0;
+      int nmax = (pk == OM_ORDER_HAUL) ? c.D : c.L;
+      if (a < 0 || a >= nmax) {
+        if (a >= 0) count_order(pk, a);
+        fail(OM_IERR_BAD_ORDER);
+      } else {
+        apply_order(pt, pk, a);
+        F64(t_time, pt) = now; U32A(t_key, pt) = seq; U8A(t_phase, pt) = PH_MOVE_BEGIN;   // Initialize(move), URGENT
+        seq++;
+      }
+      h->pending_truck = -1; h->pending_kind = -1;
+    }
+    run(p.until);
+    pt = h->pending_truck; pk = h->pending_kind;
+    const bool failed = (err != OM_IERR_NONE && err != OM_IERR_TRACE_OVERFLOW);
+    if (pt >= 0 && !failed) {
+      float* ob = io.obs + (size_t)inst * p.obs_dim;
+      double delta_time = now - rl_last;
+      rl_observation(pt, pk, ob);
+      double reward = rl_reward(false);
+      int sug = -1;
+      if (io.teacher >= 0 && io.teacher != OM_DISP_RANDOM) {
+        int saved_disp = disp;
+        uint32_t saved_err = err;
+        disp = io.teacher;
+        sug = decide(pk, pt);
+        disp = saved_disp; err = saved_err;
+      }
+      rl_last = now;
+      if (lane == 0) {
+        if (io.reward) io.reward[inst] = reward;
+        if (io.done) io.done[inst] = 0;
+        if (io.order_kind) io.order_kind[inst] = pk;
+        if (io.truck) io.truck[inst] = pt;
+        if (io.sug_action) io.sug_action[inst] = sug;
+        if (io.info) { io.info[inst * 4 + 0] = reported_tons; io.info[inst * 4 + 1] = now; io.info[inst * 4 + 2] = delta_time; io.info[inst * 4 + 3] = 0.0; }
+        h->rl_steps++;
+      }
+    } else {
+      // Mine.start_rl after env.run: final reward over (last decision, until], done (mine.py:453-476)
+      double delta_time = p.until - rl_last;
+      now = p.until;
+      double reward = rl_reward(true);
+      rl_last = now;
+      if (lane == 0) {
+        if (io.reward) io.reward[inst] = reward;
+        if (io.done) io.done[inst] = 1;
+        if (io.order_kind) io.order_kind[inst] = -1;
+        if (io.truck) io.truck[inst] = -1;
+        if (io.sug_action) io.sug_action[inst] = -1;
+        if (io.info) { io.info[inst * 4 + 0] = reported_tons; io.info[inst * 4 + 1] = now; io.info[inst * 4 + 2] = delta_time; io.info[inst * 4 + 3] = 0.0; }
+        h->finished = 1;
+        h->rl_steps++;
+      }
+    }
+    __syncwarp();
   }
 
   // dumped tons at the stop time: sum() of the dumper tons in dumper order (same flavour as the monitors)

@@ -17,7 +17,7 @@ RNG_MODES = {"det": 0, "philox": 1, "tape": 2}
 
 DISPATCHER_IDS = {
     "NaiveDispatcher": 0, "RandomDispatcher": 1, "NearestDispatcher": 2, "FixedGroupDispatcher": 3,
-    "SPTFDispatcher": 4, "SQDispatcher": 5, "external": 255,
+    "SPTFDispatcher": 4, "SQDispatcher": 5, "ShortestTripDispatcher": 6, "external": 255,
 }
 
 
@@ -28,11 +28,18 @@ class OmOutputsStruct(ctypes.Structure):
                 ("reserved", ctypes.c_int32)]
 
 
+class OmStepIOStruct(ctypes.Structure):
+    _fields_ = [("actions", ctypes.c_void_p), ("obs", ctypes.c_void_p), ("reward", ctypes.c_void_p),
+                ("done", ctypes.c_void_p), ("order_kind", ctypes.c_void_p), ("truck", ctypes.c_void_p),
+                ("sug_action", ctypes.c_void_p), ("info", ctypes.c_void_p), ("teacher", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
 _LAYOUT_FIELDS = ["total_bytes", "hdr", "t_time", "t_load", "t_jstart", "t_prejam", "t_lastbrk", "t_repair",
-                  "t_total", "t_cycle", "t_dist", "t_key", "t_rng", "t_svc", "t_epoch", "t_next", "t_unit", "t_phase",
+                  "t_total", "t_cycle", "t_dist", "t_since", "t_key", "t_rng", "t_svc", "t_epoch", "t_next", "t_unit", "t_phase",
                   "t_status", "t_cur", "t_tgt", "u_rel_time", "u_last_start", "u_last_done", "u_tons", "u_lastbrk",
                   "u_rel_key", "u_svc", "u_user", "u_head", "u_tail", "u_qlen", "u_repair", "r_repair_end",
-                  "j_pos", "j_start", "j_end", "j_road", "s_qtotal", "s_coming", "scratch"]
+                  "j_pos", "j_start", "j_end", "j_road", "s_qtotal", "s_coming", "s_tons", "s_cap", "s_ability", "scratch"]
 
 
 class OmStateLayoutStruct(ctypes.Structure):
@@ -196,6 +203,24 @@ class BatchedMine:
         o.orders, o.order_capacity = ptr(r.orders), r.order_capacity
         self._ck(self.lib.om_run(self.h, until, ctypes.c_void_p(self.state.data_ptr()), ctypes.byref(o), self._stream()))
         return r
+
+    def obs_dim(self):
+        d = ctypes.c_int32()
+        self._ck(self.lib.om_obs_dim(self.h, ctypes.byref(d)))
+        return d.value
+
+    def step(self, actions, io, until=None, teacher=-1):
+        """One batched env step through ``om_step``; ``io`` is a dict of preallocated device tensors
+        (obs, reward, done, order_kind, truck, sug_action, info), ``actions`` an int32 device tensor or None."""
+        s = OmStepIOStruct()
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        s.actions = ptr(actions)
+        s.obs, s.reward, s.done = ptr(io["obs"]), ptr(io.get("reward")), ptr(io.get("done"))
+        s.order_kind, s.truck = ptr(io.get("order_kind")), ptr(io.get("truck"))
+        s.sug_action, s.info = ptr(io.get("sug_action")), ptr(io.get("info"))
+        s.teacher = int(teacher)
+        until = float(self.sim_time if until is None else until)
+        self._ck(self.lib.om_step(self.h, until, ctypes.c_void_p(self.state.data_ptr()), ctypes.byref(s), self._stream()))
 
     def stats(self, result):
         """Per-dispatcher partial sums [6, 16] (float64 device tensor) for the cross-GPU all-reduce."""

@@ -1,0 +1,80 @@
+"""Batched gym-style environment over the device engine (BASELINE.json configs[3]).
+
+Mirrors the reference's ``mine/Mine-v1`` env (utils/gym/openmines_gym/envs/mine_env.py:192-353):
+``reset() -> (obs, info)`` and ``step(action) -> (obs, reward, terminated, truncated, info)``, where one
+step is one dispatch decision of whichever truck asks next -- but for N independent mines at once, with
+observations, rewards and flags as **device tensors** (no queues, threads or processes).  The
+observation is the reference's float32[194] vector (utils/feature_processing.py:3-75; generalised to
+C = max(L, D) candidate slots when L != D), the reward its dense reward (rl_dispatch.py:194-308)
+including the final-step bonus, ``info["sug_action"]`` the teacher's decision (default
+ShortestTripDispatcher, mine_env.py:55,196).
+"""
+import numpy as np
+
+from .engine import BatchedMine, DISPATCHER_IDS
+
+
+class BatchedMineEnv:
+    def __init__(self, config, num_envs, device=0, rng_mode="philox", sug_dispatcher="ShortestTripDispatcher",
+                 auto_reset=False, jam_capacity=64):
+        import torch
+        self.torch = torch
+        self.mine = BatchedMine(config, num_envs, device=device, jam_capacity=jam_capacity)
+        self.num_envs = int(num_envs)
+        self.rng_mode = rng_mode
+        self.teacher = DISPATCHER_IDS[sug_dispatcher] if sug_dispatcher else -1
+        self.auto_reset = auto_reset
+        self.obs_dim = self.mine.obs_dim()
+        self.n_actions = max(self.mine.pc.L, self.mine.pc.D)          # spaces.Discrete(max(L, D)), mine_env.py:217-221
+        dev, n = self.mine.device, self.num_envs
+        self.io = {
+            "obs": torch.zeros((n, self.obs_dim), dtype=torch.float32, device=dev),
+            "reward": torch.zeros(n, dtype=torch.float64, device=dev),
+            "done": torch.zeros(n, dtype=torch.uint8, device=dev),
+            "order_kind": torch.full((n,), -1, dtype=torch.int32, device=dev),
+            "truck": torch.full((n,), -1, dtype=torch.int32, device=dev),
+            "sug_action": torch.full((n,), -1, dtype=torch.int32, device=dev),
+            "info": torch.zeros((n, 4), dtype=torch.float64, device=dev),
+        }
+        self._episode = 0
+        self._seeds = None
+        self._tapes = None
+
+    def _info(self):
+        io = self.io
+        return {"produce_tons": io["info"][:, 0], "time": io["info"][:, 1], "delta_time": io["info"][:, 2],
+                "sug_action": io["sug_action"], "order_kind": io["order_kind"], "truck": io["truck"],
+                "load_num": self.mine.pc.L, "unload_num": self.mine.pc.D}
+
+    def reset(self, seed=None, tapes=None):
+        """Start N fresh episodes and advance each to its first decision.  ``seed``: int base or array of N."""
+        n = self.num_envs
+        if seed is None:
+            seeds = np.arange(n, dtype=np.uint64) + np.uint64(self._episode * n)
+        elif np.isscalar(seed):
+            seeds = np.arange(n, dtype=np.uint64) + np.uint64(seed)
+        else:
+            seeds = np.asarray(seed, dtype=np.uint64)
+        self._seeds, self._tapes = seeds, tapes
+        self._episode += 1
+        self.mine.reset("external", seeds=seeds, rng_mode=self.rng_mode, tapes=tapes)
+        self.mine.step(None, self.io, teacher=self.teacher)
+        return self.io["obs"], self._info()
+
+    def step(self, actions):
+        """actions: int tensor [N] on the env's device (int64 or int32)."""
+        torch = self.torch
+        a = actions.to(device=self.mine.device, dtype=torch.int32).contiguous()
+        self.mine.step(a, self.io, teacher=self.teacher)
+        terminated = self.io["done"].bool()
+        truncated = torch.zeros_like(terminated)
+        if self.auto_reset and bool(terminated.all()):
+            # every env of one config finishes at the same simulated time but not at the same step count;
+            # restart the whole batch once all are done (done envs idle with reward 0 until then)
+            obs_final, rew, info = self.io["obs"].clone(), self.io["reward"].clone(), self._info()
+            self.reset()
+            return self.io["obs"], rew, terminated, truncated, dict(info, final_observation=obs_final)
+        return self.io["obs"], self.io["reward"], terminated, truncated, self._info()
+
+    def close(self):
+        self.mine.close()

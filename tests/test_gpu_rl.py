@@ -1,0 +1,135 @@
+"""GPU parity of the batched RL step (om_step through the C ABI) against the reference goldens and
+the RL oracle: order kinds, asking truck, teacher suggestion bit-exact; observation float32[194] within
+1 float32 ulp (device fp64 log vs libm before the float32 cast); reward within 1e-9 relative (the
+reference sums truck intervals in truck order, the engine integrates them incrementally)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _drive(env, policies, max_steps=2000):
+    """Step the batched env with one host policy per env; returns per-env logs."""
+    import torch
+    n = env.num_envs
+    logs = [[] for _ in range(n)]
+    obs, info = env.reset(seed=np.array([p["seed"] for p in policies], dtype=np.uint64),
+                          tapes=[p.get("tape") for p in policies] if env.rng_mode == "tape" else None)
+    done_prev = np.zeros(n, dtype=bool)
+    reward = np.zeros(n)
+    done = np.zeros(n, dtype=bool)
+    for _ in range(max_steps):
+        o = obs.cpu().numpy()
+        kind = info["order_kind"].cpu().numpy()
+        sug = info["sug_action"].cpu().numpy()
+        truck = info["truck"].cpu().numpy()
+        tons = info["produce_tons"].cpu().numpy()
+        acts = np.zeros(n, dtype=np.int32)
+        for e in range(n):
+            if done_prev[e]:
+                continue
+            rec = {"obs": o[e].copy(), "reward": float(reward[e]), "done": bool(done[e]), "kind": int(kind[e]),
+                   "sug_action": int(sug[e]), "truck": int(truck[e]), "produce_tons": float(tons[e])}
+            if not done[e]:
+                nch = env.mine.pc.D if kind[e] == 1 else env.mine.pc.L
+                acts[e] = policies[e]["fn"](len(logs[e]), int(kind[e]), o[e], nch)
+                rec["action"] = int(acts[e])
+            logs[e].append(rec)
+        done_prev = done_prev | done
+        if done_prev.all():
+            break
+        obs, r, term, _, info = env.step(torch.from_numpy(acts).to(env.mine.device))
+        reward = r.cpu().numpy()
+        done = term.cpu().numpy()
+    return logs
+
+
+def _compare(log, ref_obs, ref_reward, ref_kind, ref_sug, ref_done, ref_action):
+    assert len(log) == len(ref_reward), (len(log), len(ref_reward))
+    for k, rec in enumerate(log):
+        assert rec["kind"] == ref_kind[k] and rec["done"] == bool(ref_done[k]), k
+        assert rec["sug_action"] == ref_sug[k], (k, rec["sug_action"], ref_sug[k])
+        if not rec["done"]:
+            assert rec["action"] == ref_action[k], k
+            a, b = rec["obs"], ref_obs[k]
+            tol = np.maximum(np.abs(b), 1e-30) * 2.4e-7
+            bad = np.nonzero(np.abs(a - b) > tol)[0]
+            assert len(bad) == 0, (k, bad[:8], a[bad[:8]], b[bad[:8]])
+        assert abs(rec["reward"] - ref_reward[k]) <= 1e-9 * max(1.0, abs(ref_reward[k])), (k, rec["reward"], ref_reward[k])
+
+
+def test_rl_step_vs_reference_goldens(north_pit):
+    """det + two tape replays of the reference's own RL loop (ShortestTrip and SQ teachers)."""
+    import openmines_b200 as om
+    from openmines_b200.rl_env import BatchedMineEnv
+    from oracle import rl_oracle as ro
+    names = ["rl_north_pit_mine_det_s0_ShortestTripDispatcher_p1", "rl_north_pit_mine_live_s21_ShortestTripDispatcher_p2",
+             "rl_north_pit_mine_live_s22_SQDispatcher_p3"]
+    for name in names:
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        mode = "det" if str(z["mode"]) == "det" else "tape"
+        env = BatchedMineEnv(north_pit, 1, rng_mode=mode, sug_dispatcher=str(z["teacher"]))
+        assert env.obs_dim == 194
+        pol = {"fn": ro.keyed_policy(int(z["policy_seed"])), "seed": int(z["seed"]),
+               "tape": (z["tape_sites"], z["tape_values"])}
+        logs = _drive(env, [pol])
+        _compare(logs[0], z["obs"], z["reward"], z["kind"], z["sug_action"], z["done"], z["action"])
+        env.close()
+
+
+def test_rl_step_batch_vs_oracle(north_pit):
+    """A batch of envs with different policies / teachers in one om_step call vs the RL oracle."""
+    from openmines_b200.rl_env import BatchedMineEnv
+    from oracle import rl_oracle as ro
+    for teacher in ("SPTFDispatcher", "NearestDispatcher"):
+        pols = [{"fn": ro.keyed_policy(40 + k), "seed": k} for k in range(4)]
+        env = BatchedMineEnv(north_pit, len(pols), rng_mode="det", sug_dispatcher=teacher)
+        logs = _drive(env, pols)
+        for k, p in enumerate(pols):
+            r = ro.run_rl_oracle(north_pit, p["fn"], "det", seed=k, teacher=teacher)
+            ol = r.rl_log
+            _compare(logs[k], [x["obs"] for x in ol], [x["reward"] for x in ol], [x["kind"] for x in ol],
+                     [x["sug_action"] for x in ol], [x["done"] for x in ol], [x["action"] for x in ol])
+        env.close()
+
+
+def test_rl_live_runs_and_finishes(north_pit):
+    """Philox mode smoke: 256 envs with a uniform random policy all reach done with sane returns."""
+    import torch
+    from openmines_b200.rl_env import BatchedMineEnv
+    env = BatchedMineEnv(north_pit, 256, rng_mode="philox")
+    obs, info = env.reset(seed=123)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    total = torch.zeros(256, dtype=torch.float64, device=obs.device)
+    steps = 0
+    while True:
+        a = torch.randint(0, 5, (256,), generator=g)
+        obs, r, term, trunc, info = env.step(a.to(obs.device))
+        total += r
+        steps += 1
+        assert torch.isfinite(obs).all()
+        if bool(term.all()) or steps > 2000:
+            break
+    assert bool(term.all()) and 300 < steps < 1500
+    tons = info["produce_tons"].cpu().numpy()
+    assert 5000 < tons.mean() < 11000            # random dispatching: reference mean 8178 +- 421
+    env.close()
+
+
+def test_shortest_trip_as_builtin_dispatcher(north_pit):
+    """ShortestTripDispatcher as a 7th device dispatcher in om_run, det mode, vs the oracle."""
+    import openmines_b200 as om
+    from helpers import engine_vs_ref
+    from oracle import des_oracle as do
+    o = do.DesOracle(north_pit, "SQDispatcher", "det")
+    o.dispatcher = "ShortestTripDispatcher"
+    ref = o.run()
+    mine = om.BatchedMine(north_pit, 1)
+    mine.reset("ShortestTripDispatcher", rng_mode="det")
+    res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=2048)
+    diffs = engine_vs_ref(ref, mine, res, 0)
+    assert not diffs, diffs[:5]

@@ -171,6 +171,125 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: batched RL env step, random-init policy feeding the orders
+# ------------------------------------------------------------------------------------------------
+def run_c4(a):
+    """One bench step = one full batched episode: reset + (policy forward + om_step) until every env is done."""
+    import numpy as np
+    import torch
+    import openmines_b200 as om
+    from openmines_b200.rl_env import BatchedMineEnv
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = a.instances or 16384
+    cfg = load_cfg()
+    env = BatchedMineEnv(cfg, n, device=local, rng_mode="philox", sug_dispatcher="ShortestTripDispatcher")
+    dev = env.mine.device
+    torch.manual_seed(1)
+    # policy of ppo_single_net.Agent shape (openmines/test/cleanrl/ppo_single_net.py:124-185): 194-256-256-256-5, ReLU, orthogonal init
+    layers, d = [], env.obs_dim
+    for width in (256, 256, 256):
+        lin = torch.nn.Linear(d, width); torch.nn.init.orthogonal_(lin.weight, 2 ** 0.5); torch.nn.init.zeros_(lin.bias)
+        layers += [lin, torch.nn.ReLU()]; d = width
+    head = torch.nn.Linear(d, env.n_actions); torch.nn.init.orthogonal_(head.weight, 0.01); torch.nn.init.zeros_(head.bias)
+    policy = torch.nn.Sequential(*layers, head).to(dev)
+
+    def episode(host_sync_every):
+        obs, info = env.reset(seed=rank * n)
+        steps = 0
+        with torch.no_grad():
+            while True:
+                logits = policy(obs)
+                act = torch.distributions.Categorical(logits=logits).sample()
+                obs, rew, term, trunc, info = env.step(act)
+                steps += 1
+                if steps % host_sync_every == 0 and bool(term.all()):
+                    break
+        return steps
+
+    for _ in range(max(1, a.warmup // 3)):
+        episode(16)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    env_steps = 0
+    for _ in range(a.steps):
+        env_steps += episode(16)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    # per-env totals from the state headers: decisions and truck events of the last episode
+    hdr = env.mine.state[:, :192].cpu().numpy()
+    n_events = hdr[:, 56:60].copy().view(np.uint32).astype(np.float64).sum()      # InstHdr.n_events
+    n_dec = hdr[:, 60:64].copy().view(np.uint32).astype(np.float64).sum()         # InstHdr.n_decisions
+    tot = torch.tensor([ms, n_events, n_dec], dtype=torch.float64, device=dev)
+    if dist is not None:
+        mx = tot[:1].clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot[1:].clone(); dist.all_reduce(sm)
+        ms, n_events, n_dec = float(mx[0]), float(sm[0]), float(sm[1])
+    ms_per_step = ms / a.steps
+    # kernel-only timing of om_step for the HBM roofline
+    obs, info = env.reset(seed=rank * n)
+    act = torch.zeros(n, dtype=torch.int32, device=dev)
+    for _ in range(60):
+        env.mine.step(act, env.io, teacher=env.teacher)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(100):
+        env.mine.step(act, env.io, teacher=env.teacher)
+    k1.record()
+    torch.cuda.synchronize()
+    step_ms = k0.elapsed_time(k1) / 100
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg = n * (2 * env.mine.state_bytes + env.obs_dim * 4 + 4 + 8 + 1 + 3 * 4 + 32)
+    achieved = alg / (step_ms / 1000.0) / 1e9
+    line = {"metric": METRIC, "value": n_events / (ms_per_step / 1000.0),
+            "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3]: batched RL env step, %d parallel north_pit_mine envs/GPU, random-init "
+                                   "policy (194-256-256-256-5 MLP, Categorical sample) feeding every order; one bench step = one "
+                                   "full batched episode (reset + policy/om_step until all envs are done)" % n,
+                       "sim_time": 240, "instances_per_gpu": n, "state_bytes_per_instance": env.mine.state_bytes,
+                       "l2_policy": "inputs larger than L2 (state %.0f MB/GPU round-trips HBM every env step)" % (n * env.mine.state_bytes / 1e6),
+                       "launch": env.mine.launch_info()},
+            "episodes_per_s": n * world / (ms_per_step / 1000.0),
+            "decisions_per_s": n_dec / (ms_per_step / 1000.0),
+            "env_steps_per_episode": env_steps / a.steps,
+            "clocks": clocks,
+            "e2e": {"value": n_events / (ms_per_step / 1000.0), "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": int(env_steps / a.steps / 16) * 1,
+                    "note": "observations/actions stay on the device by design; the host reads the all-done flag every 16 env steps"},
+            "gpu_launches": env_steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "kernel": "om_step_kernel<philox>", "kernel_ms": step_ms,
+                         "algorithmic_bytes_per_launch": alg,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                         "note": "kernel_ms measured mid-episode with a constant action (100 launches)"}}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def main():
@@ -179,12 +298,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"])
     ap.add_argument("--instances", type=int, default=0, help="instances per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference_arm(a)
+    if a.workload == "c4":
+        return run_c4(a)
 
     import numpy as np
     import torch

@@ -134,6 +134,16 @@ typedef struct OmTickRecord {
   uint16_t pad;
 } OmTickRecord;
 
+/* Per-minute sample of one shovel / dumper (Shovel.monitor_status load_site.py:130-141, Dumper.monitor_status
+ * dump_site.py:25-34, ParkingLot.monitor_resource load_site.py:88-104); 16 bytes. */
+typedef struct OmUnitTick {
+  double tons;
+  uint32_t service_count;
+  uint16_t queue_length;
+  uint8_t repair;
+  uint8_t pad;
+} OmUnitTick;
+
 /* Per-instance end-of-run summary; 64 bytes. */
 typedef struct OmSummary {
   double reported_tons; /* mine.status[last tick]["produced_tons"] (the reported production) */
@@ -160,6 +170,7 @@ typedef struct OmOutputs {
   int16_t* orders;            /* [N * order_capacity] (kind<<12 | site) per decision, in order; NULL to skip */
   int32_t order_capacity;
   int32_t reserved;
+  OmUnitTick* unit_ticks;     /* [N * tick_capacity * (S+M)] per-minute shovel/dumper samples; NULL to skip */
 } OmOutputs;
 
 /* Byte offsets of the per-instance state arrays inside one state blob (om_state_bytes).  Truck

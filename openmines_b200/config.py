@@ -132,6 +132,7 @@ def pack_config(config, jam_capacity=64, sum_mode="neumaier"):
         raise NotImplementedError("duplicate truck names: SPTF/SQ exclude trucks by name "
                                   "(sptf_dispatcher.py:23); the device engine assumes unique names")
     pc.truck_names = names
+    pc.raw_caps = list(caps)
     pc.T = len(names)
     type_keys = []
     ttype = []

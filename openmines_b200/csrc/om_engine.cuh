@@ -779,6 +779,15 @@ struct Sim {
         if (out.site_queue_ticks != nullptr) out.site_queue_ticks[o] = (uint16_t)qtot;
         if (out.site_tons_ticks != nullptr) out.site_tons_ticks[o] = site_tons;
       }
+      if (out.unit_ticks != nullptr) {
+#pragma unroll 1
+        for (int u = lane; u < c.U; u += 32) {
+          OmUnitTick r;
+          r.tons = F64(u_tons, u); r.service_count = U32A(u_svc, u); r.queue_length = U16A(u_qlen, u);
+          r.repair = (u < c.S) ? U8A(u_repair, u) : (uint8_t)0; r.pad = 0;
+          out.unit_ticks[(inst * (long long)out.tick_capacity + k) * c.U + u] = r;
+        }
+      }
     }
     n_ticks++;
     if (RNG != OM_RNG_DET) {

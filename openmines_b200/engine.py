@@ -25,7 +25,7 @@ class OmOutputsStruct(ctypes.Structure):
     _fields_ = [("summary", ctypes.c_void_p), ("ticks", ctypes.c_void_p), ("tick_capacity", ctypes.c_int32),
                 ("trace_capacity", ctypes.c_int32), ("trace", ctypes.c_void_p), ("site_queue_ticks", ctypes.c_void_p),
                 ("site_tons_ticks", ctypes.c_void_p), ("orders", ctypes.c_void_p), ("order_capacity", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("reserved", ctypes.c_int32), ("unit_ticks", ctypes.c_void_p)]
 
 
 class OmStepIOStruct(ctypes.Structure):
@@ -65,6 +65,7 @@ class RunResult:
 
     def __init__(self):
         self.summary = self.ticks = self.trace = self.site_queue_ticks = self.site_tons_ticks = self.orders = None
+        self.unit_ticks = None
         self.tick_capacity = self.trace_capacity = self.order_capacity = 0
 
     def summary_np(self):
@@ -174,7 +175,8 @@ class BatchedMine:
                                    ptr(self.state), self._stream()))
         return self
 
-    def run(self, until=None, ticks=True, trace_capacity=0, site_ticks=False, order_capacity=0, result=None):
+    def run(self, until=None, ticks=True, trace_capacity=0, site_ticks=False, order_capacity=0, result=None,
+            unit_ticks=False):
         """Advance every instance to simulated time ``until`` (default: the config's sim_time)."""
         torch = self.torch
         until = float(self.sim_time if until is None else until)
@@ -189,6 +191,8 @@ class BatchedMine:
         if site_ticks and r.site_queue_ticks is None:
             r.site_queue_ticks = torch.zeros((self.n, tick_cap, ns), dtype=torch.int16, device=self.device)
             r.site_tons_ticks = torch.zeros((self.n, tick_cap, ns), dtype=torch.float64, device=self.device)
+        if unit_ticks and r.unit_ticks is None:
+            r.unit_ticks = torch.zeros((self.n, tick_cap, self.pc.S + self.pc.M, 16), dtype=torch.uint8, device=self.device)
         if trace_capacity and r.trace is None:
             r.trace = torch.zeros((self.n, trace_capacity, 32), dtype=torch.uint8, device=self.device)
             r.trace_capacity = int(trace_capacity)
@@ -201,6 +205,7 @@ class BatchedMine:
         o.tick_capacity, o.trace_capacity = r.tick_capacity, r.trace_capacity
         o.site_queue_ticks, o.site_tons_ticks = ptr(r.site_queue_ticks), ptr(r.site_tons_ticks)
         o.orders, o.order_capacity = ptr(r.orders), r.order_capacity
+        o.unit_ticks = ptr(r.unit_ticks)
         self._ck(self.lib.om_run(self.h, until, ctypes.c_void_p(self.state.data_ptr()), ctypes.byref(o), self._stream()))
         return r
 

@@ -16,6 +16,9 @@ SUMMARY_DTYPE = np.dtype([("reported_tons", "<f8"), ("dumped_tons", "<f8"), ("no
                           ("n_truck_events", "<u4"), ("n_decisions", "<u4"), ("n_wrapper_orders", "<u4"),
                           ("n_hops", "<u4"), ("n_jams", "<u4"), ("n_road_repairs", "<u4"),
                           ("n_truck_repairs", "<u4"), ("n_unrepairable", "<u4"), ("n_ticks", "<u4"), ("err", "<u4")])
+UNIT_TICK_DTYPE = np.dtype([("tons", "<f8"), ("service_count", "<u4"), ("queue_length", "<u2"), ("repair", "u1"),
+                            ("pad", "u1")])
+assert UNIT_TICK_DTYPE.itemsize == 16
 assert TRACE_DTYPE.itemsize == 32 and TICK_DTYPE.itemsize == 32 and SUMMARY_DTYPE.itemsize == 64
 
 NO_TRUCK = 0xFFFF

@@ -1,0 +1,91 @@
+"""GPU test of the tick recorder: the engine's outputs rendered into the reference's result
+JSON must equal the JSON the unmodified reference's TickGenerator wrote for the same run."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(name):
+    with gzip.open(os.path.join(GOLDEN, name), "rt") as fh:
+        return json.load(fh)
+
+
+def _close(a, b, tol=1e-9):
+    if isinstance(a, (int, float)) and isinstance(b, (int, float)) and not isinstance(a, bool):
+        return abs(a - b) <= tol * max(1.0, abs(a), abs(b))
+    if isinstance(a, (list, tuple)) and isinstance(b, (list, tuple)):
+        return len(a) == len(b) and all(_close(x, y, tol) for x, y in zip(a, b))
+    if isinstance(a, dict) and isinstance(b, dict):
+        return a.keys() == b.keys() and all(_close(a[k], b[k], tol) for k in a)
+    return a == b
+
+
+def _compare(got, ref, skip_mine_keys=(), skip_summary=("avg_time_per_order",), tol=1e-9, skip_truck_states=()):
+    got = json.loads(json.dumps(got))          # what a consumer of the file sees
+    assert set(got.keys()) == set(ref.keys())
+    problems = []
+    for k in ref:
+        if k == "summary":
+            for f in ref[k]:
+                if f in skip_summary:
+                    continue
+                if not _close(got[k][f], ref[k][f], tol):
+                    problems.append(("summary", f, got[k][f] if not isinstance(got[k][f], list) else "list", ref[k][f] if not isinstance(ref[k][f], list) else "list"))
+            continue
+        g, r = got[k], ref[k]
+        for sec in ("load_site_states", "dump_site_states", "shovel_states", "dumper_states"):
+            if not _close(g[sec], r[sec], tol):
+                bad = [n for n in r[sec] if not _close(g[sec].get(n), r[sec][n], tol)]
+                problems.append((k, sec, bad[:2], g[sec].get(bad[0]) if bad else None, r[sec][bad[0]] if bad else None))
+        for f in r["mine_states"]:
+            if f in skip_mine_keys:
+                continue
+            if not _close(g["mine_states"][f], r["mine_states"][f], tol):
+                problems.append((k, "mine_states", f, g["mine_states"][f], r["mine_states"][f]))
+        for name, ts in r["truck_states"].items():
+            if ts["state"] in skip_truck_states:
+                continue
+            if not _close(g["truck_states"][name], ts, 1e-9):
+                problems.append((k, "truck", name, g["truck_states"][name], ts))
+    return problems
+
+
+def test_result_json_det_sq(north_pit):
+    import openmines_b200 as om
+    from openmines_b200.ticker import TickRecorder
+    ref = _load("ticks_north_pit_mine_SQDispatcher_det_t120.json.gz")
+    cfg = dict(north_pit, sim_time=120)
+    mine = om.BatchedMine(cfg, 1)
+    mine.reset("SQDispatcher", rng_mode="det")
+    res = mine.run(trace_capacity=4096, site_ticks=True, unit_ticks=True, order_capacity=1024)
+    rec = TickRecorder(mine, res, "SQDispatcher")
+    ticks = rec.ticks(0)
+    problems = _compare(ticks, ref)
+    assert not problems, problems[:6]
+    sd = rec.states_dict(ticks)
+    assert sd["produced_tons_list"][-1] == ref["summary"]["produced_tons"] and len(sd["times"]) == 120
+    path = rec.write_to_file(ticks, result_dir=str(__import__("tempfile").mkdtemp()))
+    assert os.path.basename(path).startswith("MINE-NorthPitMine-ALGO-SQDispatcher-TIME-")
+    assert json.load(open(path))["summary"]["total_order_count"] == ref["summary"]["total_order_count"]
+
+
+def test_result_json_tape_sptf(north_pit):
+    """Stochastic run (tape replay of the reference's draws), including the reference's dict-collision
+    event counters, which the recorder re-derives from the event trace."""
+    import openmines_b200 as om
+    from openmines_b200.ticker import TickRecorder
+    ref = _load("ticks_north_pit_mine_SPTFDispatcher_live_s11.json.gz")
+    z = np.load(os.path.join(GOLDEN, "live_north_pit_mine_SPTFDispatcher_s11.npz"))
+    mine = om.BatchedMine(north_pit, 1)
+    mine.reset("SPTFDispatcher", rng_mode="tape", tapes=[(z["tape_sites"], z["tape_values"])])
+    res = mine.run(trace_capacity=8192, site_ticks=True, unit_ticks=True, order_capacity=2048)
+    ticks = TickRecorder(mine, res, "SPTFDispatcher").ticks(0)
+    problems = _compare(ticks, ref)
+    assert not problems, problems[:6]

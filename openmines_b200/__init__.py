@@ -6,7 +6,7 @@ dispatcher / Mine.start / gym-step surface.  See DESIGN.md and INTEGRATION.md.
 """
 from .config import pack_config, load_config, PackedConfig          # noqa: F401
 from .dispatcher import (BaseDispatcher, NaiveDispatcher, RandomDispatcher, NearestDispatcher,   # noqa: F401
-                         FixedGroupDispatcher, SPTFDispatcher, SQDispatcher, by_name)
+                         FixedGroupDispatcher, SPTFDispatcher, SQDispatcher, ShortestTripDispatcher, by_name)
 from .engine import BatchedMine, RunResult, DISPATCHER_IDS          # noqa: F401
 
 __version__ = "0.1.0"

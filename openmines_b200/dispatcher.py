@@ -84,9 +84,10 @@ NearestDispatcher = _make("NearestDispatcher", 2, "dispatch_algorithms/nearest_d
 FixedGroupDispatcher = _make("FixedGroupDispatcher", 3, "dispatch_algorithms/fixed_group_dispatcher.py:15-110")
 SPTFDispatcher = _make("SPTFDispatcher", 4, "dispatch_algorithms/sptf_dispatcher.py:15-61")
 SQDispatcher = _make("SQDispatcher", 5, "dispatch_algorithms/sq_dispatcher.py:12-100")
+ShortestTripDispatcher = _make("ShortestTripDispatcher", 6, "dispatch_algorithms/shortest_trip_dispatcher.py:7-84")
 
 BUILTIN = {c.__name__: c for c in (NaiveDispatcher, RandomDispatcher, NearestDispatcher, FixedGroupDispatcher,
-                                   SPTFDispatcher, SQDispatcher)}
+                                   SPTFDispatcher, SQDispatcher, ShortestTripDispatcher)}
 
 
 def by_name(name):

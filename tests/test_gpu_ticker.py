@@ -89,3 +89,25 @@ def test_result_json_tape_sptf(north_pit):
     ticks = TickRecorder(mine, res, "SPTFDispatcher").ticks(0)
     problems = _compare(ticks, ref)
     assert not problems, problems[:6]
+
+
+def test_experiment_drivers(north_pit):
+    """run_dispatch_sim / run_simulation / fleet ablation facades (cli/run.py:48-112,115-273,283-370)."""
+    from openmines_b200 import experiments as ex
+    import openmines_b200 as om
+    cfg = dict(north_pit, sim_time=60)
+    cfg["dispatcher"] = {"type": ["NaiveDispatcher", "SQDispatcher", "PPODispatcher"]}
+    d = om.SQDispatcher()
+    out = ex.run_dispatch_sim(d, cfg, n_seeds=4, stochastic=False)
+    assert set(out["ticks"].keys()) == set(range(60)) | {"summary"}
+    assert (out["summary"]["reported_tons"] == out["summary"]["reported_tons"][0]).all()
+    assert d.total_order_count == out["ticks"]["summary"]["total_order_count"] > 71
+    out["mine"].close()
+    states = ex.run_simulation(cfg, stochastic=False)
+    assert set(states) == {"NaiveDispatcher", "SQDispatcher"}
+    assert len(states["SQDispatcher"]["produced_tons_list"]) == 60
+    assert ex.fleet_sizes_for(10, 100) == [10, 20, 30, 40, 50, 60, 70, 80, 90, 100]
+    c = ex.scaled_fleet_config(north_pit, 40)
+    assert sum(t["count"] for t in c["charging_site"]["trucks"]) == 40
+    res = ex.scene_based_fleet_ablation(cfg, 20, 20, dispatchers=["NaiveDispatcher", "SQDispatcher"], n_seeds=8)
+    assert res["SQDispatcher"]["fleet_sizes"] == [20] and res["SQDispatcher"]["productions"][0] > res["NaiveDispatcher"]["productions"][0]

@@ -264,6 +264,10 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
     int limit = maxsm < OM_SMEM_LIMIT ? maxsm : OM_SMEM_LIMIT;
     int w = limit / (int)h->ly.total_bytes;
     if (w > OM_MAX_WARPS_PER_CTA) w = OM_MAX_WARPS_PER_CTA;
+    if (const char* ev = getenv("OM_WARPS_PER_CTA")) {   // tuning knob (occupancy experiments)
+      int wv = atoi(ev);
+      if (wv >= 1 && wv < w) w = wv;
+    }
     if (w < 1) rc = set_err(h, OM_E_UNSUPPORTED, "om_create: one instance's state does not fit in shared memory");
     else {
       h->warps = w; h->block = w * 32; h->smem = w * (int)h->ly.total_bytes;

@@ -250,6 +250,14 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
   UP(fixed_group, fixed_group, T); UP(shovel_rate, shovel_rate, S); UP(site_prod, site_productivity, L);
 #undef UP
   if (rc == OM_OK) {
+    // service time of truck type x unit: (cap/shovel_tons)*cycle for shovels (truck.py:223), the dumper's cycle time otherwise
+    std::vector<double> svc((size_t)c.NT * c.U);
+    for (int tt = 0; tt < c.NT; ++tt)
+      for (int u = 0; u < c.U; ++u)
+        svc[(size_t)tt * c.U + u] = (u < S) ? cfg->load_time[(size_t)tt * S + u] : cfg->dumper_cycle[u - S];
+    rc = upload(h, svc.data(), svc.size(), &c.svc_time);
+  }
+  if (rc == OM_OK) {
     void* d = nullptr;
     e = cudaMalloc(&d, sizeof(unsigned long long));
     if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, cudaGetErrorString(e));

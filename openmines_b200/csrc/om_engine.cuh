@@ -68,6 +68,7 @@ struct DevCfg {
   const double* dcycle;
   const double* rdist;
   const double* load_time;
+  const double* svc_time;   // [NT*U] load_time for shovels, dumper cycle for dumpers (built in om_create)
   const double* sptf_cost;
   const double* jam_chance;
   const int32_t* near_haul;
@@ -958,7 +959,23 @@ struct Sim {
   // goes through the reduction exactly as SimPy's heap would order it.  `seq` advances identically in
   // both modes, so the state is the same whichever path ran.
   // ---------------------------------------------------------------------------------------------
-  enum : uint32_t { XP_ORDER = 32, XP_DEPART, XP_AFTER_LOAD, XP_AFTER_DEPART, XP_DONE, XP_PAUSE };
+  // Code layout: the kernel is instruction-fetch bound (profiles/r1_d: ~1 IPC per SM whatever the occupancy), so the
+  // continuations are laid out in the order the two hot chains execute them and fall through from one to the
+  // next (no dispatch loop): shovels and dumpers share the GRANTED / BEGIN / DONE / RET code, cold paths (external
+  // pause, errors, maintenance) are marked unlikely.  (No __noinline__ member functions: they would force the
+  // register-resident Sim scalars onto the local-memory stack.)
+  __device__ __forceinline__ void pause_for_order(int i, int kind, int rel_u, uint32_t rel_key, int& pend_truck, int& pend_kind) {
+    U8A(t_phase, i) = PH_AWAIT_ORDER;
+    F64(t_time, i) = om_inf();
+    U32A(t_key, i) = OM_KEY_SENTINEL;
+    pend_truck = i; pend_kind = kind;
+    if (rel_u >= 0) file_release(rel_u, rel_key);
+  }
+  __device__ __forceinline__ void bad_order(int kind, int site, int rel_u, uint32_t rel_key) {
+    if (site >= 0) count_order(kind, site);   // the wrapper logs the order before truck.py indexes the site list
+    fail(OM_IERR_BAD_ORDER);
+    if (rel_u >= 0) file_release(rel_u, rel_key);
+  }
 
   __device__ __forceinline__ void run(double until) {
     const int T = c.T, U = c.U, L = c.L, D = c.D, S = c.S;
@@ -978,16 +995,17 @@ struct Sim {
         if (tlt) dup = false;
         if (tlt || (teq && kk < bk)) { bhi = tv.y; blo = tv.x; bk = kk; bid = i; }
       }
-            if (n_rel != 0)
-#pragma unroll 1
-      for (int u = lane; u < U; u += 32) {
-        uint2 tv = *(const uint2*)&F64(u_rel_time, u);
-        uint32_t kk = U32A(u_rel_key, u);
-        bool teq = (tv.y == bhi) && (tv.x == blo);
-        bool tlt = (tv.y < bhi) || (tv.y == bhi && tv.x < blo);
-        if (teq) dup = true;
-        if (tlt) dup = false;
-        if (tlt || (teq && kk < bk)) { bhi = tv.y; blo = tv.x; bk = kk; bid = T + u; }
+      if (n_rel != 0) {
+        #pragma unroll 1
+        for (int u = lane; u < U; u += 32) {
+          uint2 tv = *(const uint2*)&F64(u_rel_time, u);
+          uint32_t kk = U32A(u_rel_key, u);
+          bool teq = (tv.y == bhi) && (tv.x == blo);
+          bool tlt = (tv.y < bhi) || (tv.y == bhi && tv.x < blo);
+          if (teq) dup = true;
+          if (tlt) dup = false;
+          if (tlt || (teq && kk < bk)) { bhi = tv.y; blo = tv.x; bk = kk; bid = T + u; }
+        }
       }
       uint32_t mhi = __reduce_min_sync(OM_FULL, bhi);
       uint32_t mlo = __reduce_min_sync(OM_FULL, (bhi == mhi) ? blo : 0xFFFFFFFFu);
@@ -1012,268 +1030,208 @@ struct Sim {
       int i = id;
       int rel_u = -1;                        // Release created in this chain, not yet popped (kept in registers)
       uint32_t rel_key = 0;
-      int kind = 0;
-      bool dead = false;
-      uint32_t ph;
+      int kind = 0, u = 0;
+      bool dead = false, dump = false;
       if (id >= T) {
         // Release event popped: Resource._trigger_put hands the unit to the queue head
-        int u = id - T;
+        u = id - T;
         F64(u_rel_time, u) = om_inf();
         U32A(u_rel_key, u) = OM_KEY_SENTINEL;
         n_rel--;
         if (U16A(u_user, u) != OM_NONE16 || U16A(u_qlen, u) == 0) continue;
         i = q_pop(u);
         U16A(u_user, u) = (uint16_t)i;
-        ph = (u < S) ? PH_LOAD_GRANTED : PH_DUMP_GRANTED;
-        if (!chain) { sched_truck(i, now, OM_KEY_NORMAL, (uint8_t)ph); continue; }
+        if (!chain) { sched_truck(i, now, OM_KEY_NORMAL, (u < S) ? PH_LOAD_GRANTED : PH_DUMP_GRANTED); continue; }
         seq++;
-      } else {
-        ph = U8A(t_phase, i);
+        goto L_GRANTED;
+      }
+      switch (U8A(t_phase, i)) {
+        case PH_MOVE_ARRIVE: goto L_ARRIVE;
+        case PH_LOAD_DONE: case PH_DUMP_DONE: goto L_SVC_DONE;
+        case PH_MOVE_RET: goto L_MOVE_RET;
+        case PH_LOAD_GRANTED: case PH_DUMP_GRANTED: goto L_GRANTED;
+        case PH_LOAD_BEGIN: case PH_DUMP_BEGIN: goto L_BEGIN;
+        case PH_LOAD_RET: case PH_DUMP_RET: goto L_SVC_RET;
+        case PH_MOVE_BEGIN: goto L_MOVE_BEGIN;
+        case PH_RUN_INIT:                                              // truck.py:296-302
+          U8A(t_cur, i) = 0;
+          U8A(t_status, i) = ST_WAIT_INIT;
+          kind = OM_ORDER_INIT;
+          goto L_ORDER;
+        case PH_MOVE_REPAIRED:
+          F64(t_repair, i) = 0.0;
+          U8A(t_status, i) = ST_MOVING;
+          goto L_DEPART;
+        case PH_MAINT_DONE:                                            // truck.py:372-379
+          u = U16A(t_unit, i);
+          emit(K_SHOVEL_MAINT_DONE, (uint32_t)i, (uint32_t)u, 0, 0.0, 0.0);
+          F64(u_lastbrk, u) = now;
+          goto L_RELEASE;
+        default:
+          continue;
       }
 
-      for (;;) {
-        switch (ph) {
-          case PH_RUN_INIT:                                            // truck.py:296-302
-            U8A(t_cur, i) = 0;
-            U8A(t_status, i) = ST_WAIT_INIT;
-            kind = OM_ORDER_INIT;
-            ph = XP_ORDER;
-            break;
-          case XP_ORDER: {                                             // dispatcher.py:35-89 + truck.py:303-317,389-402,441-453
-            if (disp == OM_DISP_EXTERNAL) {
-              U8A(t_phase, i) = PH_AWAIT_ORDER;
-              F64(t_time, i) = om_inf();
-              U32A(t_key, i) = OM_KEY_SENTINEL;
-              pend_truck = i; pend_kind = kind;
-              if (rel_u >= 0) { file_release(rel_u, rel_key); rel_u = -1; }
-              ph = XP_PAUSE;
-              break;
-            }
-            int site = decide(kind, i);
-            int nmax = (kind == OM_ORDER_HAUL) ? D : L;
-            if (site < 0 || site >= nmax) {
-              if (site >= 0) count_order(kind, site);   // the wrapper logs the order before truck.py indexes the site list
-              fail(OM_IERR_BAD_ORDER);
-              if (rel_u >= 0) { file_release(rel_u, rel_key); rel_u = -1; }
-              ph = XP_DONE;
-              break;
-            }
-            apply_order(i, kind, site);
-            seq++;                                                     // env.process(move): Initialize URGENT
-            if (inl) { ph = PH_MOVE_BEGIN; break; }
-            F64(t_time, i) = now; U32A(t_key, i) = seq - 1; U8A(t_phase, i) = PH_MOVE_BEGIN;
-            ph = XP_AFTER_DEPART;
-            break;
-          }
-          case PH_MOVE_BEGIN: {                                        // truck.py:116-150
-            F64(t_jstart, i) = now;
-            dead = false;
-            if (RNG != OM_RNG_DET) {
-              double g = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(U32A(t_rng, i)) * c.unrepairable_mean
-                                                : draw_exp(OM_S_UNREPAIRABLE, U16A(t_epoch, i), (uint32_t)i, c.unrepairable_mean);
-              dead = now >= g;                                         // check_vehicle_availability, truck.py:538-547
-            }
-            double rep = F64(t_repair, i);
-            if (!dead && rep != 0.0) {
-              n_brk++;
-              emit(K_BREAKDOWN, (uint32_t)i, 0, 0, F64(t_lastbrk, i), rep);
-              U8A(t_status, i) = ST_REPAIRING;
-              sched_truck(i, now + rep, OM_KEY_NORMAL, PH_MOVE_REPAIRED);
-              ph = XP_AFTER_DEPART;
-            } else {
-              ph = XP_DEPART;
-            }
-            break;
-          }
-          case PH_MOVE_REPAIRED:
-            F64(t_repair, i) = 0.0;
-            U8A(t_status, i) = ST_MOVING;
-            dead = false;
-            ph = XP_DEPART;
-            break;
-          case XP_DEPART:                                              // truck.py:151-210
-            move_depart(i, dead);
-            ph = XP_AFTER_DEPART;
-            break;
-          case XP_AFTER_DEPART: {
-            // the Release issued earlier in this chain is now the unique minimum: pop it
-            ph = XP_DONE;
-            if (rel_u >= 0) {
-              int u = rel_u;
-              rel_u = -1;
-              if (U16A(u_user, u) == OM_NONE16 && U16A(u_qlen, u) > 0) {
-                i = q_pop(u);
-                U16A(u_user, u) = (uint16_t)i;
-                seq++;                                                 // Request.succeed()
-                ph = (u < S) ? PH_LOAD_GRANTED : PH_DUMP_GRANTED;
-              }
-            }
-            break;
-          }
-          case PH_MOVE_ARRIVE:                                         // truck.py:211-218
-            rl_close(acc_move, i);
-            U8A(t_cur, i) = U8A(t_tgt, i);
-            F64(t_prejam, i) = 0.0;
-            if (chain) { seq++; ph = PH_MOVE_RET; break; }             // Process(move) event
-            sched_truck(i, now, OM_KEY_NORMAL, PH_MOVE_RET);
-            ph = XP_DONE;
-            break;
-          case PH_MOVE_RET: {                                          // truck.py:324-339 / 409-419
-            int cur = U8A(t_cur, i);
-            int u = pick_unit(cur - 1);
-            q_push(u, i);
-            U16A(t_unit, i) = (uint16_t)u;
-            bool me = false;
-            ph = XP_DONE;
-            if (U16A(u_user, u) == OM_NONE16) {                        // head-only _trigger_put
-              int h = q_pop(u);
-              U16A(u_user, u) = (uint16_t)h;
-              uint8_t gph = (u < S) ? PH_LOAD_GRANTED : PH_DUMP_GRANTED;
-              me = (h == i);
-              if (me && chain) { seq++; ph = gph; }
-              else sched_truck(h, now, OM_KEY_NORMAL, gph);
-            }
-            if (!me) {
-              F64(t_time, i) = om_inf();
-              U32A(t_key, i) = OM_KEY_SENTINEL;
-              U8A(t_phase, i) = PH_WAITING;
-            }
-            int qi = me ? 0 : (int)U16A(u_qlen, u) - 1;
-            if (cur <= L) {
-              emit(K_WAIT_SHOVEL, (uint32_t)i, (uint32_t)u, (uint32_t)qi, 0.0, 0.0);
-              if (RL) F64(t_since, i) = now;
-              U8A(t_status, i) = ST_WAIT_SHOVEL;
-            } else {
-              emit(K_WAIT_DUMPER, (uint32_t)i, (uint32_t)(u - S), 0, 0.0, 0.0);
-              U8A(t_status, i) = ST_WAIT_DUMPER;
-            }
-            break;
-          }
-          case PH_LOAD_GRANTED:                                        // truck.py:342-350
-            rl_close(acc_wait, i);
-            if (RL) F64(t_since, i) = now;
-            emit(K_GET_SHOVEL, (uint32_t)i, (uint32_t)U16A(t_unit, i), 0, 0.0, 0.0);
-            seq++;                                                     // env.process(load): Initialize URGENT
-            if (inl) { ph = PH_LOAD_BEGIN; break; }
-            F64(t_time, i) = now; U32A(t_key, i) = seq - 1; U8A(t_phase, i) = PH_LOAD_BEGIN;
-            ph = XP_DONE;
-            break;
-          case PH_LOAD_BEGIN: {                                        // truck.py:221-228
-            int u = U16A(t_unit, i);
-            U8A(t_status, i) = ST_LOADING;
-            F64(u_last_start, u) = now;
-            sched_truck(i, now + __ldg(&c.load_time[__ldg(&c.ttype[i]) * S + u]), OM_KEY_NORMAL, PH_LOAD_DONE);
-            ph = XP_DONE;
-            break;
-          }
-          case PH_LOAD_DONE: {                                         // truck.py:230-235
-            int u = U16A(t_unit, i);
-            double jit;
-            if (RNG == OM_RNG_PHILOX) {
-              // one call per load: x -> load jitter, y -> shovel-maintenance gap (read at LOAD_RET)
-              Philox4 r = px(U16A(t_epoch, i), (uint32_t)i, OM_S_LOAD_JITTER);
-              jit = -0.1 + 0.2 * (double)om_u01(r.x);
-              U32A(t_rng, i) = r.y;
-            } else {
-              jit = draw_jitter(U16A(t_epoch, i), (uint32_t)i);
-            }
-            double load = __ldg(&c.cap[i]) * (1.0 + jit);
-            F64(t_load, i) = load;
-            F64(u_tons, u) = F64(u_tons, u) + load;
-            U32A(u_svc, u) = U32A(u_svc, u) + 1;
-            F64(u_last_done, u) = now;
-            if (chain) { seq++; ph = PH_LOAD_RET; break; }             // Process(load) event
-            sched_truck(i, now, OM_KEY_NORMAL, PH_LOAD_RET);
-            ph = XP_DONE;
-            break;
-          }
-          case PH_LOAD_RET: {                                          // truck.py:352-370
-            rl_close(acc_shovel, i);
-            ph = XP_AFTER_LOAD;
-            if (RNG != OM_RNG_DET) {
-              int u = U16A(t_unit, i);
-              double gap = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(U32A(t_rng, i)) * c.maint_mean
-                                                  : draw_exp(OM_S_MAINT_GAP, U16A(t_epoch, i), (uint32_t)i, c.maint_mean);
-              if (now >= F64(u_lastbrk, u) + gap) {
-                U8A(u_repair, u) = 1;
-                double dn = draw_normal(OM_S_MAINT_DUR, U16A(t_epoch, i), (uint32_t)i, c.maint_mu, c.maint_sigma);
-                double dur = (0.0 > dn) ? 0.0 : dn;                    // max(x, 0)
-                emit(K_SHOVEL_MAINT_START, (uint32_t)i, (uint32_t)u, 0, now + dur, 0.0);
-                sched_truck(i, now + dur, OM_KEY_NORMAL, PH_MAINT_DONE);
-                ph = XP_DONE;
-              }
-            }
-            break;
-          }
-          case PH_MAINT_DONE: {                                        // truck.py:372-379
-            int u = U16A(t_unit, i);
-            emit(K_SHOVEL_MAINT_DONE, (uint32_t)i, (uint32_t)u, 0, 0.0, 0.0);
-            F64(u_lastbrk, u) = now;
-            ph = XP_AFTER_LOAD;
-            break;
-          }
-          case XP_AFTER_LOAD: {                                        // leave `with req:` -> release; truck.py:383-389
-            int u = U16A(t_unit, i);
-            rel_key = release(u);
-            if (chain) rel_u = u; else file_release(u, rel_key);
-            U8A(t_status, i) = ST_WAIT_HAUL;
-            kind = OM_ORDER_HAUL;
-            ph = XP_ORDER;
-            break;
-          }
-          case PH_DUMP_GRANTED:                                        // truck.py:422-429
-            if (RL) F64(t_since, i) = now;
-            emit(K_GET_DUMPER, (uint32_t)i, (uint32_t)(U16A(t_unit, i) - S), 0, 0.0, 0.0);
-            seq++;
-            if (inl) { ph = PH_DUMP_BEGIN; break; }
-            F64(t_time, i) = now; U32A(t_key, i) = seq - 1; U8A(t_phase, i) = PH_DUMP_BEGIN;
-            ph = XP_DONE;
-            break;
-          case PH_DUMP_BEGIN: {                                        // truck.py:238-242
-            int u = U16A(t_unit, i);
-            U8A(t_status, i) = ST_UNLOADING;
-            F64(u_last_start, u) = now;
-            sched_truck(i, now + __ldg(&c.dcycle[u - S]), OM_KEY_NORMAL, PH_DUMP_DONE);
-            ph = XP_DONE;
-            break;
-          }
-          case PH_DUMP_DONE: {                                         // truck.py:243-251
-            int u = U16A(t_unit, i);
-            double load = F64(t_load, i);
-            F64(u_tons, u) = F64(u_tons, u) + load;
-            F64(t_total, i) = F64(t_total, i) + load;
-            uint32_t sc = (uint32_t)U16A(t_svc, i) + 1;
-            U16A(t_svc, i) = (uint16_t)sc;
-            F64(t_cycle, i) = om_ddiv(now - 0.0, (double)sc);          // first_order_time is always 0 (truck.py:304)
-            F64(t_load, i) = 0.0;
-            U32A(u_svc, u) = U32A(u_svc, u) + 1;
-            F64(u_last_done, u) = now;
-            if (chain) { seq++; ph = PH_DUMP_RET; break; }             // Process(unload) event
-            sched_truck(i, now, OM_KEY_NORMAL, PH_DUMP_RET);
-            ph = XP_DONE;
-            break;
-          }
-          case PH_DUMP_RET: {                                          // truck.py:431-441
-            rl_close(acc_dumper, i);
-            int u = U16A(t_unit, i);
-            rel_key = release(u);
-            if (chain) rel_u = u; else file_release(u, rel_key);
-            U8A(t_status, i) = ST_WAIT_BACK;
-            kind = OM_ORDER_BACK;
-            ph = XP_ORDER;
-            break;
-          }
-          default:
-            ph = XP_DONE;
-            break;
-        }
-        if (ph >= XP_DONE) break;
+      // ================= chain 1: ARRIVE -> RET -> (grant) -> GRANTED -> BEGIN =================
+    L_ARRIVE:                                                          // truck.py:211-218
+      rl_close(acc_move, i);
+      U8A(t_cur, i) = U8A(t_tgt, i);
+      F64(t_prejam, i) = 0.0;
+      if (!chain) { sched_truck(i, now, OM_KEY_NORMAL, PH_MOVE_RET); continue; }
+      seq++;                                                           // Process(move) event
+    L_MOVE_RET: {                                                      // truck.py:324-339 / 409-419
+      int cur = U8A(t_cur, i);
+      u = pick_unit(cur - 1);
+      q_push(u, i);
+      U16A(t_unit, i) = (uint16_t)u;
+      bool me = false;
+      if (U16A(u_user, u) == OM_NONE16) {                              // head-only _trigger_put
+        int h = q_pop(u);
+        U16A(u_user, u) = (uint16_t)h;
+        me = (h == i);
+        if (!(me && chain)) sched_truck(h, now, OM_KEY_NORMAL, (u < S) ? PH_LOAD_GRANTED : PH_DUMP_GRANTED);
       }
-      if (ph == XP_PAUSE) break;
+      if (!me) {
+        F64(t_time, i) = om_inf();
+        U32A(t_key, i) = OM_KEY_SENTINEL;
+        U8A(t_phase, i) = PH_WAITING;
+      }
+      int qi = me ? 0 : (int)U16A(u_qlen, u) - 1;
+      if (cur <= L) {
+        emit(K_WAIT_SHOVEL, (uint32_t)i, (uint32_t)u, (uint32_t)qi, 0.0, 0.0);
+        if (RL) F64(t_since, i) = now;
+        U8A(t_status, i) = ST_WAIT_SHOVEL;
+      } else {
+        emit(K_WAIT_DUMPER, (uint32_t)i, (uint32_t)(u - S), 0, 0.0, 0.0);
+        U8A(t_status, i) = ST_WAIT_DUMPER;
+      }
+      if (!(me && chain)) continue;
+      seq++;                                                           // Request.succeed()
+    }
+    L_GRANTED:                                                         // truck.py:342-350 / 422-429
+      u = U16A(t_unit, i);
+      dump = u >= S;
+      if (!dump) rl_close(acc_wait, i);
+      if (RL) F64(t_since, i) = now;
+      emit(dump ? K_GET_DUMPER : K_GET_SHOVEL, (uint32_t)i, (uint32_t)(dump ? u - S : u), 0, 0.0, 0.0);
+      seq++;                                                           // env.process(load/unload): Initialize URGENT
+      if (!inl) {
+        F64(t_time, i) = now; U32A(t_key, i) = seq - 1; U8A(t_phase, i) = dump ? PH_DUMP_BEGIN : PH_LOAD_BEGIN;
+        continue;
+      }
+    L_BEGIN: {                                                         // truck.py:221-228 / 238-242
+      u = U16A(t_unit, i);
+      dump = u >= S;
+      U8A(t_status, i) = dump ? ST_UNLOADING : ST_LOADING;
+      F64(u_last_start, u) = now;
+      double dt = __ldg(&c.svc_time[__ldg(&c.ttype[i]) * U + u]);      // (cap/shovel_tons)*cycle | dumper cycle time
+      sched_truck(i, now + dt, OM_KEY_NORMAL, dump ? PH_DUMP_DONE : PH_LOAD_DONE);
+      continue;
+    }
+
+      // ====== chain 2: DONE -> RET -> release + order -> MOVE_BEGIN -> depart -> Release pops -> (GRANTED) ======
+    L_SVC_DONE: {                                                      // truck.py:230-235 / 243-251
+      u = U16A(t_unit, i);
+      dump = u >= S;
+      double load;
+      if (!dump) {
+        double jit;
+        if (RNG == OM_RNG_PHILOX) {
+          // one call per load: x -> load jitter, y -> shovel-maintenance gap (read at LOAD_RET)
+          Philox4 r = px(U16A(t_epoch, i), (uint32_t)i, OM_S_LOAD_JITTER);
+          jit = -0.1 + 0.2 * (double)om_u01(r.x);
+          U32A(t_rng, i) = r.y;
+        } else {
+          jit = draw_jitter(U16A(t_epoch, i), (uint32_t)i);
+        }
+        load = __ldg(&c.cap[i]) * (1.0 + jit);
+        F64(t_load, i) = load;
+      } else {
+        load = F64(t_load, i);
+        F64(t_total, i) = F64(t_total, i) + load;
+        uint32_t sc = (uint32_t)U16A(t_svc, i) + 1;
+        U16A(t_svc, i) = (uint16_t)sc;
+        F64(t_cycle, i) = om_ddiv(now - 0.0, (double)sc);              // first_order_time is always 0 (truck.py:304)
+        F64(t_load, i) = 0.0;
+      }
+      F64(u_tons, u) = F64(u_tons, u) + load;
+      U32A(u_svc, u) = U32A(u_svc, u) + 1;
+      F64(u_last_done, u) = now;
+      if (!chain) { sched_truck(i, now, OM_KEY_NORMAL, dump ? PH_DUMP_RET : PH_LOAD_RET); continue; }
+      seq++;                                                           // Process(load/unload) event
+    }
+    L_SVC_RET:                                                         // truck.py:352-370 / 431-441
+      u = U16A(t_unit, i);
+      dump = u >= S;
+      if (dump) {
+        rl_close(acc_dumper, i);
+      } else {
+        rl_close(acc_shovel, i);
+        if (RNG != OM_RNG_DET) {
+          double gap = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(U32A(t_rng, i)) * c.maint_mean
+                                              : draw_exp(OM_S_MAINT_GAP, U16A(t_epoch, i), (uint32_t)i, c.maint_mean);
+          if (__builtin_expect(now >= F64(u_lastbrk, u) + gap, 0)) { shovel_maintenance(i, u); continue; }
+        }
+      }
+    L_RELEASE:                                                         // leave `with req:` -> release; truck.py:383-389 / 436-441
+      dump = u >= S;
+      rel_key = release(u);
+      if (chain) rel_u = u; else file_release(u, rel_key);
+      U8A(t_status, i) = dump ? ST_WAIT_BACK : ST_WAIT_HAUL;
+      kind = dump ? OM_ORDER_BACK : OM_ORDER_HAUL;
+    L_ORDER: {                                                         // dispatcher.py:35-89 + truck.py:303-317,389-402,441-453
+      if (__builtin_expect(disp == OM_DISP_EXTERNAL, 0)) { pause_for_order(i, kind, rel_u, rel_key, pend_truck, pend_kind); break; }
+      int site = decide(kind, i);
+      int nmax = (kind == OM_ORDER_HAUL) ? D : L;
+      if (__builtin_expect(site < 0 || site >= nmax, 0)) { bad_order(kind, site, rel_u, rel_key); continue; }
+      apply_order(i, kind, site);
+      seq++;                                                           // env.process(move): Initialize URGENT
+      if (!inl) {
+        F64(t_time, i) = now; U32A(t_key, i) = seq - 1; U8A(t_phase, i) = PH_MOVE_BEGIN;
+        goto L_AFTER_DEPART;
+      }
+    }
+    L_MOVE_BEGIN: {                                                    // truck.py:116-150
+      F64(t_jstart, i) = now;
+      dead = false;
+      if (RNG != OM_RNG_DET) {
+        double g = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(U32A(t_rng, i)) * c.unrepairable_mean
+                                          : draw_exp(OM_S_UNREPAIRABLE, U16A(t_epoch, i), (uint32_t)i, c.unrepairable_mean);
+        dead = now >= g;                                               // check_vehicle_availability, truck.py:538-547
+      }
+      double rep = F64(t_repair, i);
+      if (!dead && rep != 0.0) { begin_repair(i, rep); goto L_AFTER_DEPART; }
+    }
+    L_DEPART:                                                          // truck.py:151-210
+      move_depart(i, dead);
+    L_AFTER_DEPART:
+      // the Release issued earlier in this chain is now the unique minimum: pop it
+      if (rel_u < 0) continue;
+      u = rel_u;
+      rel_u = -1;
+      if (U16A(u_user, u) != OM_NONE16 || U16A(u_qlen, u) == 0) continue;
+      i = q_pop(u);
+      U16A(u_user, u) = (uint16_t)i;
+      seq++;                                                           // Request.succeed()
+      goto L_GRANTED;
     }
     InstHdr* h = (InstHdr*)(sm + ly.hdr);
     h->pending_truck = pend_truck;
     h->pending_kind = pend_kind;
+  }
+
+  // rare continuations
+  __device__ __forceinline__ void shovel_maintenance(int i, int u) {       // truck.py:358-372
+    U8A(u_repair, u) = 1;
+    double dn = draw_normal(OM_S_MAINT_DUR, U16A(t_epoch, i), (uint32_t)i, c.maint_mu, c.maint_sigma);
+    double dur = (0.0 > dn) ? 0.0 : dn;                                // max(x, 0)
+    emit(K_SHOVEL_MAINT_START, (uint32_t)i, (uint32_t)u, 0, now + dur, 0.0);
+    sched_truck(i, now + dur, OM_KEY_NORMAL, PH_MAINT_DONE);
+  }
+  __device__ __forceinline__ void begin_repair(int i, double rep) {    // truck.py:143-150
+    n_brk++;
+    emit(K_BREAKDOWN, (uint32_t)i, 0, 0, F64(t_lastbrk, i), rep);
+    U8A(t_status, i) = ST_REPAIRING;
+    sched_truck(i, now + rep, OM_KEY_NORMAL, PH_MOVE_REPAIRED);
   }
 
   // ---------------------------------------------------------------------------------------------

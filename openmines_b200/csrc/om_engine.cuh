@@ -804,21 +804,28 @@ struct Sim {
           }
         }
       } else {
-        // one Philox call serves four trucks (words x,y,z,w -> trucks q, q+C, q+2C, q+3C); the rare
-        // repair-time normal draws its own call
-        const int C = (T + 3) >> 2;
+        // one Philox call serves three trucks (words x,y,z -> gaps of trucks q, q+C, q+2C); the repair-time normal of
+        // the lane's first breakdown in this minute comes from word w and the gap words' unused low bytes, a second
+        // or third one (rare) draws its own call.  Rolled loops on purpose (instruction-fetch bound).
+        const int C = (T + 2) / 3;
         #pragma unroll 1
         for (int q = lane; q < C; q += 32) {
           Philox4 r = px((uint32_t)k, (uint32_t)q, OM_S_BREAK_GAP);
-          uint32_t w4[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
+          uint32_t na = r.w, nb2 = ((r.x & 0xFFu) << 24) | ((r.y & 0xFFu) << 16) | ((r.z & 0xFFu) << 8);
+          bool used = false;
+          #pragma unroll 1
+          for (int w = 0; w < 3; ++w) {
             int i = q + w * C;
+            uint32_t word = (w == 0) ? r.x : ((w == 1) ? r.y : r.z);
             if (i < T) {
-              double gap = (double)om_exp1(w4[w]) * c.breakdown_mean;
+              double gap = (double)om_exp1(word) * c.breakdown_mean;
               if (now >= F64(t_lastbrk, i) + gap) {
-                Philox4 r2 = px((uint32_t)k, (uint32_t)i, OM_S_BREAK_DUR);
-                double d = c.repair_mu + c.repair_sigma * (double)om_normal(r2.x, r2.y);
+                if (used) {
+                  Philox4 r2 = px((uint32_t)k, (uint32_t)i, OM_S_BREAK_DUR);
+                  na = r2.x; nb2 = r2.y;
+                }
+                used = true;
+                double d = c.repair_mu + c.repair_sigma * (double)om_normal_fast(na, nb2);
                 F64(t_repair, i) = (0.0 > d) ? 0.0 : d;
                 F64(t_lastbrk, i) = now;
               }
@@ -848,21 +855,25 @@ struct Sim {
       if (U8A(t_status, i) == ST_MOVING && cur != tgt) atomicAdd(&rcnt[road_id(cur, tgt)], 1u);
     }
     __syncwarp();
+    // every candidate road flips its own keyed coin (road.py:179): lane l of the 64-road group g serves roads
+    // 64g + l (words x: coin, z: duration) and 64g + 32 + l (words y, w) from ONE Philox call
+    Philox4 rr;
+    rr.x = rr.y = rr.z = rr.w = 0u;
     #pragma unroll 1
     for (int base = 0; base < R; base += 32) {
       int r = base + lane;
       uint32_t n_on = (r < R) ? rcnt[r] : 0u;
       bool candidate = n_on >= 2u;                          // road.py:148-176: >= 2 moving trucks
-      Philox4 rr;
-      rr.x = rr.y = rr.z = rr.w = 0u;
       bool hit = candidate;
+      const bool second = (base & 32) != 0;
       if (RNG == OM_RNG_PHILOX) {
-        // every candidate road flips its own keyed coin in parallel (road.py:179)
-        if (__any_sync(OM_FULL, candidate)) {
-          rr = px((uint32_t)k, (uint32_t)r, OM_S_JAM_COIN);
-          double coin = (double)((float)(rr.x >> 8) * 5.9604644775390625e-08f);   // [0,1)
-          hit = candidate && coin < __ldg(&c.jam_chance[candidate ? n_on : 0u]);
+        if (!second) {
+          uint32_t n2 = (r + 32 < R) ? rcnt[r + 32] : 0u;
+          if (__any_sync(OM_FULL, candidate || n2 >= 2u)) rr = px((uint32_t)k, (uint32_t)r, OM_S_JAM_COIN);
         }
+        uint32_t cw = second ? rr.y : rr.x;
+        double coin = (double)((float)(cw >> 8) * 5.9604644775390625e-08f);   // [0,1)
+        hit = candidate && coin < __ldg(&c.jam_chance[candidate ? n_on : 0u]);
       }
       unsigned m = __ballot_sync(OM_FULL, hit);
       #pragma unroll 1
@@ -878,7 +889,7 @@ struct Sim {
           pos = tape_next(OM_S_JAM_POS);
           dur = tape_next(OM_S_JAM_DUR) * c.jam_scale;
         } else {
-          uint32_t wz = __shfl_sync(OM_FULL, rr.z, b);
+          uint32_t wz = __shfl_sync(OM_FULL, second ? rr.w : rr.z, b);
           pos = sample_jam_position(k, rid, __shfl_sync(OM_FULL, n_on, b));
           dur = (double)sqrtf(om_exp1(wz)) * c.jam_scale;                         // Weibull(shape 2) * scale
         }

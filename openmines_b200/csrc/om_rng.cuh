@@ -55,6 +55,14 @@ __device__ __noinline__ float om_normal(uint32_t a, uint32_t b) {
   return r * cospif(2.0f * om_u01(b));
 }
 
+// standard normal, fast flavour for the per-minute breakdown block (MUFU log2 / rsqrt / cos; live-mode draws are
+// distribution-level only): ~12 instructions inline
+__device__ __forceinline__ float om_normal_fast(uint32_t a, uint32_t b) {
+  float x = -2.0f * __logf(om_u01(a));
+  float r = x * rsqrtf(fmaxf(x, 1e-30f));
+  return r * __cosf(6.283185307179586f * om_u01(b) - 3.14159265358979f);   // cos(2 pi u - pi) = -cos(2 pi u): same law
+}
+
 // bounded integer in [0, n): Lemire multiply-shift (no rejection); mirrored by oracle/philox.py
 __device__ __forceinline__ uint32_t om_randint(uint32_t x, uint32_t n) { return __umulhi(x, n); }
 

@@ -176,6 +176,9 @@ typedef struct OmOutputs {
 /* Byte offsets of the per-instance state arrays inside one state blob (om_state_bytes).  Truck
  * arrays have n_trucks elements, unit arrays n_shovels+n_dumpers, road arrays R. */
 typedef struct OmStateLayout {
+  /* Byte offsets inside one instance's state blob.  Every field is the offset of ITS ELEMENT 0; element i lives at
+   * offset + i * stride, where stride = t_stride for the per-truck record fields (all t_* except t_time / t_key),
+   * u_stride for the per-unit record fields (all u_* except u_rel_time / u_rel_key) and the element size otherwise. */
   uint32_t total_bytes;
   uint32_t hdr;
   uint32_t t_time, t_load, t_jstart, t_prejam, t_lastbrk, t_repair, t_total, t_cycle, t_dist, t_since; /* f64 */
@@ -192,6 +195,8 @@ typedef struct OmStateLayout {
   uint32_t s_qtotal, s_coming;                                                               /* u16 [L+D] */
   uint32_t s_tons, s_cap, s_ability;                                                         /* f64 [L+D] minute-sampled */
   uint32_t scratch;                                                                          /* f64 [max(U, 32)] */
+  uint32_t t_rec, u_rec;       /* start of the truck / unit record arrays */
+  uint32_t t_stride, u_stride; /* record sizes in bytes */
 } OmStateLayout;
 
 typedef struct OmEngine* OmHandle;

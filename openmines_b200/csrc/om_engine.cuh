@@ -180,10 +180,63 @@ struct Sim {
   __device__ __forceinline__ Sim(unsigned char* sm_, const RunParams& p, int lane_, long long inst_)
       : sm(sm_), c(p.c), ly(p.ly), out(p.out), lane(lane_), inst(inst_) {}
 
-#define F64(field, i) (((double*)(sm + ly.field))[i])
-#define U32A(field, i) (((uint32_t*)(sm + ly.field))[i])
-#define U16A(field, i) (((uint16_t*)(sm + ly.field))[i])
-#define U8A(field, i) (((uint8_t*)(sm + ly.field))[i])
+  // State accessors.  Per-truck and per-unit scalars live in fixed-size records (array of structures): the scalar
+  // DES code touches many fields of ONE truck / unit, so a record base + compile-time field offsets costs one
+  // address computation per handler instead of one constant-bank load + add per access (the kernel is
+  // instruction-fetch bound).  Fields scanned lane-parallel on every pop (t_time / t_key, u_rel_time / u_rel_key),
+  // roads, jams and per-site samples stay structure-of-arrays.  F64(t_load, i) etc. dispatch on the field name.
+#define OM_TSTRIDE 88u
+#define OM_USTRIDE 48u
+#define OM_SOA(type, field, i) (((type*)(sm + ly.field))[i])
+#define OM_TREC(type, off, i) (*(type*)(sm + ly.t_rec + (uint32_t)(i) * OM_TSTRIDE + (off)))
+#define OM_UREC(type, off, i) (*(type*)(sm + ly.u_rec + (uint32_t)(i) * OM_USTRIDE + (off)))
+#define OM_A_t_time(type, i) OM_SOA(type, t_time, i)
+#define OM_A_t_key(type, i) OM_SOA(type, t_key, i)
+#define OM_A_t_load(type, i) OM_TREC(type, 0, i)
+#define OM_A_t_jstart(type, i) OM_TREC(type, 8, i)
+#define OM_A_t_prejam(type, i) OM_TREC(type, 16, i)
+#define OM_A_t_lastbrk(type, i) OM_TREC(type, 24, i)
+#define OM_A_t_repair(type, i) OM_TREC(type, 32, i)
+#define OM_A_t_total(type, i) OM_TREC(type, 40, i)
+#define OM_A_t_cycle(type, i) OM_TREC(type, 48, i)
+#define OM_A_t_dist(type, i) OM_TREC(type, 56, i)
+#define OM_A_t_since(type, i) OM_TREC(type, 64, i)
+#define OM_A_t_rng(type, i) OM_TREC(type, 72, i)
+#define OM_A_t_svc(type, i) OM_TREC(type, 76, i)
+#define OM_A_t_epoch(type, i) OM_TREC(type, 78, i)
+#define OM_A_t_next(type, i) OM_TREC(type, 80, i)
+#define OM_A_t_unit(type, i) OM_TREC(type, 82, i)
+#define OM_A_t_phase(type, i) OM_TREC(type, 84, i)
+#define OM_A_t_status(type, i) OM_TREC(type, 85, i)
+#define OM_A_t_cur(type, i) OM_TREC(type, 86, i)
+#define OM_A_t_tgt(type, i) OM_TREC(type, 87, i)
+#define OM_A_u_rel_time(type, i) OM_SOA(type, u_rel_time, i)
+#define OM_A_u_rel_key(type, i) OM_SOA(type, u_rel_key, i)
+#define OM_A_u_last_start(type, i) OM_UREC(type, 0, i)
+#define OM_A_u_last_done(type, i) OM_UREC(type, 8, i)
+#define OM_A_u_tons(type, i) OM_UREC(type, 16, i)
+#define OM_A_u_lastbrk(type, i) OM_UREC(type, 24, i)
+#define OM_A_u_svc(type, i) OM_UREC(type, 32, i)
+#define OM_A_u_user(type, i) OM_UREC(type, 36, i)
+#define OM_A_u_head(type, i) OM_UREC(type, 38, i)
+#define OM_A_u_tail(type, i) OM_UREC(type, 40, i)
+#define OM_A_u_qlen(type, i) OM_UREC(type, 42, i)
+#define OM_A_u_repair(type, i) OM_UREC(type, 44, i)
+#define OM_A_r_repair_end(type, i) OM_SOA(type, r_repair_end, i)
+#define OM_A_j_pos(type, i) OM_SOA(type, j_pos, i)
+#define OM_A_j_start(type, i) OM_SOA(type, j_start, i)
+#define OM_A_j_end(type, i) OM_SOA(type, j_end, i)
+#define OM_A_j_road(type, i) OM_SOA(type, j_road, i)
+#define OM_A_s_qtotal(type, i) OM_SOA(type, s_qtotal, i)
+#define OM_A_s_coming(type, i) OM_SOA(type, s_coming, i)
+#define OM_A_s_tons(type, i) OM_SOA(type, s_tons, i)
+#define OM_A_s_cap(type, i) OM_SOA(type, s_cap, i)
+#define OM_A_s_ability(type, i) OM_SOA(type, s_ability, i)
+#define OM_A_scratch(type, i) OM_SOA(type, scratch, i)
+#define F64(field, i) OM_A_##field(double, i)
+#define U32A(field, i) OM_A_##field(uint32_t, i)
+#define U16A(field, i) OM_A_##field(uint16_t, i)
+#define U8A(field, i) OM_A_##field(uint8_t, i)
 
   // ---------------------------------------------------------------------------------------------
   // header <-> registers

@@ -39,7 +39,9 @@ _LAYOUT_FIELDS = ["total_bytes", "hdr", "t_time", "t_load", "t_jstart", "t_preja
                   "t_total", "t_cycle", "t_dist", "t_since", "t_key", "t_rng", "t_svc", "t_epoch", "t_next", "t_unit", "t_phase",
                   "t_status", "t_cur", "t_tgt", "u_rel_time", "u_last_start", "u_last_done", "u_tons", "u_lastbrk",
                   "u_rel_key", "u_svc", "u_user", "u_head", "u_tail", "u_qlen", "u_repair", "r_repair_end",
-                  "j_pos", "j_start", "j_end", "j_road", "s_qtotal", "s_coming", "s_tons", "s_cap", "s_ability", "scratch"]
+                  "j_pos", "j_start", "j_end", "j_road", "s_qtotal", "s_coming", "s_tons", "s_cap", "s_ability", "scratch",
+                  "t_rec", "u_rec", "t_stride", "u_stride"]
+_SOA_FIELDS = {"t_time", "t_key", "u_rel_time", "u_rel_key"}   # every other t_* / u_* field lives in a record
 
 
 class OmStateLayoutStruct(ctypes.Structure):
@@ -243,9 +245,15 @@ class BatchedMine:
         ly, pc = self.layout, self.pc
         T, U, S = pc.T, pc.S + pc.M, pc.S
 
+        raw = blob.tobytes()
+
         def arr(field, dtype, count):
             off = getattr(ly, field)
-            return np.frombuffer(blob.tobytes(), dtype=dtype, count=count, offset=off).copy()
+            item = np.dtype(dtype).itemsize
+            stride = item
+            if field not in _SOA_FIELDS and field[:2] in ("t_", "u_"):
+                stride = ly.t_stride if field[0] == "t" else ly.u_stride
+            return np.ndarray((count,), dtype=dtype, buffer=raw, offset=off, strides=(stride,)).copy()
         out = {}
         for f in ("t_time", "t_load", "t_jstart", "t_prejam", "t_lastbrk", "t_repair", "t_total", "t_cycle", "t_dist"):
             out[f] = arr(f, np.float64, T)
@@ -256,7 +264,7 @@ class BatchedMine:
             out[f] = arr(f, np.uint8, T)
         for f in ("u_rel_time", "u_last_start", "u_last_done", "u_tons"):
             out[f] = arr(f, np.float64, U)
-        out["u_lastbrk"] = arr("u_lastbrk", np.float64, S)
+        out["u_lastbrk"] = arr("u_lastbrk", np.float64, S)   # shovels only (dumpers never break down)
         out["u_svc"] = arr("u_svc", np.uint32, U)
         for f in ("u_user", "u_head", "u_tail", "u_qlen"):
             out[f] = arr(f, np.uint16, U)

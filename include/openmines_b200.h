@@ -177,8 +177,9 @@ typedef struct OmOutputs {
  * arrays have n_trucks elements, unit arrays n_shovels+n_dumpers, road arrays R. */
 typedef struct OmStateLayout {
   /* Byte offsets inside one instance's state blob.  Every field is the offset of ITS ELEMENT 0; element i lives at
-   * offset + i * stride, where stride = t_stride for the per-truck record fields (all t_* except t_time / t_key),
-   * u_stride for the per-unit record fields (all u_* except u_rel_time / u_rel_key) and the element size otherwise. */
+   * offset + i * stride, where stride = e_stride for t_time / t_key / t_phase (the truck's pending entry), t_stride for
+   * the other t_* fields (per-truck record), u_stride for the u_* fields except u_rel_time / u_rel_key / u_lastbrk
+   * (per-unit record), and the element size otherwise.  t_phase is a uint32. */
   uint32_t total_bytes;
   uint32_t hdr;
   uint32_t t_time, t_load, t_jstart, t_prejam, t_lastbrk, t_repair, t_total, t_cycle, t_dist, t_since; /* f64 */
@@ -197,6 +198,7 @@ typedef struct OmStateLayout {
   uint32_t scratch;                                                                          /* f64 [max(U, 32)] */
   uint32_t t_rec, u_rec;       /* start of the truck / unit record arrays */
   uint32_t t_stride, u_stride; /* record sizes in bytes */
+  uint32_t e_stride;           /* pending-entry size in bytes */
 } OmStateLayout;
 
 typedef struct OmEngine* OmHandle;

@@ -184,7 +184,9 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly) {
   const size_t T = c.T, U = c.U, R = c.R, J = c.J, NS = c.NS;
   ly.hdr = take(off, 8, OM_HDR_BYTES / 8);
   // scanned on every pop: structure of arrays
-  ly.t_time = take(off, 8, T); ly.u_rel_time = take(off, 8, U);
+  ly.t_time = take(off, 16, T);       // 16-byte entries {time, key, phase}
+  ly.t_key = ly.t_time + 8; ly.t_phase = ly.t_time + 12; ly.e_stride = OM_ESTRIDE;
+  ly.u_rel_time = take(off, 8, U);
   // per-truck / per-unit records (see the accessor table in om_engine.cuh)
   ly.t_stride = OM_TSTRIDE; ly.u_stride = OM_USTRIDE;
   ly.t_rec = take(off, 8, (size_t)T * OM_TSTRIDE / 8);
@@ -192,11 +194,12 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly) {
   ly.t_load = ly.t_rec + 0; ly.t_jstart = ly.t_rec + 8; ly.t_prejam = ly.t_rec + 16; ly.t_lastbrk = ly.t_rec + 24;
   ly.t_repair = ly.t_rec + 32; ly.t_total = ly.t_rec + 40; ly.t_cycle = ly.t_rec + 48; ly.t_dist = ly.t_rec + 56;
   ly.t_since = ly.t_rec + 64; ly.t_rng = ly.t_rec + 72; ly.t_svc = ly.t_rec + 76; ly.t_epoch = ly.t_rec + 78;
-  ly.t_next = ly.t_rec + 80; ly.t_unit = ly.t_rec + 82; ly.t_phase = ly.t_rec + 84; ly.t_status = ly.t_rec + 85;
+  ly.t_next = ly.t_rec + 80; ly.t_unit = ly.t_rec + 82; ly.t_status = ly.t_rec + 85;
   ly.t_cur = ly.t_rec + 86; ly.t_tgt = ly.t_rec + 87;
-  ly.u_last_start = ly.u_rec + 0; ly.u_last_done = ly.u_rec + 8; ly.u_tons = ly.u_rec + 16; ly.u_lastbrk = ly.u_rec + 24;
-  ly.u_svc = ly.u_rec + 32; ly.u_user = ly.u_rec + 36; ly.u_head = ly.u_rec + 38; ly.u_tail = ly.u_rec + 40;
-  ly.u_qlen = ly.u_rec + 42; ly.u_repair = ly.u_rec + 44;
+  ly.u_last_start = ly.u_rec + 0; ly.u_last_done = ly.u_rec + 8; ly.u_tons = ly.u_rec + 16;
+  ly.u_svc = ly.u_rec + 24; ly.u_user = ly.u_rec + 28; ly.u_head = ly.u_rec + 30; ly.u_tail = ly.u_rec + 32;
+  ly.u_qlen = ly.u_rec + 34; ly.u_repair = ly.u_rec + 36;
+  ly.u_lastbrk = take(off, 8, c.S);
   ly.r_repair_end = take(off, 8, R);
   ly.s_tons = take(off, 8, NS); ly.s_cap = take(off, 8, NS); ly.s_ability = take(off, 8, NS);
   ly.j_pos = take(off, 8, J); ly.j_start = take(off, 8, J); ly.j_end = take(off, 8, J);
@@ -204,7 +207,7 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly) {
   if (nscr < (R + 1) / 2) nscr = (R + 1) / 2;
   if (nscr < 32) nscr = 32;
   ly.scratch = take(off, 8, nscr);
-  ly.t_key = take(off, 4, T); ly.u_rel_key = take(off, 4, U);
+  ly.u_rel_key = take(off, 4, U);
   ly.j_road = take(off, 2, J); ly.s_qtotal = take(off, 2, NS); ly.s_coming = take(off, 2, NS);
   ly.total_bytes = (off + 15u) & ~15u;
 }

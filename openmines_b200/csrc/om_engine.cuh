@@ -183,15 +183,19 @@ struct Sim {
   // State accessors.  Per-truck and per-unit scalars live in fixed-size records (array of structures): the scalar
   // DES code touches many fields of ONE truck / unit, so a record base + compile-time field offsets costs one
   // address computation per handler instead of one constant-bank load + add per access (the kernel is
-  // instruction-fetch bound).  Fields scanned lane-parallel on every pop (t_time / t_key, u_rel_time / u_rel_key),
-  // roads, jams and per-site samples stay structure-of-arrays.  F64(t_load, i) etc. dispatch on the field name.
+  // instruction-fetch bound).  The pending entry of a truck {time, key, phase} is one 16-byte element (one LDS.128 per truck in the
+  // next-event scan, one STS.128 per schedule); u_rel_time / u_rel_key, roads, jams and per-site samples stay
+  // structure-of-arrays.  F64(t_load, i) etc. dispatch on the field name.
 #define OM_TSTRIDE 88u
-#define OM_USTRIDE 48u
+#define OM_USTRIDE 40u
+#define OM_ESTRIDE 16u   // pending entry of a truck: {double time; uint32 key; uint32 phase}
 #define OM_SOA(type, field, i) (((type*)(sm + ly.field))[i])
 #define OM_TREC(type, off, i) (*(type*)(sm + ly.t_rec + (uint32_t)(i) * OM_TSTRIDE + (off)))
 #define OM_UREC(type, off, i) (*(type*)(sm + ly.u_rec + (uint32_t)(i) * OM_USTRIDE + (off)))
-#define OM_A_t_time(type, i) OM_SOA(type, t_time, i)
-#define OM_A_t_key(type, i) OM_SOA(type, t_key, i)
+#define OM_TEV(type, off, i) (*(type*)(sm + ly.t_time + (uint32_t)(i) * OM_ESTRIDE + (off)))
+#define OM_A_t_time(type, i) OM_TEV(type, 0, i)
+#define OM_A_t_key(type, i) OM_TEV(type, 8, i)
+#define OM_A_t_phase(type, i) OM_TEV(type, 12, i)
 #define OM_A_t_load(type, i) OM_TREC(type, 0, i)
 #define OM_A_t_jstart(type, i) OM_TREC(type, 8, i)
 #define OM_A_t_prejam(type, i) OM_TREC(type, 16, i)
@@ -206,7 +210,6 @@ struct Sim {
 #define OM_A_t_epoch(type, i) OM_TREC(type, 78, i)
 #define OM_A_t_next(type, i) OM_TREC(type, 80, i)
 #define OM_A_t_unit(type, i) OM_TREC(type, 82, i)
-#define OM_A_t_phase(type, i) OM_TREC(type, 84, i)
 #define OM_A_t_status(type, i) OM_TREC(type, 85, i)
 #define OM_A_t_cur(type, i) OM_TREC(type, 86, i)
 #define OM_A_t_tgt(type, i) OM_TREC(type, 87, i)
@@ -215,13 +218,13 @@ struct Sim {
 #define OM_A_u_last_start(type, i) OM_UREC(type, 0, i)
 #define OM_A_u_last_done(type, i) OM_UREC(type, 8, i)
 #define OM_A_u_tons(type, i) OM_UREC(type, 16, i)
-#define OM_A_u_lastbrk(type, i) OM_UREC(type, 24, i)
-#define OM_A_u_svc(type, i) OM_UREC(type, 32, i)
-#define OM_A_u_user(type, i) OM_UREC(type, 36, i)
-#define OM_A_u_head(type, i) OM_UREC(type, 38, i)
-#define OM_A_u_tail(type, i) OM_UREC(type, 40, i)
-#define OM_A_u_qlen(type, i) OM_UREC(type, 42, i)
-#define OM_A_u_repair(type, i) OM_UREC(type, 44, i)
+#define OM_A_u_lastbrk(type, i) OM_SOA(type, u_lastbrk, i)
+#define OM_A_u_svc(type, i) OM_UREC(type, 24, i)
+#define OM_A_u_user(type, i) OM_UREC(type, 28, i)
+#define OM_A_u_head(type, i) OM_UREC(type, 30, i)
+#define OM_A_u_tail(type, i) OM_UREC(type, 32, i)
+#define OM_A_u_qlen(type, i) OM_UREC(type, 34, i)
+#define OM_A_u_repair(type, i) OM_UREC(type, 36, i)
 #define OM_A_r_repair_end(type, i) OM_SOA(type, r_repair_end, i)
 #define OM_A_j_pos(type, i) OM_SOA(type, j_pos, i)
 #define OM_A_j_start(type, i) OM_SOA(type, j_start, i)
@@ -324,7 +327,7 @@ struct Sim {
   __device__ __forceinline__ double draw_normal(int site, uint32_t epoch, uint32_t entity, double mu, double sigma) {
     if (RNG == OM_RNG_TAPE) return tape_next(site);
     Philox4 r = px(epoch, entity, site);
-    return mu + sigma * (double)om_normal(r.x, r.y);
+    return mu + sigma * (double)om_normal_fast(r.x, r.y);
   }
   __device__ __forceinline__ double draw_jitter(uint32_t epoch, uint32_t entity) {
     if (RNG == OM_RNG_DET) return 0.0;
@@ -339,11 +342,15 @@ struct Sim {
   // ---------------------------------------------------------------------------------------------
   // scheduling primitives
   // ---------------------------------------------------------------------------------------------
+  // one 16-byte store: {time, key, phase}
+  __device__ __forceinline__ void set_entry(int i, double t, uint32_t key, uint32_t phase) {
+    uint4 e;
+    e.x = (uint32_t)__double2loint(t); e.y = (uint32_t)__double2hiint(t); e.z = key; e.w = phase;
+    *(uint4*)(sm + ly.t_time + (uint32_t)i * OM_ESTRIDE) = e;
+  }
   __device__ __forceinline__ void sched_truck(int i, double t, uint32_t prio, uint8_t phase) {
-    F64(t_time, i) = t;
-    U32A(t_key, i) = prio | seq;
+    set_entry(i, t, prio | seq, phase);
     seq++;
-    U8A(t_phase, i) = phase;
   }
   // RL reward bookkeeping: a truck leaves a timed state (wait shovel / get shovel / get dumper / move record);
   // add the part of [t_since, now] that lies in the current reward window (rl_dispatch.py:221-273)
@@ -713,9 +720,7 @@ struct Sim {
       n_unrep++;
       emit(K_UNREPAIRABLE, (uint32_t)i, 0, 0, 0.0, 0.0);
       U8A(t_status, i) = ST_UNREPAIRABLE;
-      U8A(t_phase, i) = PH_DEAD;
-      F64(t_time, i) = om_inf();
-      U32A(t_key, i) = OM_KEY_SENTINEL;
+      set_entry(i, om_inf(), OM_KEY_SENTINEL, PH_DEAD);
       return;
     }
     uint8_t kind = (cur > c.L) ? K_MOVE_UNHAUL : (cur == 0 ? K_MOVE_INIT : K_MOVE_HAUL);
@@ -992,7 +997,7 @@ struct Sim {
       }
       if (found < 0) break;                                 // cannot happen: n_on trucks are on the road
       float cv = coverage(found, base_dist);
-      float xx = cv + sd * om_normal(r.y, r.z);
+      float xx = cv + sd * om_normal_fast(r.y, r.z);
       if (xx >= -0.5f * h && xx <= 1.0f + 0.5f * h) { x = xx; break; }
     }
     int idx = __float2int_rn(x * 999.0f);
@@ -1029,9 +1034,7 @@ struct Sim {
   // pause, errors, maintenance) are marked unlikely.  (No __noinline__ member functions: they would force the
   // register-resident Sim scalars onto the local-memory stack.)
   __device__ __forceinline__ void pause_for_order(int i, int kind, int rel_u, uint32_t rel_key, int& pend_truck, int& pend_kind) {
-    U8A(t_phase, i) = PH_AWAIT_ORDER;
-    F64(t_time, i) = om_inf();
-    U32A(t_key, i) = OM_KEY_SENTINEL;
+    set_entry(i, om_inf(), OM_KEY_SENTINEL, PH_AWAIT_ORDER);
     pend_truck = i; pend_kind = kind;
     if (rel_u >= 0) file_release(rel_u, rel_key);
   }
@@ -1049,15 +1052,17 @@ struct Sim {
       uint32_t bhi = 0x7FF00000u, blo = 0u, bk = OM_KEY_SENTINEL;
       int bid = -1;
       bool dup = false;
-      #pragma unroll 1
-      for (int i = lane; i < T; i += 32) {
-        uint2 tv = *(const uint2*)&F64(t_time, i);
-        uint32_t kk = U32A(t_key, i);
-        bool teq = (tv.y == bhi) && (tv.x == blo);
-        bool tlt = (tv.y < bhi) || (tv.y == bhi && tv.x < blo);
-        if (teq) dup = true;
-        if (tlt) dup = false;
-        if (tlt || (teq && kk < bk)) { bhi = tv.y; blo = tv.x; bk = kk; bid = i; }
+      {
+        const uint4* ev = (const uint4*)(sm + ly.t_time) + lane;
+        #pragma unroll 1
+        for (int i = lane; i < T; i += 32, ev += 32) {
+          const uint4 e = *ev;                         // {time lo, time hi, key, phase}
+          bool teq = (e.y == bhi) && (e.x == blo);
+          bool tlt = (e.y < bhi) || (e.y == bhi && e.x < blo);
+          if (teq) dup = true;
+          if (tlt) dup = false;
+          if (tlt || (teq && e.z < bk)) { bhi = e.y; blo = e.x; bk = e.z; bid = i; }
+        }
       }
       if (n_rel != 0) {
         #pragma unroll 1
@@ -1109,7 +1114,7 @@ struct Sim {
         seq++;
         goto L_GRANTED;
       }
-      switch (U8A(t_phase, i)) {
+      switch (U32A(t_phase, i)) {
         case PH_MOVE_ARRIVE: goto L_ARRIVE;
         case PH_LOAD_DONE: case PH_DUMP_DONE: goto L_SVC_DONE;
         case PH_MOVE_RET: goto L_MOVE_RET;
@@ -1155,9 +1160,7 @@ struct Sim {
         if (!(me && chain)) sched_truck(h, now, OM_KEY_NORMAL, (u < S) ? PH_LOAD_GRANTED : PH_DUMP_GRANTED);
       }
       if (!me) {
-        F64(t_time, i) = om_inf();
-        U32A(t_key, i) = OM_KEY_SENTINEL;
-        U8A(t_phase, i) = PH_WAITING;
+        set_entry(i, om_inf(), OM_KEY_SENTINEL, PH_WAITING);
       }
       int qi = me ? 0 : (int)U16A(u_qlen, u) - 1;
       if (cur <= L) {
@@ -1179,7 +1182,7 @@ struct Sim {
       emit(dump ? K_GET_DUMPER : K_GET_SHOVEL, (uint32_t)i, (uint32_t)(dump ? u - S : u), 0, 0.0, 0.0);
       seq++;                                                           // env.process(load/unload): Initialize URGENT
       if (!inl) {
-        F64(t_time, i) = now; U32A(t_key, i) = seq - 1; U8A(t_phase, i) = dump ? PH_DUMP_BEGIN : PH_LOAD_BEGIN;
+        set_entry(i, now, seq - 1, dump ? PH_DUMP_BEGIN : PH_LOAD_BEGIN);
         continue;
       }
     L_BEGIN: {                                                         // truck.py:221-228 / 238-242
@@ -1250,7 +1253,7 @@ struct Sim {
       apply_order(i, kind, site);
       seq++;                                                           // env.process(move): Initialize URGENT
       if (!inl) {
-        F64(t_time, i) = now; U32A(t_key, i) = seq - 1; U8A(t_phase, i) = PH_MOVE_BEGIN;
+        set_entry(i, now, seq - 1, PH_MOVE_BEGIN);
         goto L_AFTER_DEPART;
       }
     }
@@ -1313,7 +1316,7 @@ struct Sim {
     double w = 0.0, sh = 0.0, du = 0.0, mv = 0.0, jm = 0.0;
 #pragma unroll 1
     for (int i = lane; i < T; i += 32) {           // intervals still open at this decision
-      int ph = U8A(t_phase, i), cur = U8A(t_cur, i);
+      int ph = (int)U32A(t_phase, i), cur = U8A(t_cur, i);
       double st = F64(t_since, i);
       double lo = (st > rl_last) ? st : rl_last;
       double part = (lo < now) ? (now - lo) : 0.0;
@@ -1445,7 +1448,7 @@ struct Sim {
         fail(OM_IERR_BAD_ORDER);
       } else {
         apply_order(pt, pk, a);
-        F64(t_time, pt) = now; U32A(t_key, pt) = seq; U8A(t_phase, pt) = PH_MOVE_BEGIN;   // Initialize(move), URGENT
+        set_entry(pt, now, seq, PH_MOVE_BEGIN);   // Initialize(move), URGENT
         seq++;
       }
       h->pending_truck = -1; h->pending_kind = -1;
@@ -1520,7 +1523,7 @@ __device__ __forceinline__ void om_init_state(unsigned char* sm, const DevCfg& c
   for (int i = lane; i < c.T; i += 32) {
     F64(t_time, i) = 0.0;
     U32A(t_key, i) = (uint32_t)(1 + i);          // URGENT, after the monitors
-    U8A(t_phase, i) = PH_RUN_INIT;
+    U32A(t_phase, i) = PH_RUN_INIT;
     U8A(t_status, i) = ST_IDLE;
     U8A(t_cur, i) = OM_NOLOC;
     U8A(t_tgt, i) = OM_NOLOC;

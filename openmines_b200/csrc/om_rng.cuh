@@ -49,13 +49,7 @@ __device__ __forceinline__ float om_u01(uint32_t x) { return (float)((x >> 8) + 
 // -ln(u), u in (0,1]
 __device__ __forceinline__ float om_exp1(uint32_t x) { return -__logf(om_u01(x)); }
 
-// standard normal from two 32-bit words (Box-Muller, accurate libm flavours: draws are rare)
-__device__ __noinline__ float om_normal(uint32_t a, uint32_t b) {
-  float r = sqrtf(-2.0f * logf(om_u01(a)));
-  return r * cospif(2.0f * om_u01(b));
-}
-
-// standard normal, fast flavour for the per-minute breakdown block (MUFU log2 / rsqrt / cos; live-mode draws are
+// standard normal from two 32-bit words (Box-Muller on the MUFU log2 / rsqrt / cos units; live-mode draws are
 // distribution-level only): ~12 instructions inline
 __device__ __forceinline__ float om_normal_fast(uint32_t a, uint32_t b) {
   float x = -2.0f * __logf(om_u01(a));
@@ -65,6 +59,3 @@ __device__ __forceinline__ float om_normal_fast(uint32_t a, uint32_t b) {
 
 // bounded integer in [0, n): Lemire multiply-shift (no rejection); mirrored by oracle/philox.py
 __device__ __forceinline__ uint32_t om_randint(uint32_t x, uint32_t n) { return __umulhi(x, n); }
-
-// standard normal CDF, out of line (used only when a jam is created)
-__device__ __noinline__ float om_normcdf(float x) { return normcdff(x); }

@@ -40,8 +40,9 @@ _LAYOUT_FIELDS = ["total_bytes", "hdr", "t_time", "t_load", "t_jstart", "t_preja
                   "t_status", "t_cur", "t_tgt", "u_rel_time", "u_last_start", "u_last_done", "u_tons", "u_lastbrk",
                   "u_rel_key", "u_svc", "u_user", "u_head", "u_tail", "u_qlen", "u_repair", "r_repair_end",
                   "j_pos", "j_start", "j_end", "j_road", "s_qtotal", "s_coming", "s_tons", "s_cap", "s_ability", "scratch",
-                  "t_rec", "u_rec", "t_stride", "u_stride"]
-_SOA_FIELDS = {"t_time", "t_key", "u_rel_time", "u_rel_key"}   # every other t_* / u_* field lives in a record
+                  "t_rec", "u_rec", "t_stride", "u_stride", "e_stride"]
+_ENTRY_FIELDS = {"t_time", "t_key", "t_phase"}                # the truck's 16-byte pending entry
+_SOA_FIELDS = {"u_rel_time", "u_rel_key", "u_lastbrk"}         # every other t_* / u_* field lives in a record
 
 
 class OmStateLayoutStruct(ctypes.Structure):
@@ -251,7 +252,9 @@ class BatchedMine:
             off = getattr(ly, field)
             item = np.dtype(dtype).itemsize
             stride = item
-            if field not in _SOA_FIELDS and field[:2] in ("t_", "u_"):
+            if field in _ENTRY_FIELDS:
+                stride = ly.e_stride
+            elif field not in _SOA_FIELDS and field[:2] in ("t_", "u_"):
                 stride = ly.t_stride if field[0] == "t" else ly.u_stride
             return np.ndarray((count,), dtype=dtype, buffer=raw, offset=off, strides=(stride,)).copy()
         out = {}
@@ -260,8 +263,9 @@ class BatchedMine:
         out["t_key"] = arr("t_key", np.uint32, T)
         for f in ("t_svc", "t_epoch", "t_next", "t_unit"):
             out[f] = arr(f, np.uint16, T)
-        for f in ("t_phase", "t_status", "t_cur", "t_tgt"):
+        for f in ("t_status", "t_cur", "t_tgt"):
             out[f] = arr(f, np.uint8, T)
+        out["t_phase"] = arr("t_phase", np.uint32, T).astype(np.uint8)
         for f in ("u_rel_time", "u_last_start", "u_last_done", "u_tons"):
             out[f] = arr(f, np.float64, U)
         out["u_lastbrk"] = arr("u_lastbrk", np.float64, S)   # shovels only (dumpers never break down)

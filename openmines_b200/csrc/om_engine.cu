@@ -265,6 +265,13 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
     rc = upload(h, svc.data(), svc.size(), &c.svc_time);
   }
   if (rc == OM_OK) {
+    std::vector<int32_t> rb(c.NS + 1);
+    rb[0] = -1;
+    for (int cur = 1; cur <= c.NS; ++cur)
+      rb[cur] = (cur <= L) ? (cur - 1) * D - 1 : L + L * D + (cur - L - 1) * L - 1;
+    rc = upload(h, rb.data(), rb.size(), &c.rbase);
+  }
+  if (rc == OM_OK) {
     void* d = nullptr;
     e = cudaMalloc(&d, sizeof(unsigned long long));
     if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, cudaGetErrorString(e));

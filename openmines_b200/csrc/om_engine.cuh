@@ -68,6 +68,7 @@ struct DevCfg {
   const double* dcycle;
   const double* rdist;
   const double* load_time;
+  const int32_t* rbase;     // [NS+1] road_id(cur, tgt) = rbase[cur] + tgt
   const double* svc_time;   // [NT*U] load_time for shovels, dumper cycle for dumpers (built in om_create)
   const double* sptf_cost;
   const double* jam_chance;
@@ -141,17 +142,16 @@ __device__ __noinline__ double om_ddiv(double a, double b) { return a / b; }
 struct PySum {
   double s, c;
   __device__ __forceinline__ void init() { s = 0.0; c = 0.0; }
-  __device__ __forceinline__ void add(double x, bool neumaier) {
+  // branch-free step: the compensation is always accumulated and only used when the Neumaier flavour is selected
+  __device__ __forceinline__ void add(double x, bool /*neumaier*/) {
     double t = s + x;
-    if (neumaier) {
-      if (fabs(s) >= fabs(x)) c += (s - t) + x;
-      else c += (x - t) + s;
-    }
+    double big = (fabs(s) >= fabs(x)) ? s : x, small = (fabs(s) >= fabs(x)) ? x : s;
+    c += (big - t) + small;
     s = t;
   }
-  __device__ __forceinline__ double result() const {
+  __device__ __forceinline__ double result(bool neumaier) const {
     double r = s;
-    if (c != 0.0 && isfinite(c)) r += c;
+    if (neumaier && c != 0.0 && isfinite(c)) r += c;
     return r;
   }
 };
@@ -413,11 +413,9 @@ struct Sim {
   // ---------------------------------------------------------------------------------------------
   // road: distance + repair state (road.py:235-331)
   // ---------------------------------------------------------------------------------------------
-  __device__ __forceinline__ int road_id(int cur, int tgt) const {
-    if (cur == 0) return tgt - 1;
-    if (cur <= c.L) return c.L + (cur - 1) * c.D + (tgt - c.L - 1);
-    return c.L + c.L * c.D + (cur - c.L - 1) * c.L + (tgt - 1);
-  }
+  // directed road (cur -> tgt): charging->load i: i; load i->dump j: L + i*D + j; dump j->load i: L + L*D + j*L + i.
+  // rbase[cur] folds the per-origin part (built in om_create), so rid = rbase[cur] + tgt.
+  __device__ __forceinline__ int road_id(int cur, int tgt) const { return __ldg(&c.rbase[cur]) + tgt; }
   __device__ __forceinline__ double get_distance(int i, int cur, int tgt, uint32_t epoch) {
     int rid = road_id(cur, tgt);
     double end = F64(r_repair_end, rid);
@@ -570,7 +568,7 @@ struct Sim {
               ps.add(__ldg(&c.sptf_cost[__ldg(&c.ttype[base + b]) * L + lane]), neu);
             }
           }
-          if (lane < L) v = ps.result() + site_est(lane);
+          if (lane < L) v = ps.result(neu) + site_est(lane);
           r = argmin_lanes(v, L);
         }
         __syncwarp();
@@ -778,7 +776,7 @@ struct Sim {
         ps.add(F64(u_tons, u), neu);
         site_svc += U32A(u_svc, u);
       }
-      site_tons = ps.result();
+      site_tons = ps.result(neu);
       U16A(s_qtotal, lane) = (uint16_t)qtot;
       if (RL) {
         // minute-sampled values the observation reads (load_site.py:175-185, dump_site.py:69-78)
@@ -789,12 +787,12 @@ struct Sim {
           for (int u = ub; u < ue; ++u) pa.add(__ldg(&c.shovel_rate[u]) * (U8A(u_repair, u) ? 0.0 : 1.0), neu);
           double prod = __ldg(&c.site_prod[lane]);
           F64(s_cap, lane) = prod;
-          F64(s_ability, lane) = om_ddiv(pa.result(), prod);
+          F64(s_ability, lane) = om_ddiv(pa.result(neu), prod);
         } else {
           PySum pd; pd.init();
 #pragma unroll 1
           for (int u = ub; u < ue; ++u) pd.add(om_ddiv(F64(u_tons, u), __ldg(&c.dcycle[u - c.S])), neu);
-          F64(s_cap, lane) = pd.result();
+          F64(s_cap, lane) = pd.result(neu);
           F64(s_ability, lane) = 1.0;
         }
       }
@@ -808,7 +806,7 @@ struct Sim {
       pm.add(__shfl_sync(OM_FULL, site_tons, L + j), neu);
       svc_total += (int)__shfl_sync(OM_FULL, site_svc, L + j);
     }
-    double produce = pm.result();
+    double produce = pm.result(neu);
     reported_tons = produce;
     uint32_t n_work = 0, n_wait = 0, n_lu = 0, n_mov = 0, n_rep = 0;
     #pragma unroll 1
@@ -1081,13 +1079,12 @@ struct Sim {
       bool cand = (bhi == mhi) && (blo == mlo);
       uint32_t mk = __reduce_min_sync(OM_FULL, cand ? bk : OM_KEY_SENTINEL);
       unsigned cands = __ballot_sync(OM_FULL, cand);
-      unsigned ball = __ballot_sync(OM_FULL, cand && bk == mk);
-      int winner = __ffs(ball) - 1;
-      int id = __shfl_sync(OM_FULL, bid, winner);
-      bool wdup = __shfl_sync(OM_FULL, (int)dup, winner) != 0;
+      // keys are unique, so exactly one lane holds (tmin, mk); a tie inside the only candidate lane shows in its dup flag
+      int id = (int)__reduce_min_sync(OM_FULL, (cand && bk == mk) ? (uint32_t)bid : 0x7FFFFFFFu);
+      bool anydup = __any_sync(OM_FULL, cand && dup);
       double tmin = __hiloint2double((int)mhi, (int)mlo);
       bool is_tick = (tick_time < tmin) || (tick_time == tmin && tick_key < mk);
-      bool unique = (__popc(cands) == 1) && !wdup && (tick_time != tmin);
+      bool unique = (__popc(cands) == 1) && !anydup && (tick_time != tmin);
       if (is_tick) tmin = tick_time;
       if (!(tmin < until) || (err != OM_IERR_NONE && err != OM_IERR_TRACE_OVERFLOW)) break;
       now = tmin;
@@ -1505,7 +1502,7 @@ struct Sim {
     const bool neu = c.sum_mode != 0;
     #pragma unroll 1
     for (int u = c.S; u < c.U; ++u) ps.add(F64(u_tons, u), neu);
-    return ps.result();
+    return ps.result(neu);
   }
 };
 

@@ -199,6 +199,7 @@ typedef struct OmStateLayout {
   uint32_t t_rec, u_rec;       /* start of the truck / unit record arrays */
   uint32_t t_stride, u_stride; /* record sizes in bytes */
   uint32_t e_stride;           /* pending-entry size in bytes */
+  uint32_t hot_bytes;          /* prefix of the blob the kernels stage in shared memory (== total_bytes unless split) */
 } OmStateLayout;
 
 typedef struct OmEngine* OmHandle;

@@ -24,12 +24,13 @@ __global__ void om_reset_kernel(DevCfg c, OmStateLayout ly, unsigned char* state
   om_init_state(state + (size_t)inst * ly.total_bytes, c, ly, threadIdx.x & 31, seeds[inst], dispatcher[inst]);
 }
 
-template <int RNG, bool TRACE>
+template <int RNG, bool TRACE, bool SPLIT>
 __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(const __grid_constant__ RunParams p) {
   extern __shared__ __align__(16) unsigned char om_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* sm = om_smem + (size_t)warp * p.ly.total_bytes;
-  const uint32_t n16 = p.ly.total_bytes >> 4;
+  const uint32_t staged = SPLIT ? p.ly.hot_bytes : p.ly.total_bytes;   // SPLIT: truck records / jam pool stay in HBM
+  unsigned char* sm = om_smem + (size_t)warp * staged;
+  const uint32_t n16 = staged >> 4;
   while (true) {
     unsigned long long inst = 0;
     if (lane == 0) inst = atomicAdd(p.counter, 1ull);
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
       for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
     }
     __syncwarp();
-    Sim<RNG, TRACE, false> s(sm, p, lane, (long long)inst);
+    Sim<RNG, TRACE, false, SPLIT> s(sm, g, p, lane, (long long)inst);
     s.load_hdr(p);
     s.run(p.until);
     s.store_hdr(p);
@@ -72,12 +73,13 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
 
 // Batched gym-style step: one warp per env; the state blob round-trips HBM every step (this kernel IS
 // HBM-bound: 2 * S_state + obs row per env step).
-template <int RNG>
+template <int RNG, bool SPLIT>
 __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_step_kernel(const __grid_constant__ RunParams p) {
   extern __shared__ __align__(16) unsigned char om_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* sm = om_smem + (size_t)warp * p.ly.total_bytes;
-  const uint32_t n16 = p.ly.total_bytes >> 4;
+  const uint32_t staged = SPLIT ? p.ly.hot_bytes : p.ly.total_bytes;
+  unsigned char* sm = om_smem + (size_t)warp * staged;
+  const uint32_t n16 = staged >> 4;
   while (true) {
     unsigned long long inst = 0;
     if (lane == 0) inst = atomicAdd(p.counter, 1ull);
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_step_kernel(c
       for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
     }
     __syncwarp();
-    Sim<RNG, false, true> s(sm, p, lane, (long long)inst);
+    Sim<RNG, false, true, SPLIT> s(sm, g, p, lane, (long long)inst);
     s.load_hdr(p);
     s.rl_step(p);
     s.store_hdr(p);
@@ -143,6 +145,7 @@ struct OmEngine {
   const uint8_t* tape_sites = nullptr;
   const int64_t* tape_offsets = nullptr;
   int grid = 0, block = 0, smem = 0, warps = 0;
+  bool split = false;   // cold part of the blob accessed in place in HBM
   std::string err;
 };
 
@@ -182,33 +185,36 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly) {
   memset(&ly, 0, sizeof(ly));
   uint32_t off = 0;
   const size_t T = c.T, U = c.U, R = c.R, J = c.J, NS = c.NS;
+  // ---- hot part (always staged in shared memory) ----
   ly.hdr = take(off, 8, OM_HDR_BYTES / 8);
-  // scanned on every pop: structure of arrays
-  ly.t_time = take(off, 16, T);       // 16-byte entries {time, key, phase}
+  ly.t_time = take(off, 16, T);       // 16-byte entries {time, key, phase}, scanned on every pop
   ly.t_key = ly.t_time + 8; ly.t_phase = ly.t_time + 12; ly.e_stride = OM_ESTRIDE;
   ly.u_rel_time = take(off, 8, U);
-  // per-truck / per-unit records (see the accessor table in om_engine.cuh)
   ly.t_stride = OM_TSTRIDE; ly.u_stride = OM_USTRIDE;
-  ly.t_rec = take(off, 8, (size_t)T * OM_TSTRIDE / 8);
   ly.u_rec = take(off, 8, (size_t)U * OM_USTRIDE / 8);
-  ly.t_load = ly.t_rec + 0; ly.t_jstart = ly.t_rec + 8; ly.t_prejam = ly.t_rec + 16; ly.t_lastbrk = ly.t_rec + 24;
-  ly.t_repair = ly.t_rec + 32; ly.t_total = ly.t_rec + 40; ly.t_cycle = ly.t_rec + 48; ly.t_dist = ly.t_rec + 56;
-  ly.t_since = ly.t_rec + 64; ly.t_rng = ly.t_rec + 72; ly.t_svc = ly.t_rec + 76; ly.t_epoch = ly.t_rec + 78;
-  ly.t_next = ly.t_rec + 80; ly.t_unit = ly.t_rec + 82; ly.t_status = ly.t_rec + 85;
-  ly.t_cur = ly.t_rec + 86; ly.t_tgt = ly.t_rec + 87;
   ly.u_last_start = ly.u_rec + 0; ly.u_last_done = ly.u_rec + 8; ly.u_tons = ly.u_rec + 16;
   ly.u_svc = ly.u_rec + 24; ly.u_user = ly.u_rec + 28; ly.u_head = ly.u_rec + 30; ly.u_tail = ly.u_rec + 32;
   ly.u_qlen = ly.u_rec + 34; ly.u_repair = ly.u_rec + 36;
   ly.u_lastbrk = take(off, 8, c.S);
   ly.r_repair_end = take(off, 8, R);
   ly.s_tons = take(off, 8, NS); ly.s_cap = take(off, 8, NS); ly.s_ability = take(off, 8, NS);
-  ly.j_pos = take(off, 8, J); ly.j_start = take(off, 8, J); ly.j_end = take(off, 8, J);
   size_t nscr = U;
   if (nscr < (R + 1) / 2) nscr = (R + 1) / 2;
   if (nscr < 32) nscr = 32;
   ly.scratch = take(off, 8, nscr);
   ly.u_rel_key = take(off, 4, U);
-  ly.j_road = take(off, 2, J); ly.s_qtotal = take(off, 2, NS); ly.s_coming = take(off, 2, NS);
+  ly.s_qtotal = take(off, 2, NS); ly.s_coming = take(off, 2, NS);
+  ly.hot_bytes = (off + 15u) & ~15u;
+  off = ly.hot_bytes;
+  // ---- cold part (truck records, jam pool): in shared memory too unless the engine runs split ----
+  ly.t_rec = take(off, 8, (size_t)T * OM_TSTRIDE / 8);
+  ly.t_load = ly.t_rec + 0; ly.t_jstart = ly.t_rec + 8; ly.t_prejam = ly.t_rec + 16; ly.t_lastbrk = ly.t_rec + 24;
+  ly.t_repair = ly.t_rec + 32; ly.t_total = ly.t_rec + 40; ly.t_cycle = ly.t_rec + 48; ly.t_dist = ly.t_rec + 56;
+  ly.t_since = ly.t_rec + 64; ly.t_rng = ly.t_rec + 72; ly.t_svc = ly.t_rec + 76; ly.t_epoch = ly.t_rec + 78;
+  ly.t_next = ly.t_rec + 80; ly.t_unit = ly.t_rec + 82; ly.t_status = ly.t_rec + 85;
+  ly.t_cur = ly.t_rec + 86; ly.t_tgt = ly.t_rec + 87;
+  ly.j_pos = take(off, 8, J); ly.j_start = take(off, 8, J); ly.j_end = take(off, 8, J);
+  ly.j_road = take(off, 2, J);
   ly.total_bytes = (off + 15u) & ~15u;
 }
 
@@ -284,28 +290,37 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
     int maxsm = 0;
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     int limit = maxsm < OM_SMEM_LIMIT ? maxsm : OM_SMEM_LIMIT;
-    int w = limit / (int)h->ly.total_bytes;
+    // Whole blob in shared memory when that leaves at least 8 resident warps per SM; otherwise only the hot part
+    // (pending entries, unit records, roads) is staged and truck records / the jam pool are accessed in place.
+    h->split = (limit / (int)h->ly.total_bytes) < 8;
+    if (const char* ev = getenv("OM_SPLIT")) h->split = atoi(ev) != 0;   // tuning knob
+    const int staged = (int)(h->split ? h->ly.hot_bytes : h->ly.total_bytes);
+    int w = limit / staged;
     if (w > OM_MAX_WARPS_PER_CTA) w = OM_MAX_WARPS_PER_CTA;
     if (const char* ev = getenv("OM_WARPS_PER_CTA")) {   // tuning knob (occupancy experiments)
       int wv = atoi(ev);
       if (wv >= 1 && wv < w) w = wv;
     }
-    if (w < 1) rc = set_err(h, OM_E_UNSUPPORTED, "om_create: one instance's state does not fit in shared memory");
+    if (w < 1) rc = set_err(h, OM_E_UNSUPPORTED, "om_create: one instance's hot state does not fit in shared memory");
     else {
-      h->warps = w; h->block = w * 32; h->smem = w * (int)h->ly.total_bytes;
+      // no more resident warps than instances per SM need (balances the last wave)
+      long long per_sm = (n_instances + sms - 1) / sms;
+      if (per_sm < w) w = (int)(per_sm < 1 ? 1 : per_sm);
+      h->warps = w; h->block = w * 32; h->smem = w * staged;
       long long ctas = (n_instances + w - 1) / w;
       h->grid = (int)(ctas < sms ? ctas : sms);
-      const void* fns[6] = {(const void*)om_run_kernel<OM_RNG_DET, false>, (const void*)om_run_kernel<OM_RNG_PHILOX, false>,
-                            (const void*)om_run_kernel<OM_RNG_TAPE, false>, (const void*)om_run_kernel<OM_RNG_DET, true>,
-                            (const void*)om_run_kernel<OM_RNG_PHILOX, true>, (const void*)om_run_kernel<OM_RNG_TAPE, true>};
-      for (int i = 0; i < 6 && rc == OM_OK; ++i) {
+      const void* fns[] = {
+          (const void*)om_run_kernel<OM_RNG_DET, false, false>, (const void*)om_run_kernel<OM_RNG_PHILOX, false, false>,
+          (const void*)om_run_kernel<OM_RNG_TAPE, false, false>, (const void*)om_run_kernel<OM_RNG_DET, true, false>,
+          (const void*)om_run_kernel<OM_RNG_PHILOX, true, false>, (const void*)om_run_kernel<OM_RNG_TAPE, true, false>,
+          (const void*)om_run_kernel<OM_RNG_DET, false, true>, (const void*)om_run_kernel<OM_RNG_PHILOX, false, true>,
+          (const void*)om_run_kernel<OM_RNG_TAPE, false, true>, (const void*)om_run_kernel<OM_RNG_DET, true, true>,
+          (const void*)om_run_kernel<OM_RNG_PHILOX, true, true>, (const void*)om_run_kernel<OM_RNG_TAPE, true, true>,
+          (const void*)om_step_kernel<OM_RNG_DET, false>, (const void*)om_step_kernel<OM_RNG_PHILOX, false>,
+          (const void*)om_step_kernel<OM_RNG_TAPE, false>, (const void*)om_step_kernel<OM_RNG_DET, true>,
+          (const void*)om_step_kernel<OM_RNG_PHILOX, true>, (const void*)om_step_kernel<OM_RNG_TAPE, true>};
+      for (size_t i = 0; i < sizeof(fns) / sizeof(fns[0]) && rc == OM_OK; ++i) {
         e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
-        if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-      }
-      const void* sfns[3] = {(const void*)om_step_kernel<OM_RNG_DET>, (const void*)om_step_kernel<OM_RNG_PHILOX>,
-                             (const void*)om_step_kernel<OM_RNG_TAPE>};
-      for (int i = 0; i < 3 && rc == OM_OK; ++i) {
-        e = cudaFuncSetAttribute(sfns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
         if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
       }
     }
@@ -380,10 +395,15 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
   const bool trace = p.out.trace != nullptr || p.out.orders != nullptr;   // event-trace / order-log variant
-#define OM_LAUNCH(MODE)                                                                     \
-  do {                                                                                      \
-    if (trace) om_run_kernel<MODE, true><<<h->grid, h->block, h->smem, st>>>(p);            \
-    else om_run_kernel<MODE, false><<<h->grid, h->block, h->smem, st>>>(p);                 \
+#define OM_LAUNCH(MODE)                                                                             \
+  do {                                                                                              \
+    if (h->split) {                                                                                 \
+      if (trace) om_run_kernel<MODE, true, true><<<h->grid, h->block, h->smem, st>>>(p);            \
+      else om_run_kernel<MODE, false, true><<<h->grid, h->block, h->smem, st>>>(p);                 \
+    } else {                                                                                        \
+      if (trace) om_run_kernel<MODE, true, false><<<h->grid, h->block, h->smem, st>>>(p);           \
+      else om_run_kernel<MODE, false, false><<<h->grid, h->block, h->smem, st>>>(p);                \
+    }                                                                                               \
   } while (0)
   switch (h->rng_mode) {
     case OM_RNG_DET: OM_LAUNCH(OM_RNG_DET); break;
@@ -418,9 +438,15 @@ int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* str
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
   switch (h->rng_mode) {
-    case OM_RNG_DET: om_step_kernel<OM_RNG_DET><<<h->grid, h->block, h->smem, st>>>(p); break;
-    case OM_RNG_PHILOX: om_step_kernel<OM_RNG_PHILOX><<<h->grid, h->block, h->smem, st>>>(p); break;
-    default: om_step_kernel<OM_RNG_TAPE><<<h->grid, h->block, h->smem, st>>>(p); break;
+#define OM_STEP(MODE)                                                                        \
+  do {                                                                                       \
+    if (h->split) om_step_kernel<MODE, true><<<h->grid, h->block, h->smem, st>>>(p);         \
+    else om_step_kernel<MODE, false><<<h->grid, h->block, h->smem, st>>>(p);                 \
+  } while (0)
+    case OM_RNG_DET: OM_STEP(OM_RNG_DET); break;
+    case OM_RNG_PHILOX: OM_STEP(OM_RNG_PHILOX); break;
+    default: OM_STEP(OM_RNG_TAPE); break;
+#undef OM_STEP
   }
   CK(cudaGetLastError());
   return OM_OK;

@@ -156,9 +156,10 @@ struct PySum {
   }
 };
 
-template <int RNG, bool TRACE, bool RL>
+template <int RNG, bool TRACE, bool RL, bool SPLIT = false>
 struct Sim {
-  unsigned char* sm;
+  unsigned char* sm;     // shared-memory image of the blob (SPLIT: only its first ly.hot_bytes)
+  unsigned char* cold;   // base for the cold fields (truck records, jam pool): sm, or the blob in HBM when SPLIT
   const DevCfg& c;
   const OmStateLayout& ly;
   const OmOutputs& out;
@@ -177,8 +178,8 @@ struct Sim {
   Philox4 ordw;   // words of the current order's Philox call (PHILOX mode)
   double rl_last, rl_last_prod, acc_wait, acc_shovel, acc_dumper, acc_move, acc_jam;   // RL only
 
-  __device__ __forceinline__ Sim(unsigned char* sm_, const RunParams& p, int lane_, long long inst_)
-      : sm(sm_), c(p.c), ly(p.ly), out(p.out), lane(lane_), inst(inst_) {}
+  __device__ __forceinline__ Sim(unsigned char* sm_, unsigned char* blob, const RunParams& p, int lane_, long long inst_)
+      : sm(sm_), cold(SPLIT ? blob : sm_), c(p.c), ly(p.ly), out(p.out), lane(lane_), inst(inst_) {}
 
   // State accessors.  Per-truck and per-unit scalars live in fixed-size records (array of structures): the scalar
   // DES code touches many fields of ONE truck / unit, so a record base + compile-time field offsets costs one
@@ -190,7 +191,8 @@ struct Sim {
 #define OM_USTRIDE 40u
 #define OM_ESTRIDE 16u   // pending entry of a truck: {double time; uint32 key; uint32 phase}
 #define OM_SOA(type, field, i) (((type*)(sm + ly.field))[i])
-#define OM_TREC(type, off, i) (*(type*)(sm + ly.t_rec + (uint32_t)(i) * OM_TSTRIDE + (off)))
+#define OM_SOAC(type, field, i) (((type*)(cold + ly.field))[i])
+#define OM_TREC(type, off, i) (*(type*)(cold + ly.t_rec + (uint32_t)(i) * OM_TSTRIDE + (off)))
 #define OM_UREC(type, off, i) (*(type*)(sm + ly.u_rec + (uint32_t)(i) * OM_USTRIDE + (off)))
 #define OM_TEV(type, off, i) (*(type*)(sm + ly.t_time + (uint32_t)(i) * OM_ESTRIDE + (off)))
 #define OM_A_t_time(type, i) OM_TEV(type, 0, i)
@@ -226,10 +228,10 @@ struct Sim {
 #define OM_A_u_qlen(type, i) OM_UREC(type, 34, i)
 #define OM_A_u_repair(type, i) OM_UREC(type, 36, i)
 #define OM_A_r_repair_end(type, i) OM_SOA(type, r_repair_end, i)
-#define OM_A_j_pos(type, i) OM_SOA(type, j_pos, i)
-#define OM_A_j_start(type, i) OM_SOA(type, j_start, i)
-#define OM_A_j_end(type, i) OM_SOA(type, j_end, i)
-#define OM_A_j_road(type, i) OM_SOA(type, j_road, i)
+#define OM_A_j_pos(type, i) OM_SOAC(type, j_pos, i)
+#define OM_A_j_start(type, i) OM_SOAC(type, j_start, i)
+#define OM_A_j_end(type, i) OM_SOAC(type, j_end, i)
+#define OM_A_j_road(type, i) OM_SOAC(type, j_road, i)
 #define OM_A_s_qtotal(type, i) OM_SOA(type, s_qtotal, i)
 #define OM_A_s_coming(type, i) OM_SOA(type, s_coming, i)
 #define OM_A_s_tons(type, i) OM_SOA(type, s_tons, i)
@@ -1512,6 +1514,7 @@ struct Sim {
 __device__ __forceinline__ void om_init_state(unsigned char* sm, const DevCfg& c, const OmStateLayout& ly, int lane,
                                               uint64_t seed, int dispatcher) {
   const double inf = om_inf();
+  unsigned char* cold = sm;   // the reset kernel writes the blob in place
   // zero everything first
   #pragma unroll 1
   for (uint32_t o = lane * 8; o < ly.total_bytes; o += 256) *(unsigned long long*)(sm + o) = 0ull;

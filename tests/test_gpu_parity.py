@@ -43,6 +43,29 @@ def test_tape_replay_vs_golden(north_pit):
         assert s["err"] == 0
 
 
+def test_split_state_mode_vs_golden(north_pit, monkeypatch):
+    """The split layout (truck records + jam pool accessed in place in HBM, only the hot part staged in shared
+    memory; chosen automatically for big mines) must give the same bits: forced here on north_pit, det + tape."""
+    monkeypatch.setenv("OM_SPLIT", "1")
+    cases = [(d, 0) for d in DISPATCHERS]
+    mine = _mine(north_pit, len(cases))
+    assert mine.layout.hot_bytes < mine.layout.total_bytes
+    assert mine.launch_info()["smem_bytes"] == mine.launch_info()["warps_per_cta"] * mine.layout.hot_bytes
+    mine.reset([d for d, _ in cases], seeds=[s for _, s in cases], rng_mode="det")
+    res = mine.run(trace_capacity=4096, site_ticks=True, order_capacity=2048)
+    for i, (d, seed) in enumerate(cases):
+        g = Golden("det_north_pit_mine_%s_s%d" % (d, seed))
+        diffs = engine_vs_ref(g, mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s seed %d: %s" % (d, seed, diffs[:5])
+    goldens = [Golden("live_north_pit_mine_%s_s11" % d) for d in DISPATCHERS]
+    mine = _mine(north_pit, len(DISPATCHERS))
+    mine.reset(DISPATCHERS, rng_mode="tape", tapes=[g.tape for g in goldens])
+    res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=2048)
+    for i, d in enumerate(DISPATCHERS):
+        diffs = engine_vs_ref(goldens[i], mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s: %s" % (d, diffs[:5])
+
+
 def test_tape_replay_short(short_mine):
     names = ["RandomDispatcher", "SQDispatcher"]
     goldens = [Golden("live_north_pit_mine_short_%s_s3" % d) for d in names]

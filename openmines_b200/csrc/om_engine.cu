@@ -198,8 +198,7 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly) {
   ly.u_lastbrk = take(off, 8, c.S);
   ly.r_repair_end = take(off, 8, R);
   ly.s_tons = take(off, 8, NS); ly.s_cap = take(off, 8, NS); ly.s_ability = take(off, 8, NS);
-  size_t nscr = U;
-  if (nscr < (R + 1) / 2) nscr = (R + 1) / 2;
+  size_t nscr = ((U + 1) & ~(size_t)1) + (R + 1) / 2;   // unit_est_all() results [U] + per-road counters [R] (u32)
   if (nscr < 32) nscr = 32;
   ly.scratch = take(off, 8, nscr);
   ly.u_rel_key = take(off, 4, U);

@@ -510,6 +510,39 @@ struct Sim {
     return idx;
   }
 
+  // Trucks on the roads from location `from` to every candidate site of an order (candidate q <-> location tgt0 + q):
+  // lane q gets the number of trucks whose (current, target) pair is that road (mine.update_road_status, mine.py:182-187),
+  // the number of MOVING ones (Road.truck_on_road) and the sum of their capacities in truck order.  Lanes run over
+  // trucks, one ballot per candidate; the candidate's lane walks its own mask.
+  __device__ __forceinline__ void road_load(int from, int tgt0, int ncand, int& pair_cnt, int& on_cnt, double& capsum) {
+    const int T = c.T;
+    pair_cnt = 0; on_cnt = 0; capsum = 0.0;
+#pragma unroll 1
+    for (int base = 0; base < T; base += 32) {
+      int o = base + lane;
+      int tg = -1;
+      bool mv = false;
+      if (o < T && U8A(t_cur, o) == from) { tg = (int)U8A(t_tgt, o) - tgt0; mv = U8A(t_status, o) == ST_MOVING; }
+      if (!__any_sync(OM_FULL, tg >= 0 && tg < ncand)) continue;
+      unsigned mvmask = __ballot_sync(OM_FULL, mv);
+      unsigned my_pair = 0;
+#pragma unroll 1
+      for (int q = 0; q < ncand; ++q) {
+        unsigned mp = __ballot_sync(OM_FULL, tg == q);
+        if (lane == q) my_pair = mp;
+      }
+      unsigned my_on = my_pair & mvmask;
+      pair_cnt += __popc(my_pair);
+      on_cnt += __popc(my_on);
+#pragma unroll 1
+      while (my_on) {
+        int b = __ffs(my_on) - 1;
+        my_on &= my_on - 1;
+        capsum += __ldg(&c.cap[base + b]);
+      }
+    }
+  }
+
   // ---------------------------------------------------------------------------------------------
   // the six built-in dispatchers as device functions (dispatch_algorithms/*.py) behind
   // give_init_order / give_haul_order / give_back_order.  Returns the site index, or -1 on error.
@@ -598,14 +631,13 @@ struct Sim {
         double val = om_inf();
         if (kind == OM_ORDER_HAUL) {
           unit_est_all(false);
+          int pc_, cnt;
+          double cs_;
+          road_load(cur, 1 + L, D, pc_, cnt, cs_);
           if (lane < D) {
             int site = L + lane, tgt = 1 + site;
             int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
             double dt0 = __ldg(&c.dcycle[ub - c.S]);
-            int cnt = 0;
-#pragma unroll 1
-            for (int o = 0; o < c.T; ++o)
-              cnt += (U8A(t_status, o) == ST_MOVING && U8A(t_cur, o) == cur && U8A(t_tgt, o) == tgt) ? 1 : 0;
             double reach = now + om_ddiv(60.0 * __ldg(&c.rdist[road_id(cur, tgt)]), v);
             double avail = (now + site_est(site)) + om_ddiv((double)cnt, (double)(ue - ub)) * dt0;
             double service = (avail > reach) ? avail : reach;      // np.maximum
@@ -614,13 +646,12 @@ struct Sim {
           r = argmin_lanes(val, D);
         } else {
           unit_est_all(true);
+          int pc_, oc_;
+          double capsum;                                           // trucks on the charging-site road, also for back orders (:71)
+          road_load(0, 1, L, pc_, oc_, capsum);
           if (lane < L) {
             int tgt = 1 + lane;
             int ub = __ldg(&c.ubeg[lane]), ue = __ldg(&c.ubeg[lane + 1]);
-            double capsum = 0.0;                                   // trucks on the charging-site road, also for back orders (:71)
-#pragma unroll 1
-            for (int o = 0; o < c.T; ++o)
-              if (U8A(t_status, o) == ST_MOVING && U8A(t_cur, o) == 0 && U8A(t_tgt, o) == tgt) capsum += __ldg(&c.cap[o]);
             double prod = __ldg(&c.site_prod[lane]);
             double dist = __ldg(&c.rdist[road_id(cur, tgt)]);
             double reach = now + om_ddiv(60.0 * dist, v);
@@ -1372,44 +1403,46 @@ struct Sim {
     for (int q = lane; q < 1 + NS; q += 32) ob[o1 + q] = (q == cur) ? 1.f : 0.f;
     // candidate roads from the current location
     const int ncand = (kind == OM_ORDER_HAUL) ? D : L;
+    {
+      int pair_cnt, on_cnt;
+      double capsum;
+      road_load(cur, (kind == OM_ORDER_HAUL) ? 1 + L : 1, ncand, pair_cnt, on_cnt, capsum);
 #pragma unroll 1
-    for (int q = lane; q < C; q += 32) {
-      float tt = 0.f, tc = 0.f, sw = 0.f;
-      if (q < ncand) {
-        int tgt = (kind == OM_ORDER_HAUL) ? 1 + L + q : 1 + q;
-        int site = tgt - 1;
-        int pair_cnt = 0, on_cnt = 0;
-        double capsum = 0.0;
-#pragma unroll 1
-        for (int o = 0; o < T; ++o) {
-          if (U8A(t_cur, o) == cur && U8A(t_tgt, o) == tgt) {          // mine.update_road_status pair counts
-            pair_cnt++;
-            if (U8A(t_status, o) == ST_MOVING) { on_cnt++; capsum += __ldg(&c.cap[o]); }   // Road.truck_on_road
+      for (int q = lane; q < C; q += 32) {          // C <= 32: one trip, lane q = candidate q
+        float tt = 0.f, tc = 0.f, sw = 0.f;
+        if (q < ncand) {
+          int tgt = (kind == OM_ORDER_HAUL) ? 1 + L + q : 1 + q;
+          int site = tgt - 1;
+          double dist = __ldg(&c.rdist[road_id(cur, tgt)]);
+          tt = (float)om_ddiv(dist * 60.0, 25.0);                        // speed is hard-coded (feature_processing.py:43)
+          tc = (float)om_ddiv((double)pair_cnt, tn);
+          double extra;
+          if (kind == OM_ORDER_HAUL) {
+            int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
+            extra = om_ddiv((double)on_cnt, (double)(ue - ub)) * __ldg(&c.dcycle[ub - c.S]);
+          } else {
+            extra = om_ddiv(capsum, __ldg(&c.site_prod[q]));
           }
+          sw = (float)log((site_est(site) + extra) + 1.0);
         }
-        double dist = __ldg(&c.rdist[road_id(cur, tgt)]);
-        tt = (float)om_ddiv(dist * 60.0, 25.0);                        // speed is hard-coded (feature_processing.py:43)
-        tc = (float)om_ddiv((double)pair_cnt, tn);
-        double extra;
-        if (kind == OM_ORDER_HAUL) {
-          int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
-          extra = om_ddiv((double)on_cnt, (double)(ue - ub)) * __ldg(&c.dcycle[ub - c.S]);
-        } else {
-          extra = om_ddiv(capsum, __ldg(&c.site_prod[q]));
-        }
-        sw = (float)log((site_est(site) + extra) + 1.0);
+        ob[o3 + q] = tt; ob[o4 + q] = tc; ob[o7 + q] = sw;
       }
-      ob[o3 + q] = tt; ob[o4 + q] = tc; ob[o7 + q] = sw;
     }
-    // all roads: distance and active-jam count
+    // all roads: distance and active-jam count (lanes over the jam pool, shared-memory counters per road)
+    {
+      uint32_t* rj = (uint32_t*)(sm + ly.scratch) + ((c.U + 1) & ~1) * 2;   // behind the unit_est_all() results
 #pragma unroll 1
-    for (int r = lane; r < R; r += 32) {
-      int cnt = 0;
+      for (int r = lane; r < R; r += 32) rj[r] = 0u;
+      __syncwarp();
 #pragma unroll 1
-      for (uint32_t j = 0; j < jam_count; ++j)
-        cnt += (U16A(j_road, j) == r && F64(j_start, j) <= now && F64(j_end, j) >= now) ? 1 : 0;
-      ob[o5 + r] = (float)__ldg(&c.rdist[r]);
-      ob[o6 + r] = (float)cnt;
+      for (uint32_t j = lane; j < jam_count; j += 32)
+        if (F64(j_start, j) <= now && F64(j_end, j) >= now) atomicAdd(&rj[U16A(j_road, j)], 1u);
+      __syncwarp();
+#pragma unroll 1
+      for (int r = lane; r < R; r += 32) {
+        ob[o5 + r] = (float)__ldg(&c.rdist[r]);
+        ob[o6 + r] = (float)rj[r];
+      }
     }
     // per-site blocks
 #pragma unroll 1

@@ -12,7 +12,47 @@
 #include "om_engine.cuh"
 
 #define OM_MAX_WARPS_PER_CTA 20
-#define OM_SMEM_LIMIT (227 * 1024)
+#define OM_SMEM_LIMIT (227 * 1024 - 256)   /* minus the static shared memory (mbarriers) */
+
+// ------------------------------------------------------------------------------------------------
+// TMA staging of one instance's state blob (1-D bulk copies): HBM -> shared memory completing on an mbarrier
+// transaction count, shared memory -> HBM as a bulk group.  One elected lane issues, the whole warp waits.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t om_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void om_mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(om_smem_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// called by every lane; `phase` is the parity of the barrier phase this load completes
+__device__ __forceinline__ void om_stage_in(unsigned char* sm, const unsigned char* g, uint32_t bytes, uint64_t* bar,
+                                            uint32_t phase, int lane) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses to this buffer are done
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(om_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(om_smem_u32(sm)), "l"(g), "r"(bytes), "r"(om_smem_u32(bar)) : "memory");
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(om_smem_u32(bar)), "r"(phase) : "memory");
+  }
+}
+
+// called by every lane after the last shared-memory write of the instance; returns when the buffer may be reused
+__device__ __forceinline__ void om_stage_out(unsigned char* g, const unsigned char* sm, uint32_t bytes, int lane) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(om_smem_u32(sm)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  __syncwarp();
+}
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -30,21 +70,19 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t staged = SPLIT ? p.ly.hot_bytes : p.ly.total_bytes;   // SPLIT: truck records / jam pool stay in HBM
   unsigned char* sm = om_smem + (size_t)warp * staged;
-  const uint32_t n16 = staged >> 4;
+  __shared__ __align__(8) uint64_t om_mbar[OM_MAX_WARPS_PER_CTA];
+  uint32_t phase = 0;
+  if (lane == 0) om_mbar_init(&om_mbar[warp]);
+  __syncwarp();
   while (true) {
     unsigned long long inst = 0;
     if (lane == 0) inst = atomicAdd(p.counter, 1ull);
     inst = __shfl_sync(OM_FULL, inst, 0);
     if (inst >= (unsigned long long)p.n_instances) break;
-    // stage the instance's SoA blob HBM -> shared memory (coalesced 16-byte vectors)
+    // stage the instance's blob HBM -> shared memory
     unsigned char* g = p.state + (size_t)inst * p.ly.total_bytes;
-    {
-      const uint4* src = (const uint4*)g;
-      uint4* dst = (uint4*)sm;
-#pragma unroll 2
-      for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
-    }
-    __syncwarp();
+    om_stage_in(sm, g, staged, &om_mbar[warp], phase, lane);   // one TMA bulk copy
+    phase ^= 1u;
     Sim<RNG, TRACE, false, SPLIT> s(sm, g, p, lane, (long long)inst);
     s.load_hdr(p);
     s.run(p.until);
@@ -60,14 +98,7 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
         p.out.summary[inst] = r;
       }
     }
-    __syncwarp();
-    {
-      uint4* dst = (uint4*)g;
-      const uint4* src = (const uint4*)sm;
-#pragma unroll 2
-      for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
-    }
-    __syncwarp();
+    om_stage_out(g, sm, staged, lane);
   }
 }
 
@@ -79,32 +110,23 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_step_kernel(c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t staged = SPLIT ? p.ly.hot_bytes : p.ly.total_bytes;
   unsigned char* sm = om_smem + (size_t)warp * staged;
-  const uint32_t n16 = staged >> 4;
+  __shared__ __align__(8) uint64_t om_mbar[OM_MAX_WARPS_PER_CTA];
+  uint32_t phase = 0;
+  if (lane == 0) om_mbar_init(&om_mbar[warp]);
+  __syncwarp();
   while (true) {
     unsigned long long inst = 0;
     if (lane == 0) inst = atomicAdd(p.counter, 1ull);
     inst = __shfl_sync(OM_FULL, inst, 0);
     if (inst >= (unsigned long long)p.n_instances) break;
     unsigned char* g = p.state + (size_t)inst * p.ly.total_bytes;
-    {
-      const uint4* src = (const uint4*)g;
-      uint4* dst = (uint4*)sm;
-#pragma unroll 2
-      for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
-    }
-    __syncwarp();
+    om_stage_in(sm, g, staged, &om_mbar[warp], phase, lane);   // one TMA bulk copy
+    phase ^= 1u;
     Sim<RNG, false, true, SPLIT> s(sm, g, p, lane, (long long)inst);
     s.load_hdr(p);
     s.rl_step(p);
     s.store_hdr(p);
-    __syncwarp();
-    {
-      uint4* dst = (uint4*)g;
-      const uint4* src = (const uint4*)sm;
-#pragma unroll 2
-      for (uint32_t o = lane; o < n16; o += 32) dst[o] = src[o];
-    }
-    __syncwarp();
+    om_stage_out(g, sm, staged, lane);
   }
 }
 
@@ -198,7 +220,8 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly) {
   ly.u_lastbrk = take(off, 8, c.S);
   ly.r_repair_end = take(off, 8, R);
   ly.s_tons = take(off, 8, NS); ly.s_cap = take(off, 8, NS); ly.s_ability = take(off, 8, NS);
-  size_t nscr = ((U + 1) & ~(size_t)1) + (R + 1) / 2;   // unit_est_all() results [U] + per-road counters [R] (u32)
+  size_t nscr = U;                                      // unit_est_all() results [U] or per-road counters [R] (u32)
+  if (nscr < (R + 1) / 2) nscr = (R + 1) / 2;
   if (nscr < 32) nscr = 32;
   ly.scratch = take(off, 8, nscr);
   ly.u_rel_key = take(off, 4, U);

@@ -1388,6 +1388,23 @@ struct Sim {
               o8 = o7 + C, o9 = o8 + NS, o10 = o9 + NS, o11 = o10 + NS, o12 = o11 + NS;
     const int cur = U8A(t_cur, i);
     const double tn = (double)T + 1e-8;
+    // all roads: distance and active-jam count (lanes over the jam pool, shared-memory counters per road)
+    {
+      uint32_t* rj = (uint32_t*)(sm + ly.scratch);   // scratch is reused by unit_est_all() right after
+#pragma unroll 1
+      for (int r = lane; r < R; r += 32) rj[r] = 0u;
+      __syncwarp();
+#pragma unroll 1
+      for (uint32_t j = lane; j < jam_count; j += 32)
+        if (F64(j_start, j) <= now && F64(j_end, j) >= now) atomicAdd(&rj[U16A(j_road, j)], 1u);
+      __syncwarp();
+#pragma unroll 1
+      for (int r = lane; r < R; r += 32) {
+        ob[o5 + r] = (float)__ldg(&c.rdist[r]);
+        ob[o6 + r] = (float)rj[r];
+      }
+      __syncwarp();
+    }
     unit_est_all(true);                             // dispatcher.update_mine (dispatcher.py:24-33)
     unit_est_all(false);
     if (lane == 0) {
@@ -1426,22 +1443,6 @@ struct Sim {
           sw = (float)log((site_est(site) + extra) + 1.0);
         }
         ob[o3 + q] = tt; ob[o4 + q] = tc; ob[o7 + q] = sw;
-      }
-    }
-    // all roads: distance and active-jam count (lanes over the jam pool, shared-memory counters per road)
-    {
-      uint32_t* rj = (uint32_t*)(sm + ly.scratch) + ((c.U + 1) & ~1) * 2;   // behind the unit_est_all() results
-#pragma unroll 1
-      for (int r = lane; r < R; r += 32) rj[r] = 0u;
-      __syncwarp();
-#pragma unroll 1
-      for (uint32_t j = lane; j < jam_count; j += 32)
-        if (F64(j_start, j) <= now && F64(j_end, j) >= now) atomicAdd(&rj[U16A(j_road, j)], 1u);
-      __syncwarp();
-#pragma unroll 1
-      for (int r = lane; r < R; r += 32) {
-        ob[o5 + r] = (float)__ldg(&c.rdist[r]);
-        ob[o6 + r] = (float)rj[r];
       }
     }
     // per-site blocks

@@ -30,6 +30,28 @@ METRIC = "simulated truck-events/sec (north_pit_mine)"   # c5 runs the synthetic
 UNIT = "truck-events/s"
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout: NCCL / torch may print banners (e.g. "NCCL version ...") on fd 1,
+    so fd 1 is pointed at stderr for the whole run and the line is written to the saved descriptor at the end."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def load_cfg(name="north_pit_mine"):
     with open(os.path.join(ROOT, "tests", "golden", "configs", name + ".json"), encoding="utf-8") as fh:
         return json.load(fh)
@@ -167,7 +189,7 @@ def run_reference_arm(a):
             "episodes_per_s": sum(eps) / len(eps),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit_line(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -284,7 +306,7 @@ def run_c4(a):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                          "note": "kernel_ms measured mid-episode with a constant action (100 launches)"}}
     if rank == 0:
-        print(json.dumps(line))
+        emit_line(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -302,6 +324,7 @@ def main():
     ap.add_argument("--instances", type=int, default=0, help="instances per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
+    _quiet_stdout()
     if a.impl == "reference":
         return run_reference_arm(a)
     if a.workload == "c4":
@@ -452,6 +475,22 @@ def main():
                         "~0 by construction; the limiter is warp-instruction issue / dependent-chain latency "
                         "(see profiles/ for smsp__inst_executed and issue-active from ncu)"}
 
+    # ncu-derived counters of the same kernel/workload (profiles/kernel_counters.json): DRAM traffic per launch and the
+    # warp-instruction issue rate, which is what actually bounds this kernel
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_counters.json")) as fh:
+            kc = json.load(fh).get(a.workload)
+    except Exception:
+        kc = None
+    if kc:
+        scale = n / float(kc["instances"])
+        roofline["traffic"] = (kc["dram__bytes_read.sum"] + kc["dram__bytes_write.sum"]) * scale
+        sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        inst = kc["smsp__inst_executed.sum"] * scale
+        peak_issue = 148 * 4 * sm_mhz * 1e6
+        roofline["issue"] = {"warp_inst_per_launch": inst, "achieved_inst_per_s": inst / (kern_ms / 1000.0),
+                             "peak_inst_per_s": peak_issue, "frac": inst / (kern_ms / 1000.0) / peak_issue,
+                             "source": kc["source"] + " (instruction count from the committed ncu capture, kernel time live)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -473,7 +512,7 @@ def main():
                                     "episodes_per_s": s["episodes_per_s"],
                                     "sample": "%d episodes of the same workload (%.1f s wall) on %d host processes, "
                                               "oracle/des_oracle.py" % (s["episodes"], s["wall_s"], s["cores"])}
-        print(json.dumps(line))
+        emit_line(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -13,4 +13,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:om_run_kernel -s 1 -c 1 -o gpurun_out/${TAG}_prof -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:om_step_kernel -s 200 -c 1 -o gpurun_out/${TAG}_step_prof -f \
+    python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_step.log 2>&1; echo "ncu step rc=$?"
 cat gpurun_out/${TAG}_bench_c3.json

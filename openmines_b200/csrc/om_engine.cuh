@@ -112,6 +112,7 @@ struct InstHdr {
   uint32_t rl_steps;
 };
 static_assert(sizeof(InstHdr) == 184, "InstHdr size");
+static_assert(sizeof(OmTickRecord) == 32 && sizeof(OmUnitTick) == 16 && sizeof(OmSummary) == 64, "output record sizes");
 #define OM_HDR_BYTES 192
 
 struct RunParams {
@@ -856,13 +857,14 @@ struct Sim {
     }
     if (out.ticks != nullptr && k < out.tick_capacity) {
       if (lane == 0) {
-        OmTickRecord r;
-        r.produced_tons = produce; r.service_count = svc_total;
-        r.working = (uint16_t)n_work; r.waiting = (uint16_t)n_wait; r.load_unload = (uint16_t)n_lu;
-        r.moving = (uint16_t)n_mov; r.repairing = (uint16_t)n_rep;
-        r.n_jams = (uint16_t)n_jams; r.n_road_repairs = (uint16_t)n_road_rep;
-        r.n_truck_repairs = (uint16_t)n_brk; r.n_unrepairable = (uint16_t)n_unrep; r.pad = 0;
-        out.ticks[inst * (long long)out.tick_capacity + k] = r;
+        // OmTickRecord (32 B) packed in registers and written as two 16-byte stores
+        uint4 a, b;
+        a.x = (uint32_t)__double2loint(produce); a.y = (uint32_t)__double2hiint(produce);
+        a.z = (uint32_t)svc_total; a.w = (n_work & 0xFFFFu) | (n_wait << 16);
+        b.x = (n_lu & 0xFFFFu) | (n_mov << 16); b.y = (n_rep & 0xFFFFu) | (n_jams << 16);
+        b.z = (n_road_rep & 0xFFFFu) | (n_brk << 16); b.w = n_unrep & 0xFFFFu;
+        uint4* dst = (uint4*)(out.ticks + inst * (long long)out.tick_capacity + k);
+        dst[0] = a; dst[1] = b;
       }
       if (lane < NS) {
         long long o = (inst * (long long)out.tick_capacity + k) * NS + lane;

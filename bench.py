@@ -222,14 +222,21 @@ def run_c4(a):
     head = torch.nn.Linear(d, env.n_actions); torch.nn.init.orthogonal_(head.weight, 0.01); torch.nn.init.zeros_(head.bias)
     policy = torch.nn.Sequential(*layers, head).to(dev)
 
+    # one rollout iteration (policy forward + Categorical sample + om_step) captured in a CUDA graph
+    replay = env.capture_rollout_step(policy) if not a.no_graph else None
+
     def episode(host_sync_every):
         obs, info = env.reset(seed=rank * n)
         steps = 0
         with torch.no_grad():
             while True:
-                logits = policy(obs)
-                act = torch.distributions.Categorical(logits=logits).sample()
-                obs, rew, term, trunc, info = env.step(act)
+                if replay is not None:
+                    replay()
+                    term = env.io["done"]
+                else:
+                    logits = policy(obs)
+                    act = torch.distributions.Categorical(logits=logits).sample()
+                    obs, rew, term, trunc, info = env.step(act)
                 steps += 1
                 if steps % host_sync_every == 0 and bool(term.all()):
                     break
@@ -288,7 +295,8 @@ def run_c4(a):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "BASELINE configs[3]: batched RL env step, %d parallel north_pit_mine envs/GPU, random-init "
                                    "policy (194-256-256-256-5 MLP, Categorical sample) feeding every order; one bench step = one "
-                                   "full batched episode (reset + policy/om_step until all envs are done)" % n,
+                                   "full batched episode (reset + policy/om_step until all envs are done); rollout iteration %s" %
+                                   (n, "launched eagerly" if a.no_graph else "replayed from a CUDA graph"),
                        "sim_time": 240, "instances_per_gpu": n, "state_bytes_per_instance": env.mine.state_bytes,
                        "l2_policy": "inputs larger than L2 (state %.0f MB/GPU round-trips HBM every env step)" % (n * env.mine.state_bytes / 1e6),
                        "launch": env.mine.launch_info()},
@@ -323,6 +331,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"])
     ap.add_argument("--instances", type=int, default=0, help="instances per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="c4: launch the rollout iteration eagerly instead of replaying a CUDA graph")
     a = ap.parse_args()
     _quiet_stdout()
     if a.impl == "reference":

@@ -168,6 +168,7 @@ struct OmEngine {
   const int64_t* tape_offsets = nullptr;
   int grid = 0, block = 0, smem = 0, warps = 0;
   bool split = false;   // cold part of the blob accessed in place in HBM
+  bool reset_done = false;   // om_reset has been enqueued at least once (om_run / om_step on a never-written blob could spin)
   std::string err;
 };
 
@@ -394,6 +395,7 @@ int om_reset(OmHandle h, const uint64_t* seeds, const int32_t* dispatcher, int r
     return set_err(h, OM_E_INVALID, "om_reset: OM_RNG_TAPE needs tape_values/tape_sites/tape_offsets");
   CK(cudaSetDevice(h->device));
   h->rng_mode = rng_mode;
+  h->reset_done = true;
   h->tape_values = tape_values; h->tape_sites = tape_sites; h->tape_offsets = tape_offsets;
   const int wpb = 8;
   long long blocks = (h->n + wpb - 1) / wpb;
@@ -405,6 +407,7 @@ int om_reset(OmHandle h, const uint64_t* seeds, const int32_t* dispatcher, int r
 
 int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* stream) {
   if (!h || !state) return set_err(h, OM_E_INVALID, "om_run: null argument");
+  if (!h->reset_done) return set_err(h, OM_E_INVALID, "om_run: om_reset has not been called on this handle (the state blobs are uninitialised)");
   CK(cudaSetDevice(h->device));
   RunParams p;
   memset(&p, 0, sizeof(p));
@@ -447,6 +450,7 @@ int om_obs_dim(OmHandle h, int32_t* dim) {
 
 int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* stream) {
   if (!h || !state || !io || !io->obs) return set_err(h, OM_E_INVALID, "om_step: null argument");
+  if (!h->reset_done) return set_err(h, OM_E_INVALID, "om_step: om_reset has not been called on this handle (the state blobs are uninitialised)");
   CK(cudaSetDevice(h->device));
   RunParams p;
   memset(&p, 0, sizeof(p));

@@ -109,7 +109,7 @@ class BatchedMine:
         self.state_bytes = int(sb.value)
         self.layout = OmStateLayoutStruct()
         self._ck(self.lib.om_state_layout(self.h, ctypes.byref(self.layout)))
-        self.state = torch.empty((self.n, self.state_bytes), dtype=torch.uint8, device=self.device)
+        self.state = torch.zeros((self.n, self.state_bytes), dtype=torch.uint8, device=self.device)
         self.dispatcher_ids = None
         self.seeds = None
         self._tape = None

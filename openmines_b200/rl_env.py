@@ -76,5 +76,38 @@ class BatchedMineEnv:
             return self.io["obs"], rew, terminated, truncated, dict(info, final_observation=obs_final)
         return self.io["obs"], self.io["reward"], terminated, truncated, self._info()
 
+    def capture_rollout_step(self, policy, sample=None, warmup=3):
+        """Capture ONE rollout iteration -- policy forward on the current observation, action sampling, ``om_step``
+        -- into a CUDA graph and return ``replay()``.  The iteration is launch-bound (a small MLP, a sampler and one
+        engine kernel per env step), so replaying a graph removes most of the host time between env steps.  The
+        env's ``io`` tensors are the graph's static buffers: after ``replay()`` read ``env.io["obs"]``,
+        ``env.io["reward"]``, ``env.io["done"]`` (``env.last_actions`` holds the sampled actions).  Capturing
+        advances the envs by ``warmup + 1`` steps: call ``reset()`` afterwards."""
+        torch = self.torch
+        if self._seeds is None:
+            self.reset()          # the warm-up / capture steps need initialised envs
+        if sample is None:
+            def sample(logits):
+                # validate_args=False: argument validation synchronises with the host, which is illegal during capture
+                return torch.distributions.Categorical(logits=logits, validate_args=False).sample()
+        self.last_actions = torch.zeros(self.num_envs, dtype=torch.int32, device=self.mine.device)
+
+        def body():
+            act = sample(policy(self.io["obs"]))
+            self.last_actions.copy_(act)
+            self.mine.step(self.last_actions, self.io, teacher=self.teacher)
+
+        side = torch.cuda.Stream(device=self.mine.device)
+        side.wait_stream(torch.cuda.current_stream(self.mine.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream(self.mine.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph):
+            body()
+        self._graph = graph
+        return graph.replay
+
     def close(self):
         self.mine.close()

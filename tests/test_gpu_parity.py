@@ -209,3 +209,15 @@ def test_scaled_mine_c5_vs_oracle():
     res = mine.run(trace_capacity=32768, site_ticks=True, order_capacity=8192)
     diffs = engine_vs_ref(live, mine, res, 0)
     assert not diffs, diffs[:5]
+
+
+def test_run_before_reset_is_an_error_not_a_hang(north_pit):
+    """om_run / om_step before om_reset must fail on the host (a never-written blob could make the kernel spin)."""
+    import torch
+    from openmines_b200.rl_env import BatchedMineEnv
+    mine = _mine(north_pit, 8)
+    with pytest.raises(RuntimeError, match="om_reset has not been called"):
+        mine.run()
+    env = BatchedMineEnv(north_pit, 4)
+    with pytest.raises(RuntimeError, match="om_reset has not been called"):
+        env.step(torch.zeros(4, dtype=torch.int32, device=env.mine.device))

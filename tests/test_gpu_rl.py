@@ -133,3 +133,29 @@ def test_shortest_trip_as_builtin_dispatcher(north_pit):
     res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=2048)
     diffs = engine_vs_ref(ref, mine, res, 0)
     assert not diffs, diffs[:5]
+
+
+def test_graphed_rollout_matches_eager(north_pit):
+    """The CUDA-graph replay of one rollout iteration (policy + om_step) gives the same trajectories as eager stepping."""
+    import torch
+    from openmines_b200.rl_env import BatchedMineEnv
+    n = 64
+    lin = torch.nn.Linear(194, 5).cuda()
+    policy = lambda o: lin(o)
+    argmax = lambda logits: logits.argmax(dim=1)
+    outs = []
+    for graphed in (False, True):
+        env = BatchedMineEnv(north_pit, n, rng_mode="philox")
+        replay = env.capture_rollout_step(policy, sample=argmax) if graphed else None
+        obs, info = env.reset(seed=5)
+        rewards = []
+        with torch.no_grad():
+            for _ in range(40):
+                if graphed:
+                    replay()
+                else:
+                    env.step(argmax(policy(obs)))
+                rewards.append(env.io["reward"].clone())
+        outs.append((torch.stack(rewards).cpu(), env.io["obs"].clone().cpu(), env.io["info"].clone().cpu()))
+        env.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])

@@ -8,5 +8,6 @@ from .config import pack_config, load_config, PackedConfig          # noqa: F401
 from .dispatcher import (BaseDispatcher, NaiveDispatcher, RandomDispatcher, NearestDispatcher,   # noqa: F401
                          FixedGroupDispatcher, SPTFDispatcher, SQDispatcher, ShortestTripDispatcher, by_name)
 from .engine import BatchedMine, RunResult, DISPATCHER_IDS          # noqa: F401
+from .external import run_external, build_mine_view                 # noqa: F401
 
 __version__ = "0.1.0"

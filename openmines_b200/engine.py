@@ -45,6 +45,19 @@ _ENTRY_FIELDS = {"t_time", "t_key", "t_phase"}                # the truck's 16-b
 _SOA_FIELDS = {"u_rel_time", "u_rel_key", "u_lastbrk"}         # every other t_* / u_* field lives in a record
 
 
+# numpy mirror of the device-side InstHdr (csrc/om_engine.cuh): the first 192 bytes of every state blob
+HDR_DTYPE = np.dtype([("now", "<f8"), ("tick_time", "<f8"), ("reported_tons", "<f8"), ("seed", "<u8"), ("tape_pos", "<u8"),
+                      ("seq", "<u4"), ("tick_key", "<u4"), ("tick_k", "<i4"), ("dispatcher", "<i4"),
+                      ("n_events", "<u4"), ("n_decisions", "<u4"), ("n_orders", "<u4"), ("n_hops", "<u4"),
+                      ("n_jams", "<u4"), ("n_road_rep", "<u4"), ("n_brk", "<u4"), ("n_unrep", "<u4"),
+                      ("jam_count", "<u4"), ("err", "<u4"), ("trace_count", "<u4"), ("order_count", "<u4"),
+                      ("pending_truck", "<i4"), ("pending_kind", "<i4"), ("n_ticks", "<u4"), ("n_rel", "<u4"),
+                      ("rl_last_time", "<f8"), ("rl_last_prod", "<f8"), ("acc_wait", "<f8"), ("acc_shovel", "<f8"),
+                      ("acc_dumper", "<f8"), ("acc_move", "<f8"), ("acc_jam", "<f8"), ("finished", "<u4"),
+                      ("rl_steps", "<u4"), ("pad", "V8")])
+assert HDR_DTYPE.itemsize == 192
+
+
 class OmStateLayoutStruct(ctypes.Structure):
     _fields_ = [(f, ctypes.c_uint32) for f in _LAYOUT_FIELDS]
 
@@ -240,9 +253,16 @@ class BatchedMine:
         return out
 
     # ------------------------------------------------------------------------------------------
-    def state_arrays(self, inst):
-        """Decode one instance's state blob into named numpy arrays (used by the parity tests)."""
-        blob = self.state[inst].cpu().numpy()
+    def headers(self):
+        """Per-instance header records (HDR_DTYPE): clock, counters, error code, pending decision."""
+        raw = self.state[:, :HDR_DTYPE.itemsize].contiguous().cpu().numpy()
+        return raw.view(HDR_DTYPE).reshape(self.n).copy()
+
+    def state_arrays(self, inst, blob=None):
+        """Decode one instance's state blob into named numpy arrays (parity tests, tick recorder, dispatcher views).
+        ``blob``: the instance's bytes if the caller already copied the state to the host."""
+        if blob is None:
+            blob = self.state[inst].cpu().numpy()
         ly, pc = self.layout, self.pc
         T, U, S = pc.T, pc.S + pc.M, pc.S
 
@@ -274,4 +294,7 @@ class BatchedMine:
             out[f] = arr(f, np.uint16, U)
         out["u_repair"] = arr("u_repair", np.uint8, S)
         out["r_repair_end"] = arr("r_repair_end", np.float64, pc.R)
+        for f in ("s_qtotal", "s_coming"):
+            out[f] = arr(f, np.uint16, pc.L + pc.D)
+        out["hdr"] = np.frombuffer(raw, dtype=HDR_DTYPE, count=1, offset=ly.hdr)[0]
         return out

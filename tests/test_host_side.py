@@ -97,3 +97,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_external_runner_needs_a_gpu(north_pit):
+    """run_external goes through the same C ABI: without a CUDA device it fails loudly (no host-side simulation)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import openmines_b200 as om
+
+    class D(om.BaseDispatcher):
+        def give_init_order(self, truck, mine):
+            return 0
+    with pytest.raises(RuntimeError):
+        om.run_external(D, north_pit, n_instances=1)

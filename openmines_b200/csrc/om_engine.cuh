@@ -50,6 +50,11 @@ enum : uint8_t {
   PH_DUMP_RET,        //    Process(unload) -> run resumes truck.py:431-453
   PH_AWAIT_ORDER      //    paused for an external decision (OM_DISP_EXTERNAL)
 };
+// An exception inside Truck.run (IndexError at truck.py:305,390,442, KeyError at sq_dispatcher.py:31) does not stop SimPy
+// at once: Process._resume schedules the failed Process event NORMAL at `now`, and env.step() re-raises when that event
+// pops -- entries of the same timestamp scheduled earlier still run.  The truck's entry becomes (now, NORMAL | seq) with
+// phase PH_CRASH_BASE + OM_IERR_* and the instance stops when it pops.
+#define PH_CRASH_BASE 32u
 
 // trace kinds (include/openmines_b200.h OmTraceRecord; same codes as oracle/trace_format.py)
 enum : uint8_t {
@@ -613,7 +618,7 @@ struct Sim {
       case OM_DISP_SQ: {
         // coming trucks + minute-sampled total queue length (sq_dispatcher.py:18-100)
         int k = (int)now;   // int(env.now)
-        if (k != tick_k) { fail(OM_IERR_SQ_KEYERROR); return -1; }
+        if (k != tick_k) return -OM_IERR_SQ_KEYERROR;   // KeyError: queue_status['total'][int(now)] not sampled yet
         int n = (kind == OM_ORDER_HAUL) ? D : L;
         int base = (kind == OM_ORDER_HAUL) ? L : 0;
         uint32_t v = 0xFFFFFFFFu;
@@ -667,8 +672,7 @@ struct Sim {
         break;
       }
       default:
-        fail(OM_IERR_BAD_ORDER);
-        return -1;
+        return -OM_IERR_BAD_ORDER;
     }
     return r;
   }
@@ -1071,9 +1075,11 @@ struct Sim {
     pend_truck = i; pend_kind = kind;
     if (rel_u >= 0) file_release(rel_u, rel_key);
   }
-  __device__ __forceinline__ void bad_order(int kind, int site, int rel_u, uint32_t rel_key) {
+  // `site` < 0: the dispatcher itself raised (-OM_IERR_*); otherwise truck.py indexes the site list out of range
+  __device__ __forceinline__ void bad_order(int i, int kind, int site, int rel_u, uint32_t rel_key) {
     if (site >= 0) count_order(kind, site);   // the wrapper logs the order before truck.py indexes the site list
-    fail(OM_IERR_BAD_ORDER);
+    uint32_t code = (site < 0) ? (uint32_t)(-site) : (uint32_t)OM_IERR_BAD_ORDER;
+    sched_truck(i, now, OM_KEY_NORMAL, (uint8_t)(PH_CRASH_BASE + code));   // the failed Process event
     if (rel_u >= 0) file_release(rel_u, rel_key);
   }
 
@@ -1132,6 +1138,7 @@ struct Sim {
       int rel_u = -1;                        // Release created in this chain, not yet popped (kept in registers)
       uint32_t rel_key = 0;
       int kind = 0, u = 0;
+      uint32_t ph0 = 0;
       bool dead = false, dump = false;
       if (id >= T) {
         // Release event popped: Resource._trigger_put hands the unit to the queue head
@@ -1146,7 +1153,8 @@ struct Sim {
         seq++;
         goto L_GRANTED;
       }
-      switch (U32A(t_phase, i)) {
+      ph0 = U32A(t_phase, i);
+      switch (ph0) {
         case PH_MOVE_ARRIVE: goto L_ARRIVE;
         case PH_LOAD_DONE: case PH_DUMP_DONE: goto L_SVC_DONE;
         case PH_MOVE_RET: goto L_MOVE_RET;
@@ -1169,6 +1177,7 @@ struct Sim {
           F64(u_lastbrk, u) = now;
           goto L_RELEASE;
         default:
+          if (ph0 >= PH_CRASH_BASE) fail(ph0 - PH_CRASH_BASE);           // the failed Process event pops: env.step() raises
           continue;
       }
 
@@ -1281,7 +1290,7 @@ struct Sim {
       if (__builtin_expect(disp == OM_DISP_EXTERNAL, 0)) { pause_for_order(i, kind, rel_u, rel_key, pend_truck, pend_kind); break; }
       int site = decide(kind, i);
       int nmax = (kind == OM_ORDER_HAUL) ? D : L;
-      if (__builtin_expect(site < 0 || site >= nmax, 0)) { bad_order(kind, site, rel_u, rel_key); continue; }
+      if (__builtin_expect(site < 0 || site >= nmax, 0)) { bad_order(i, kind, site, rel_u, rel_key); continue; }
       apply_order(i, kind, site);
       seq++;                                                           // env.process(move): Initialize URGENT
       if (!inl) {
@@ -1480,7 +1489,7 @@ struct Sim {
       int nmax = (pk == OM_ORDER_HAUL) ? c.D : c.L;
       if (a < 0 || a >= nmax) {
         if (a >= 0) count_order(pk, a);
-        fail(OM_IERR_BAD_ORDER);
+        sched_truck(pt, now, OM_KEY_NORMAL, (uint8_t)(PH_CRASH_BASE + OM_IERR_BAD_ORDER));
       } else {
         apply_order(pt, pk, a);
         set_entry(pt, now, seq, PH_MOVE_BEGIN);   // Initialize(move), URGENT
@@ -1502,6 +1511,7 @@ struct Sim {
         uint32_t saved_err = err;
         disp = io.teacher;
         sug = decide(pk, pt);
+        if (sug < 0) sug = -1;                       // the teacher raised (e.g. SQ before its minute's sample)
         disp = saved_disp; err = saved_err;
       }
       rl_last = now;

@@ -29,3 +29,20 @@ def north_pit():
 @pytest.fixture(scope="session")
 def short_mine():
     return load_cfg("north_pit_mine_short")
+
+
+@pytest.fixture(scope="session")
+def ragged_mine():
+    """L=3 != D=2, 1/4/7 shovels and 1/9 dumpers per site, 130 trucks of four types (tests/golden/make_golden_edge.py)."""
+    return load_cfg("ragged_mine")
+
+
+@pytest.fixture(scope="session")
+def one_truck_mine():
+    return load_cfg("one_truck_mine")
+
+
+@pytest.fixture(scope="session")
+def integer_mine():
+    """Every duration a whole number of minutes: constant ties between truck events, Releases and the monitor block."""
+    return load_cfg("integer_mine")

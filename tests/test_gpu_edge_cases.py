@@ -1,0 +1,100 @@
+"""GPU parity on the edge-case mines whose goldens come from the unmodified reference
+(tests/golden/make_golden_edge.py), plus the engine's own error paths."""
+import numpy as np
+import pytest
+
+from helpers import DISPATCHERS, Golden, engine_vs_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _mine(cfg, n, **kw):
+    import openmines_b200 as om
+    return om.BatchedMine(cfg, n, **kw)
+
+
+def test_ragged_mine_det_vs_golden(ragged_mine):
+    """L = 3 != D = 2, 1 / 4 / 7 shovels and 1 / 9 dumpers per site, 130 trucks (5 scan slots, ragged last one), four
+    truck types incl. a fractional capacity.  RandomDispatcher hits the reference's IndexError (haul orders are drawn
+    over len(load_sites)): the engine must stop at the same record with OM_IERR_BAD_ORDER."""
+    mine = _mine(ragged_mine, len(DISPATCHERS))
+    mine.reset(DISPATCHERS, seeds=[0] * len(DISPATCHERS), rng_mode="det")
+    res = mine.run(trace_capacity=4096, site_ticks=True, order_capacity=2048)
+    summ = res.summary_np()
+    for i, d in enumerate(DISPATCHERS):
+        g = Golden("det_ragged_mine_%s_s0" % d)
+        diffs = engine_vs_ref(g, mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s: %s" % (d, diffs[:5])
+        assert int(summ[i]["err"]) == (2 if g.error else 0), (d, summ[i]["err"], g.error)
+
+
+def test_ragged_mine_tape_vs_golden(ragged_mine):
+    names = ["SQDispatcher", "SPTFDispatcher", "RandomDispatcher"]
+    goldens = [Golden("live_ragged_mine_%s_s5" % d) for d in names]
+    mine = _mine(ragged_mine, len(names))
+    mine.reset(names, rng_mode="tape", tapes=[g.tape for g in goldens])
+    res = mine.run(trace_capacity=4096, site_ticks=True, order_capacity=2048)
+    for i, d in enumerate(names):
+        diffs = engine_vs_ref(goldens[i], mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s: %s" % (d, diffs[:5])
+        assert int(res.summary_np()[i]["err"]) == (2 if goldens[i].error else 0)
+
+
+def test_one_truck_mine_vs_golden(one_truck_mine):
+    """The smallest legal mine: one truck, one shovel, one dumper (2 + 8 event records per cycle)."""
+    g = Golden("det_one_truck_mine_NaiveDispatcher_s0")
+    mine = _mine(one_truck_mine, 1)
+    mine.reset("NaiveDispatcher", rng_mode="det")
+    res = mine.run(trace_capacity=256, site_ticks=True, order_capacity=64)
+    assert not engine_vs_ref(g, mine, res, 0)
+    g = Golden("live_one_truck_mine_NaiveDispatcher_s2")
+    mine = _mine(one_truck_mine, 1)
+    mine.reset("NaiveDispatcher", rng_mode="tape", tapes=[g.tape])
+    res = mine.run(trace_capacity=256, site_ticks=True, order_capacity=64)
+    assert not engine_vs_ref(g, mine, res, 0)
+
+
+def test_ragged_mine_live_runs_clean(ragged_mine):
+    """Philox mode on the ragged mine: no engine errors for the dispatchers that are valid on it, plausible output."""
+    names = ["NaiveDispatcher", "NearestDispatcher", "FixedGroupDispatcher", "SPTFDispatcher", "SQDispatcher"]
+    n = 64
+    ids = np.repeat(np.arange(len(names)), n)
+    mine = _mine(ragged_mine, len(ids))
+    mine.reset([names[k] for k in ids], seeds=np.tile(np.arange(n), len(names)), rng_mode="philox")
+    s = mine.run().summary_np()
+    assert (s["err"] == 0).all()
+    tons = s["reported_tons"].reshape(len(names), n).mean(axis=1)
+    assert tons[0] < tons[1:].min()                    # Naive sends everything to one single-shovel site
+    assert (s["n_truck_events"] > 100).all()
+
+
+def test_engine_error_paths(north_pit):
+    """Truncated tape -> OM_IERR_TAPE; a trace buffer that is too small -> OM_IERR_TRACE_OVERFLOW with the simulation
+    itself unaffected; a jam pool that is too small -> OM_IERR_JAM_OVERFLOW (never silent corruption)."""
+    g = Golden("live_north_pit_mine_SQDispatcher_s11")
+    sites, values = g.tape
+    mine = _mine(north_pit, 2)
+    mine.reset(["SQDispatcher", "SQDispatcher"], rng_mode="tape", tapes=[(sites, values), (sites[:5000], values[:5000])])
+    res = mine.run(trace_capacity=64)
+    s = res.summary_np()
+    assert s["err"][0] == 5 and s["err"][1] == 4       # trace overflow only | tape exhausted
+    assert float(s["reported_tons"][0]) == g.reported_tons and int(s["n_truck_events"][0]) == g.n_truck_events
+    assert s["now"][1] < s["now"][0]
+    small = _mine(north_pit, 32, jam_capacity=2)
+    small.reset("SQDispatcher", seeds=np.arange(32), rng_mode="philox")
+    e = small.run().summary_np()["err"]
+    assert set(np.unique(e)).issubset({0, 3}) and (e == 3).any()
+
+
+def test_integer_mine_tie_stress_vs_golden(integer_mine):
+    """Whole-minute durations everywhere: truck hops, Release events and the monitor block tie at integer timestamps
+    all the time, so every pop exercises the (time, priority, seq) tie-break and no chain may be fused wrongly.
+    Also: an SQ order at an integer minute always finds that minute's queue sample (the process-return hop that precedes
+    it gets a fresh eid behind the monitors'), so OM_IERR_SQ_KEYERROR must not fire."""
+    mine = _mine(integer_mine, len(DISPATCHERS))
+    mine.reset(DISPATCHERS, seeds=[0] * len(DISPATCHERS), rng_mode="det")
+    res = mine.run(trace_capacity=2048, site_ticks=True, order_capacity=1024)
+    for i, d in enumerate(DISPATCHERS):
+        diffs = engine_vs_ref(Golden("det_integer_mine_%s_s0" % d), mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s: %s" % (d, diffs[:5])
+    assert (res.summary_np()["err"] == 0).all()

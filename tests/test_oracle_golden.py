@@ -182,3 +182,41 @@ def test_rl_oracle_matches_reference_golden(name, north_pit):
     assert np.array_equal(np.array([x["sug_action"] for x in log]), z["sug_action"])
     assert np.array_equal(np.array([x["action"] for x in log]), z["action"])
     assert np.array_equal(np.array([x["done"] for x in log]), z["done"])
+
+
+# ---- edge-case mines (tests/golden/make_golden_edge.py: goldens from the unmodified reference) -------------------------
+@pytest.mark.parametrize("d", DISPATCHERS)
+def test_oracle_ragged_mine_det(d, ragged_mine):
+    """L != D, 1..9 units per site, 130 trucks of four types.  RandomDispatcher draws haul orders over len(load_sites)
+    (random_dispatcher.py:21-22), so with L = 3 > D = 2 the reference dies with IndexError -- the oracle must stop at the
+    same record."""
+    g = Golden("det_ragged_mine_%s_s0" % d)
+    o = do.run_oracle(ragged_mine, d, "det", seed=0)
+    assert not _same(g, o)
+    assert (g.error is None) == (o.error is None)
+    if d == "RandomDispatcher":
+        assert "IndexError" in g.error and "IndexError" in o.error
+
+
+@pytest.mark.parametrize("d", ["SQDispatcher", "SPTFDispatcher", "RandomDispatcher"])
+def test_oracle_ragged_mine_live(d, ragged_mine):
+    g = Golden("live_ragged_mine_%s_s5" % d)
+    o = do.run_oracle(ragged_mine, d, "live", seed=5)
+    assert not _same(g, o, check_tape=True)
+
+
+def test_oracle_one_truck_mine(one_truck_mine):
+    """Smallest legal mine: 2 + 8 records per cycle."""
+    g = Golden("det_one_truck_mine_NaiveDispatcher_s0")
+    o = do.run_oracle(one_truck_mine, "NaiveDispatcher", "det", seed=0)
+    assert not _same(g, o)
+    assert g.n_truck_events == 30 and (g.n_truck_events - 2) % 4 == 0
+    g = Golden("live_one_truck_mine_NaiveDispatcher_s2")
+    o = do.run_oracle(one_truck_mine, "NaiveDispatcher", "live", seed=2)
+    assert not _same(g, o, check_tape=True)
+
+
+@pytest.mark.parametrize("d", DISPATCHERS)
+def test_oracle_integer_mine_tie_stress(d, integer_mine):
+    """All durations are whole minutes, so truck hops, Releases and the per-minute monitors tie constantly."""
+    assert not _same(Golden("det_integer_mine_%s_s0" % d), do.run_oracle(integer_mine, d, "det", seed=0))

@@ -66,6 +66,9 @@ def workload(name, per_gpu, rank):
         gid = np.arange(rank * n, (rank + 1) * n, dtype=np.uint64)     # global instance ids
         disp = np.where(np.arange(n) % 2 == 0, 5, 4).astype(np.int32)  # SQ, SPTF interleaved
         seeds = gid // 2                                               # seed s runs once per dispatcher
+        if os.environ.get("OM_BENCH_SORTED"):                          # experiment: same set, grouped by dispatcher
+            order = np.argsort(disp, kind="stable")
+            disp, seeds = disp[order], seeds[order]
         desc = "BASELINE configs[2] per-GPU shard: north_pit_mine x %d seeds x {SQ,SPTF}, stochastic events on " \
                "(Philox4x32-10), %d instances/GPU, sim_time 240" % (half, n)
         return disp, seeds, "philox", desc

@@ -64,6 +64,22 @@ __global__ void om_reset_kernel(DevCfg c, OmStateLayout ly, unsigned char* state
   om_init_state(state + (size_t)inst * ly.total_bytes, c, ly, threadIdx.x & 31, seeds[inst], dispatcher[inst]);
 }
 
+// Work-queue order of om_run: instance ids grouped by dispatcher id (counting sort, one CTA).  The episode kernel is
+// instruction-fetch bound and each dispatcher has its own decision code, so SMs that run one dispatcher at a time keep
+// a smaller instruction working set: +13 % on the SQ/SPTF workload against the interleaved order.
+// Results are indexed by instance id, so the order is invisible outside the kernel.
+__global__ void om_order_kernel(const int32_t* dispatcher, long long n, int32_t* order) {
+  __shared__ unsigned int start[257];
+  for (int d = threadIdx.x; d < 257; d += blockDim.x) start[d] = 0u;
+  __syncthreads();
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&start[(dispatcher[i] & 0xFF) + 1], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int d = 1; d < 257; ++d) start[d] += start[d - 1];
+  __syncthreads();
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&start[dispatcher[i] & 0xFF], 1u)] = (int32_t)i;
+}
+
 template <int RNG, bool TRACE, bool SPLIT>
 __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(const __grid_constant__ RunParams p) {
   extern __shared__ __align__(16) unsigned char om_smem[];
@@ -76,7 +92,10 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
   __syncwarp();
   while (true) {
     unsigned long long inst = 0;
-    if (lane == 0) inst = atomicAdd(p.counter, 1ull);
+    if (lane == 0) {
+      inst = atomicAdd(p.counter, 1ull);
+      if (inst < (unsigned long long)p.n_instances && p.order != nullptr) inst = (unsigned long long)p.order[inst];
+    }
     inst = __shfl_sync(OM_FULL, inst, 0);
     if (inst >= (unsigned long long)p.n_instances) break;
     // stage the instance's blob HBM -> shared memory
@@ -162,6 +181,7 @@ struct OmEngine {
   OmStateLayout ly;
   std::vector<void*> dev_allocs;
   unsigned long long* counter = nullptr;
+  int32_t* order = nullptr;   // [n] instance ids grouped by dispatcher (written by om_reset)
   int rng_mode = OM_RNG_DET;
   const double* tape_values = nullptr;
   const uint8_t* tape_sites = nullptr;
@@ -249,7 +269,7 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
   OmEngine* h = nullptr;
   if (!cfg || !out) return set_err(h, OM_E_INVALID, "om_create: null argument");
   if (cfg->abi_version != OM_ABI_VERSION) return set_err(h, OM_E_INVALID, "om_create: ABI version mismatch");
-  if (n_instances <= 0) return set_err(h, OM_E_INVALID, "om_create: n_instances must be > 0");
+  if (n_instances <= 0 || n_instances > 0x7FFFFFFFLL) return set_err(h, OM_E_INVALID, "om_create: n_instances must be in 1..2^31-1");
   const int T = cfg->n_trucks, L = cfg->n_load_sites, D = cfg->n_dump_sites, S = cfg->n_shovels, M = cfg->n_dumpers;
   if (T <= 0 || L <= 0 || D <= 0 || S <= 0 || M <= 0 || cfg->n_truck_types <= 0)
     return set_err(h, OM_E_INVALID, "om_create: empty mine (mine.py:346-351 asserts)");
@@ -305,6 +325,12 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
     e = cudaMalloc(&d, sizeof(unsigned long long));
     if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, cudaGetErrorString(e));
     else { h->counter = (unsigned long long*)d; h->dev_allocs.push_back(d); }
+  }
+  if (rc == OM_OK) {
+    void* d = nullptr;
+    e = cudaMalloc(&d, sizeof(int32_t) * (size_t)n_instances);
+    if (e != cudaSuccess) rc = set_err(h, OM_E_NOMEM, cudaGetErrorString(e));
+    else { h->order = (int32_t*)d; h->dev_allocs.push_back(d); }
   }
   if (rc == OM_OK) {
     build_layout(c, h->ly);
@@ -402,6 +428,8 @@ int om_reset(OmHandle h, const uint64_t* seeds, const int32_t* dispatcher, int r
   om_reset_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(h->c, h->ly, (unsigned char*)state, seeds,
                                                                           dispatcher, h->n);
   CK(cudaGetLastError());
+  om_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dispatcher, h->n, h->order);
+  CK(cudaGetLastError());
   return OM_OK;
 }
 
@@ -417,6 +445,7 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
   p.state = (unsigned char*)state;
   p.tape_values = h->tape_values; p.tape_sites = h->tape_sites; p.tape_offsets = h->tape_offsets;
   p.counter = h->counter; p.n_instances = h->n; p.until = until;
+  p.order = h->order;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
   const bool trace = p.out.trace != nullptr || p.out.orders != nullptr;   // event-trace / order-log variant

@@ -129,6 +129,7 @@ struct RunParams {
   const uint8_t* tape_sites;
   const int64_t* tape_offsets;
   unsigned long long* counter; // dynamic instance scheduler
+  const int32_t* order;        // instance ids grouped by dispatcher (om_run): position in the work queue -> instance
   long long n_instances;
   double until;
   OmStepIO io;      // om_step only

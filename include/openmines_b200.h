@@ -25,7 +25,11 @@
 extern "C" {
 #endif
 
-#define OM_ABI_VERSION 2
+#define OM_ABI_VERSION 3
+
+/* OmConfig.flags */
+#define OM_CFG_RL_SURFACE 1 /* allocate the fields om_step needs (reward windows, minute-sampled site values): bigger
+                               state blobs, fewer resident instances per SM; om_step fails on a handle created without it */
 
 /* error codes */
 #define OM_OK 0
@@ -80,7 +84,7 @@ typedef struct OmConfig {
   int32_t jam_capacity;     /* max simultaneously tracked jam events per instance */
   int32_t sum_mode;         /* 1 = CPython>=3.12 Neumaier sum() (default), 0 = naive left-to-right */
   int32_t nearest_init;     /* nearest_dispatcher.py:24-26 */
-  int32_t reserved0;
+  int32_t flags;            /* OM_CFG_* */
   int32_t reserved1;
   const double* truck_capacity;   /* [T]  truck.py:56 */
   const double* truck_speed;      /* [T]  truck.py:57 */
@@ -178,15 +182,17 @@ typedef struct OmOutputs {
 typedef struct OmStateLayout {
   /* Byte offsets inside one instance's state blob.  Every field is the offset of ITS ELEMENT 0; element i lives at
    * offset + i * stride, where stride = e_stride for t_time / t_key / t_phase (the truck's pending entry), t_stride for
-   * the other t_* fields (per-truck record), u_stride for the u_* fields except u_rel_time / u_rel_key / u_lastbrk
-   * (per-unit record), and the element size otherwise.  t_phase is a uint32. */
+   * the other t_* fields except t_since (per-truck record), u_stride for the u_* fields except u_rel_key / u_lastbrk
+   * (per-unit record), and the element size otherwise.  t_phase is a uint32.  t_since, j_start, s_tons, s_cap and
+   * s_ability exist only with OM_CFG_RL_SURFACE (offset 0 otherwise); the header is hdr_bytes long (128 without the
+   * RL fields, 192 with them).  A pending Release has no stored time: it always equals the instance clock. */
   uint32_t total_bytes;
   uint32_t hdr;
   uint32_t t_time, t_load, t_jstart, t_prejam, t_lastbrk, t_repair, t_total, t_cycle, t_dist, t_since; /* f64 */
   uint32_t t_key, t_rng;                                                                     /* u32 */
   uint32_t t_svc, t_epoch, t_next, t_unit;                                                   /* u16 */
   uint32_t t_phase, t_status, t_cur, t_tgt;                                                  /* u8  */
-  uint32_t u_rel_time, u_last_start, u_last_done, u_tons, u_lastbrk;                         /* f64 */
+  uint32_t u_last_start, u_last_done, u_tons, u_lastbrk;                                     /* f64 */
   uint32_t u_rel_key, u_svc;                                                                 /* u32 */
   uint32_t u_user, u_head, u_tail, u_qlen;                                                   /* u16 */
   uint32_t u_repair;                                                                         /* u8  */
@@ -200,6 +206,7 @@ typedef struct OmStateLayout {
   uint32_t t_stride, u_stride; /* record sizes in bytes */
   uint32_t e_stride;           /* pending-entry size in bytes */
   uint32_t hot_bytes;          /* prefix of the blob the kernels stage in shared memory (== total_bytes unless split) */
+  uint32_t hdr_bytes;          /* bytes of the per-instance header present in the blob */
 } OmStateLayout;
 
 typedef struct OmEngine* OmHandle;

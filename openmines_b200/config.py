@@ -21,7 +21,8 @@ import math
 
 import numpy as np
 
-OM_ABI_VERSION = 2
+OM_ABI_VERSION = 3
+OM_CFG_RL_SURFACE = 1    # OmConfig.flags: allocate the fields om_step needs (bigger blobs, fewer resident instances)
 
 ROAD_EVENT_DEFAULTS = {            # road.py:37-43
     "lambda_repair": 1 / (60 * 2),
@@ -61,7 +62,7 @@ class OmConfigStruct(ctypes.Structure):
         ("abi_version", ctypes.c_int32), ("n_trucks", ctypes.c_int32), ("n_load_sites", ctypes.c_int32),
         ("n_dump_sites", ctypes.c_int32), ("n_shovels", ctypes.c_int32), ("n_dumpers", ctypes.c_int32),
         ("n_truck_types", ctypes.c_int32), ("jam_capacity", ctypes.c_int32), ("sum_mode", ctypes.c_int32),
-        ("nearest_init", ctypes.c_int32), ("reserved0", ctypes.c_int32), ("reserved1", ctypes.c_int32),
+        ("nearest_init", ctypes.c_int32), ("flags", ctypes.c_int32), ("reserved1", ctypes.c_int32),
         ("truck_capacity", _dp), ("truck_speed", _dp), ("truck_type", _ip), ("site_unit_begin", _ip),
         ("dumper_cycle", _dp), ("road_distance", _dp), ("load_time", _dp), ("sptf_cost", _dp),
         ("jam_chance", _dp), ("nearest_haul", _ip), ("nearest_back", _ip), ("fixed_group", _ip),
@@ -85,6 +86,7 @@ class PackedConfig:
         s.jam_capacity = self.jam_capacity
         s.sum_mode = 1 if self.sum_mode == "neumaier" else 0
         s.nearest_init = int(self.nearest_init)
+        s.flags = int(getattr(self, "flags", 0))
         dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
         for name in ("truck_capacity", "truck_speed", "dumper_cycle", "road_distance", "load_time", "sptf_cost",
                      "jam_chance", "shovel_rate", "site_productivity"):

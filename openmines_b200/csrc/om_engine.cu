@@ -188,6 +188,7 @@ struct OmEngine {
   const int64_t* tape_offsets = nullptr;
   int grid = 0, block = 0, smem = 0, warps = 0;
   bool split = false;   // cold part of the blob accessed in place in HBM
+  bool rl = false;           // created with OM_CFG_RL_SURFACE
   bool reset_done = false;   // om_reset has been enqueued at least once (om_run / om_step on a never-written blob could spin)
   std::string err;
 };
@@ -224,15 +225,16 @@ static uint32_t take(uint32_t& off, size_t elem, size_t count) {
   return r;
 }
 
-static void build_layout(const DevCfg& c, OmStateLayout& ly) {
+static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl) {
   memset(&ly, 0, sizeof(ly));
   uint32_t off = 0;
   const size_t T = c.T, U = c.U, R = c.R, J = c.J, NS = c.NS;
   // ---- hot part (always staged in shared memory) ----
-  ly.hdr = take(off, 8, OM_HDR_BYTES / 8);
+  // Without the RL surface the header stops before the reward-window fields (InstHdr up to n_rel = 120 bytes).
+  ly.hdr_bytes = rl ? OM_HDR_BYTES : 128;
+  ly.hdr = take(off, 8, ly.hdr_bytes / 8);
   ly.t_time = take(off, 16, T);       // 16-byte entries {time, key, phase}, scanned on every pop
   ly.t_key = ly.t_time + 8; ly.t_phase = ly.t_time + 12; ly.e_stride = OM_ESTRIDE;
-  ly.u_rel_time = take(off, 8, U);
   ly.t_stride = OM_TSTRIDE; ly.u_stride = OM_USTRIDE;
   ly.u_rec = take(off, 8, (size_t)U * OM_USTRIDE / 8);
   ly.u_last_start = ly.u_rec + 0; ly.u_last_done = ly.u_rec + 8; ly.u_tons = ly.u_rec + 16;
@@ -240,8 +242,9 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly) {
   ly.u_qlen = ly.u_rec + 34; ly.u_repair = ly.u_rec + 36;
   ly.u_lastbrk = take(off, 8, c.S);
   ly.r_repair_end = take(off, 8, R);
-  ly.s_tons = take(off, 8, NS); ly.s_cap = take(off, 8, NS); ly.s_ability = take(off, 8, NS);
-  size_t nscr = U;                                      // unit_est_all() results [U] or per-road counters [R] (u32)
+  if (rl) { ly.s_tons = take(off, 8, NS); ly.s_cap = take(off, 8, NS); ly.s_ability = take(off, 8, NS); }
+  // scratch: unit_est_all() results (both sides live at once only for the RL observation) or per-road counters (u32)
+  size_t nscr = rl ? U : ((size_t)c.S > (size_t)c.M ? (size_t)c.S : (size_t)c.M);
   if (nscr < (R + 1) / 2) nscr = (R + 1) / 2;
   if (nscr < 32) nscr = 32;
   ly.scratch = take(off, 8, nscr);
@@ -253,10 +256,12 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly) {
   ly.t_rec = take(off, 8, (size_t)T * OM_TSTRIDE / 8);
   ly.t_load = ly.t_rec + 0; ly.t_jstart = ly.t_rec + 8; ly.t_prejam = ly.t_rec + 16; ly.t_lastbrk = ly.t_rec + 24;
   ly.t_repair = ly.t_rec + 32; ly.t_total = ly.t_rec + 40; ly.t_cycle = ly.t_rec + 48; ly.t_dist = ly.t_rec + 56;
-  ly.t_since = ly.t_rec + 64; ly.t_rng = ly.t_rec + 72; ly.t_svc = ly.t_rec + 76; ly.t_epoch = ly.t_rec + 78;
-  ly.t_next = ly.t_rec + 80; ly.t_unit = ly.t_rec + 82; ly.t_status = ly.t_rec + 85;
-  ly.t_cur = ly.t_rec + 86; ly.t_tgt = ly.t_rec + 87;
-  ly.j_pos = take(off, 8, J); ly.j_start = take(off, 8, J); ly.j_end = take(off, 8, J);
+  ly.t_rng = ly.t_rec + 64; ly.t_svc = ly.t_rec + 68; ly.t_epoch = ly.t_rec + 70;
+  ly.t_next = ly.t_rec + 72; ly.t_unit = ly.t_rec + 74; ly.t_status = ly.t_rec + 77;
+  ly.t_cur = ly.t_rec + 78; ly.t_tgt = ly.t_rec + 79;
+  if (rl) ly.t_since = take(off, 8, T);
+  ly.j_pos = take(off, 8, J); ly.j_end = take(off, 8, J);
+  if (rl) ly.j_start = take(off, 8, J);
   ly.j_road = take(off, 2, J);
   ly.total_bytes = (off + 15u) & ~15u;
 }
@@ -333,7 +338,8 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
     else { h->order = (int32_t*)d; h->dev_allocs.push_back(d); }
   }
   if (rc == OM_OK) {
-    build_layout(c, h->ly);
+    h->rl = (cfg->flags & OM_CFG_RL_SURFACE) != 0;
+    build_layout(c, h->ly, h->rl);
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     int maxsm = 0;
@@ -480,6 +486,7 @@ int om_obs_dim(OmHandle h, int32_t* dim) {
 int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* stream) {
   if (!h || !state || !io || !io->obs) return set_err(h, OM_E_INVALID, "om_step: null argument");
   if (!h->reset_done) return set_err(h, OM_E_INVALID, "om_step: om_reset has not been called on this handle (the state blobs are uninitialised)");
+  if (!h->rl) return set_err(h, OM_E_INVALID, "om_step: the handle was created without OM_CFG_RL_SURFACE (OmConfig.flags)");
   CK(cudaSetDevice(h->device));
   RunParams p;
   memset(&p, 0, sizeof(p));

@@ -192,9 +192,9 @@ struct Sim {
   // DES code touches many fields of ONE truck / unit, so a record base + compile-time field offsets costs one
   // address computation per handler instead of one constant-bank load + add per access (the kernel is
   // instruction-fetch bound).  The pending entry of a truck {time, key, phase} is one 16-byte element (one LDS.128 per truck in the
-  // next-event scan, one STS.128 per schedule); u_rel_time / u_rel_key, roads, jams and per-site samples stay
+  // next-event scan, one STS.128 per schedule); u_rel_key (a pending Release always has time == now), roads, jams and per-site samples stay
   // structure-of-arrays.  F64(t_load, i) etc. dispatch on the field name.
-#define OM_TSTRIDE 88u
+#define OM_TSTRIDE 80u
 #define OM_USTRIDE 40u
 #define OM_ESTRIDE 16u   // pending entry of a truck: {double time; uint32 key; uint32 phase}
 #define OM_SOA(type, field, i) (((type*)(sm + ly.field))[i])
@@ -213,16 +213,15 @@ struct Sim {
 #define OM_A_t_total(type, i) OM_TREC(type, 40, i)
 #define OM_A_t_cycle(type, i) OM_TREC(type, 48, i)
 #define OM_A_t_dist(type, i) OM_TREC(type, 56, i)
-#define OM_A_t_since(type, i) OM_TREC(type, 64, i)
-#define OM_A_t_rng(type, i) OM_TREC(type, 72, i)
-#define OM_A_t_svc(type, i) OM_TREC(type, 76, i)
-#define OM_A_t_epoch(type, i) OM_TREC(type, 78, i)
-#define OM_A_t_next(type, i) OM_TREC(type, 80, i)
-#define OM_A_t_unit(type, i) OM_TREC(type, 82, i)
-#define OM_A_t_status(type, i) OM_TREC(type, 85, i)
-#define OM_A_t_cur(type, i) OM_TREC(type, 86, i)
-#define OM_A_t_tgt(type, i) OM_TREC(type, 87, i)
-#define OM_A_u_rel_time(type, i) OM_SOA(type, u_rel_time, i)
+#define OM_A_t_since(type, i) OM_SOAC(type, t_since, i)   /* RL surface only */
+#define OM_A_t_rng(type, i) OM_TREC(type, 64, i)
+#define OM_A_t_svc(type, i) OM_TREC(type, 68, i)
+#define OM_A_t_epoch(type, i) OM_TREC(type, 70, i)
+#define OM_A_t_next(type, i) OM_TREC(type, 72, i)
+#define OM_A_t_unit(type, i) OM_TREC(type, 74, i)
+#define OM_A_t_status(type, i) OM_TREC(type, 77, i)
+#define OM_A_t_cur(type, i) OM_TREC(type, 78, i)
+#define OM_A_t_tgt(type, i) OM_TREC(type, 79, i)
 #define OM_A_u_rel_key(type, i) OM_SOA(type, u_rel_key, i)
 #define OM_A_u_last_start(type, i) OM_UREC(type, 0, i)
 #define OM_A_u_last_done(type, i) OM_UREC(type, 8, i)
@@ -400,8 +399,7 @@ struct Sim {
     return key;
   }
   __device__ __forceinline__ void file_release(int u, uint32_t key) {
-    F64(u_rel_time, u) = now;
-    U32A(u_rel_key, u) = key;
+    U32A(u_rel_key, u) = key;          // its time is `now`: it pops before the clock can advance
     n_rel++;
   }
 
@@ -463,6 +461,8 @@ struct Sim {
   // site minima with site_est().
   __device__ __forceinline__ void unit_est_all(bool load_side) {
     int ub = load_side ? 0 : c.S, ue = load_side ? c.S : c.U;
+    // without the RL surface only one side's estimates are live at a time: dumpers share the shovels' slots
+    const int sbase = (!RL && !load_side) ? c.S : 0;
     #pragma unroll 1
     for (int u = ub + lane; u < ue; u += 32) {
       double est;
@@ -489,17 +489,18 @@ struct Sim {
         double used = now - F64(u_last_start, u);
         est = (total > used) ? (total - used) : 0.0;
       }
-      F64(scratch, u) = est;
+      F64(scratch, u - sbase) = est;
     }
     __syncwarp();
   }
   // min over the site's units (call after unit_est_all); lane-local loop
   __device__ __forceinline__ double site_est(int site) {
     int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
-    double m = F64(scratch, ub);
+    const int sbase = (!RL && site >= c.L) ? c.S : 0;
+    double m = F64(scratch, ub - sbase);
     #pragma unroll 1
     for (int u = ub + 1; u < ue; ++u) {
-      double v = F64(scratch, u);
+      double v = F64(scratch, u - sbase);
       if (v < m) m = v;
     }
     return m;
@@ -741,7 +742,7 @@ struct Sim {
         uint32_t j = base + lane;
         bool hit = false;
         if (j < jam_count)
-          hit = (U16A(j_road, j) == rid) && (F64(j_start, j) <= now) && (F64(j_end, j) >= now);
+          hit = (U16A(j_road, j) == rid) && (F64(j_end, j) >= now);   // start_time <= now holds for every stored jam
         unsigned m = __ballot_sync(OM_FULL, hit);
         #pragma unroll 1
         while (m) {
@@ -782,7 +783,7 @@ struct Sim {
         }
         if (F64(j_end, j) >= now) {
           if (w != j) {
-            F64(j_pos, w) = F64(j_pos, j); F64(j_start, w) = F64(j_start, j);
+            F64(j_pos, w) = F64(j_pos, j); if (RL) F64(j_start, w) = F64(j_start, j);
             F64(j_end, w) = F64(j_end, j); U16A(j_road, w) = U16A(j_road, j);
           }
           w++;
@@ -791,7 +792,7 @@ struct Sim {
       jam_count = w;
     }
     if (jam_count == (uint32_t)c.J) { fail(OM_IERR_JAM_OVERFLOW); return; }
-    F64(j_pos, jam_count) = pos; F64(j_start, jam_count) = now; F64(j_end, jam_count) = end;
+    F64(j_pos, jam_count) = pos; if (RL) F64(j_start, jam_count) = now; F64(j_end, jam_count) = end;
     U16A(j_road, jam_count) = (uint16_t)rid;
     jam_count++;
   }
@@ -1107,8 +1108,11 @@ struct Sim {
       if (n_rel != 0) {
         #pragma unroll 1
         for (int u = lane; u < U; u += 32) {
-          uint2 tv = *(const uint2*)&F64(u_rel_time, u);
+          // a pending Release was filed at the current clock and nothing earlier can be pending
           uint32_t kk = U32A(u_rel_key, u);
+          if (kk == OM_KEY_SENTINEL) continue;
+          uint2 tv;
+          tv.x = (uint32_t)__double2loint(now); tv.y = (uint32_t)__double2hiint(now);
           bool teq = (tv.y == bhi) && (tv.x == blo);
           bool tlt = (tv.y < bhi) || (tv.y == bhi && tv.x < blo);
           if (teq) dup = true;
@@ -1144,7 +1148,6 @@ struct Sim {
       if (id >= T) {
         // Release event popped: Resource._trigger_put hands the unit to the queue head
         u = id - T;
-        F64(u_rel_time, u) = om_inf();
         U32A(u_rel_key, u) = OM_KEY_SENTINEL;
         n_rel--;
         if (U16A(u_user, u) != OM_NONE16 || U16A(u_qlen, u) == 0) continue;
@@ -1408,7 +1411,7 @@ struct Sim {
       __syncwarp();
 #pragma unroll 1
       for (uint32_t j = lane; j < jam_count; j += 32)
-        if (F64(j_start, j) <= now && F64(j_end, j) >= now) atomicAdd(&rj[U16A(j_road, j)], 1u);
+        if (F64(j_end, j) >= now) atomicAdd(&rj[U16A(j_road, j)], 1u);
       __syncwarp();
 #pragma unroll 1
       for (int r = lane; r < R; r += 32) {
@@ -1579,7 +1582,6 @@ __device__ __forceinline__ void om_init_state(unsigned char* sm, const DevCfg& c
   }
   #pragma unroll 1
   for (int u = lane; u < c.U; u += 32) {
-    F64(u_rel_time, u) = inf;
     U32A(u_rel_key, u) = OM_KEY_SENTINEL;
     U16A(u_user, u) = OM_NONE16;
     U16A(u_head, u) = OM_NONE16;

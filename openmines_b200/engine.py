@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .config import PackedConfig, pack_config
+from .config import PackedConfig, pack_config, OM_CFG_RL_SURFACE
 from .trace import SUMMARY_DTYPE, TICK_DTYPE, TRACE_DTYPE
 
 RNG_MODES = {"det": 0, "philox": 1, "tape": 2}
@@ -37,12 +37,12 @@ class OmStepIOStruct(ctypes.Structure):
 
 _LAYOUT_FIELDS = ["total_bytes", "hdr", "t_time", "t_load", "t_jstart", "t_prejam", "t_lastbrk", "t_repair",
                   "t_total", "t_cycle", "t_dist", "t_since", "t_key", "t_rng", "t_svc", "t_epoch", "t_next", "t_unit", "t_phase",
-                  "t_status", "t_cur", "t_tgt", "u_rel_time", "u_last_start", "u_last_done", "u_tons", "u_lastbrk",
+                  "t_status", "t_cur", "t_tgt", "u_last_start", "u_last_done", "u_tons", "u_lastbrk",
                   "u_rel_key", "u_svc", "u_user", "u_head", "u_tail", "u_qlen", "u_repair", "r_repair_end",
                   "j_pos", "j_start", "j_end", "j_road", "s_qtotal", "s_coming", "s_tons", "s_cap", "s_ability", "scratch",
-                  "t_rec", "u_rec", "t_stride", "u_stride", "e_stride", "hot_bytes"]
+                  "t_rec", "u_rec", "t_stride", "u_stride", "e_stride", "hot_bytes", "hdr_bytes"]
 _ENTRY_FIELDS = {"t_time", "t_key", "t_phase"}                # the truck's 16-byte pending entry
-_SOA_FIELDS = {"u_rel_time", "u_rel_key", "u_lastbrk"}         # every other t_* / u_* field lives in a record
+_SOA_FIELDS = {"u_rel_key", "u_lastbrk", "t_since"}            # every other t_* / u_* field lives in a record
 
 
 # numpy mirror of the device-side InstHdr (csrc/om_engine.cuh): the first 192 bytes of every state blob
@@ -102,13 +102,18 @@ class RunResult:
 class BatchedMine:
     """N independent instances of one mine config on one GPU."""
 
-    def __init__(self, config, n_instances, device=0, jam_capacity=64, sum_mode="neumaier"):
+    def __init__(self, config, n_instances, device=0, jam_capacity=64, sum_mode="neumaier", rl_surface=False):
+        """``rl_surface=True`` allocates the fields ``om_step`` needs (reward windows, minute-sampled site values):
+        required by ``step()`` / ``BatchedMineEnv`` / ``run_external``; episode runs (``run()``) are faster without it
+        because smaller state blobs leave room for more resident instances per SM."""
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
             raise RuntimeError("openmines_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
         self.pc = config if isinstance(config, PackedConfig) else pack_config(config, jam_capacity, sum_mode)
+        self.pc.flags = OM_CFG_RL_SURFACE if rl_surface else 0
+        self.rl_surface = bool(rl_surface)
         self.n = int(n_instances)
         self.device = torch.device("cuda", device)
         self._cstruct = self.pc.c_struct()
@@ -255,7 +260,9 @@ class BatchedMine:
     # ------------------------------------------------------------------------------------------
     def headers(self):
         """Per-instance header records (HDR_DTYPE): clock, counters, error code, pending decision."""
-        raw = self.state[:, :HDR_DTYPE.itemsize].contiguous().cpu().numpy()
+        nb = int(self.layout.hdr_bytes)                    # 128 without the RL surface (the reward fields read as 0)
+        raw = np.zeros((self.n, HDR_DTYPE.itemsize), dtype=np.uint8)
+        raw[:, :nb] = self.state[:, :nb].contiguous().cpu().numpy()
         return raw.view(HDR_DTYPE).reshape(self.n).copy()
 
     def state_arrays(self, inst, blob=None):
@@ -286,7 +293,7 @@ class BatchedMine:
         for f in ("t_status", "t_cur", "t_tgt"):
             out[f] = arr(f, np.uint8, T)
         out["t_phase"] = arr("t_phase", np.uint32, T).astype(np.uint8)
-        for f in ("u_rel_time", "u_last_start", "u_last_done", "u_tons"):
+        for f in ("u_last_start", "u_last_done", "u_tons"):
             out[f] = arr(f, np.float64, U)
         out["u_lastbrk"] = arr("u_lastbrk", np.float64, S)   # shovels only (dumpers never break down)
         out["u_svc"] = arr("u_svc", np.uint32, U)
@@ -296,5 +303,7 @@ class BatchedMine:
         out["r_repair_end"] = arr("r_repair_end", np.float64, pc.R)
         for f in ("s_qtotal", "s_coming"):
             out[f] = arr(f, np.uint16, pc.L + pc.D)
-        out["hdr"] = np.frombuffer(raw, dtype=HDR_DTYPE, count=1, offset=ly.hdr)[0]
+        hb = bytearray(HDR_DTYPE.itemsize)
+        hb[:ly.hdr_bytes] = raw[ly.hdr:ly.hdr + ly.hdr_bytes]
+        out["hdr"] = np.frombuffer(bytes(hb), dtype=HDR_DTYPE, count=1)[0]
         return out

@@ -256,7 +256,7 @@ def run_external(dispatcher, config, n_instances=1, seeds=None, rng_mode="det", 
         dispatchers = [dispatcher() for _ in range(n)]
     else:
         dispatchers = [dispatcher] + [copy.deepcopy(dispatcher) for _ in range(n - 1)]
-    mine = BatchedMine(config, n, device=device, jam_capacity=jam_capacity)
+    mine = BatchedMine(config, n, device=device, jam_capacity=jam_capacity, rl_surface=True)   # om_step needs it
     seeds = np.arange(n, dtype=np.uint64) if seeds is None else np.asarray(seeds, dtype=np.uint64)
     mine.reset("external", seeds=seeds, rng_mode=rng_mode, tapes=tapes)
     dev = mine.device

@@ -19,7 +19,7 @@ class BatchedMineEnv:
                  auto_reset=False, jam_capacity=64):
         import torch
         self.torch = torch
-        self.mine = BatchedMine(config, num_envs, device=device, jam_capacity=jam_capacity)
+        self.mine = BatchedMine(config, num_envs, device=device, jam_capacity=jam_capacity, rl_surface=True)
         self.num_envs = int(num_envs)
         self.rng_mode = rng_mode
         self.teacher = DISPATCHER_IDS[sug_dispatcher] if sug_dispatcher else -1

@@ -221,3 +221,24 @@ def test_run_before_reset_is_an_error_not_a_hang(north_pit):
     env = BatchedMineEnv(north_pit, 4)
     with pytest.raises(RuntimeError, match="om_reset has not been called"):
         env.step(torch.zeros(4, dtype=torch.int32, device=env.mine.device))
+
+
+def test_lean_and_rl_layouts_agree(north_pit):
+    """Handles created with and without the RL surface (OM_CFG_RL_SURFACE: bigger header, reward-window fields, both
+    sides' wait estimates live at once) must simulate identically; om_step is refused on the lean layout."""
+    import torch
+    lean = _mine(north_pit, len(DISPATCHERS))
+    full = _mine(north_pit, len(DISPATCHERS), rl_surface=True)
+    assert lean.layout.total_bytes < full.layout.total_bytes and lean.layout.hdr_bytes == 128 and full.layout.hdr_bytes == 192
+    assert lean.launch_info()["warps_per_cta"] >= full.launch_info()["warps_per_cta"]
+    outs = []
+    for m in (lean, full):
+        m.reset(DISPATCHERS, seeds=np.arange(len(DISPATCHERS)) + 3, rng_mode="philox")
+        res = m.run(trace_capacity=8192, site_ticks=True)
+        outs.append((res.summary_np().copy(), res.ticks_np().copy(), [res.trace_np(i)[0].copy() for i in range(len(DISPATCHERS))]))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for a, b in zip(outs[0][2], outs[1][2]):
+        assert np.array_equal(a, b)
+    io = {"obs": torch.zeros((len(DISPATCHERS), lean.obs_dim()), device=lean.device)}
+    with pytest.raises(RuntimeError, match="OM_CFG_RL_SURFACE"):
+        lean.step(None, io)

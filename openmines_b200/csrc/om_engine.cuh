@@ -144,6 +144,9 @@ __device__ __noinline__ Philox4 om_philox(uint32_t c0, uint32_t c1, uint32_t c2,
   return philox4x32_10(c0, c1, c2, c3, k0, k1);
 }
 __device__ __noinline__ double om_ddiv(double a, double b) { return a / b; }
+// 0 / b without the division: a zero (or denormal) numerator sends div.rn.f64 down its ~110-instruction slow path, and the
+// counts / tonnages divided on the RL surface are zero most of the time.  Same value (+0.0) for b > 0.
+__device__ __forceinline__ double om_ddiv0(double a, double b) { return (a == 0.0) ? 0.0 : om_ddiv(a, b); }
 
 // CPython >= 3.12 sum() step over exact floats (Neumaier), see oracle/des_oracle.py py_sum
 struct PySum {
@@ -647,7 +650,7 @@ struct Sim {
             int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
             double dt0 = __ldg(&c.dcycle[ub - c.S]);
             double reach = now + om_ddiv(60.0 * __ldg(&c.rdist[road_id(cur, tgt)]), v);
-            double avail = (now + site_est(site)) + om_ddiv((double)cnt, (double)(ue - ub)) * dt0;
+            double avail = (now + site_est(site)) + om_ddiv0((double)cnt, (double)(ue - ub)) * dt0;
             double service = (avail > reach) ? avail : reach;      // np.maximum
             val = (service + dt0) - now;
           }
@@ -663,7 +666,7 @@ struct Sim {
             double prod = __ldg(&c.site_prod[lane]);
             double dist = __ldg(&c.rdist[road_id(cur, tgt)]);
             double reach = now + om_ddiv(60.0 * dist, v);
-            double avail = (now + site_est(lane)) + om_ddiv(capsum, prod);
+            double avail = (now + site_est(lane)) + om_ddiv0(capsum, prod);
             double service = (avail > reach) ? avail : reach;
             double loading = om_ddiv(__ldg(&c.cap[i]), om_ddiv(prod, (double)(ue - ub)));
             val = (service + loading) - now;
@@ -831,7 +834,7 @@ struct Sim {
         } else {
           PySum pd; pd.init();
 #pragma unroll 1
-          for (int u = ub; u < ue; ++u) pd.add(om_ddiv(F64(u_tons, u), __ldg(&c.dcycle[u - c.S])), neu);
+          for (int u = ub; u < ue; ++u) pd.add(om_ddiv0(F64(u_tons, u), __ldg(&c.dcycle[u - c.S])), neu);
           F64(s_cap, lane) = pd.result(neu);
           F64(s_ability, lane) = 1.0;
         }
@@ -1047,7 +1050,7 @@ struct Sim {
   // Truck.get_route_coverage (truck.py:496-520)
   __device__ __forceinline__ float coverage(int i, double base_dist) {
     double total = om_ddiv(base_dist, __ldg(&c.speed[i])) * 60.0 + F64(t_prejam, i) + F64(t_repair, i);
-    double cov = om_ddiv(now - F64(t_jstart, i), total);
+    double cov = om_ddiv0(now - F64(t_jstart, i), total);
     if (cov > 1.0) cov = 1.0;
     return (float)cov;
   }
@@ -1389,7 +1392,7 @@ struct Sim {
     rl_last_prod = reported_tons;
     double reward = -0.1 * w + -0.05 * service + -0.05 * jm + -0.01 * mv + 5.0 * log(delta + 1.0) + final_reward;
     double dt = now - rl_last;
-    if (dt > 0.0) reward += 0.1 * om_ddiv(delta, dt + 1e-6);
+    if (dt > 0.0) reward += 0.1 * om_ddiv0(delta, dt + 1e-6);
     acc_wait = acc_shovel = acc_dumper = acc_move = acc_jam = 0.0;
     return reward;
   }
@@ -1426,7 +1429,7 @@ struct Sim {
       ob[0] = kind == OM_ORDER_INIT ? 1.f : 0.f; ob[1] = kind == OM_ORDER_HAUL ? 1.f : 0.f;
       ob[2] = kind == OM_ORDER_BACK ? 1.f : 0.f;
       ob[3] = (float)(now - rl_last);
-      double time_now = om_ddiv(now, c.sim_time);
+      double time_now = om_ddiv0(now, c.sim_time);
       ob[4] = (float)time_now; ob[5] = (float)(1.0 - time_now);
       ob[o2] = (float)log(F64(t_load, i) + 1.0);
       ob[o2 + 1] = (float)log(F64(t_cycle, i) + 1.0);
@@ -1447,13 +1450,13 @@ struct Sim {
           int site = tgt - 1;
           double dist = __ldg(&c.rdist[road_id(cur, tgt)]);
           tt = (float)om_ddiv(dist * 60.0, 25.0);                        // speed is hard-coded (feature_processing.py:43)
-          tc = (float)om_ddiv((double)pair_cnt, tn);
+          tc = (float)om_ddiv0((double)pair_cnt, tn);
           double extra;
           if (kind == OM_ORDER_HAUL) {
             int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
-            extra = om_ddiv((double)on_cnt, (double)(ue - ub)) * __ldg(&c.dcycle[ub - c.S]);
+            extra = om_ddiv0((double)on_cnt, (double)(ue - ub)) * __ldg(&c.dcycle[ub - c.S]);
           } else {
-            extra = om_ddiv(capsum, __ldg(&c.site_prod[q]));
+            extra = om_ddiv0(capsum, __ldg(&c.site_prod[q]));
           }
           sw = (float)log((site_est(site) + extra) + 1.0);
         }
@@ -1464,7 +1467,7 @@ struct Sim {
 #pragma unroll 1
     for (int s = lane; s < NS; s += 32) {
       ob[o8 + s] = (float)log(site_est(s) + 1.0);
-      ob[o9 + s] = (float)om_ddiv((double)U16A(s_qtotal, s), tn);
+      ob[o9 + s] = (float)om_ddiv0((double)U16A(s_qtotal, s), tn);
       ob[o10 + s] = (float)log(F64(s_cap, s) + 1.0);
       ob[o11 + s] = (float)F64(s_ability, s);
       ob[o12 + s] = (float)log(F64(s_tons, s) + 1.0);

@@ -207,6 +207,7 @@ typedef struct OmStateLayout {
   uint32_t e_stride;           /* pending-entry size in bytes */
   uint32_t hot_bytes;          /* prefix of the blob the kernels stage in shared memory (== total_bytes unless split) */
   uint32_t hdr_bytes;          /* bytes of the per-instance header present in the blob */
+  uint32_t slot_cache;         /* kernel-internal cache (16 B per 32 trucks); contents are meaningless between calls */
 } OmStateLayout;
 
 typedef struct OmEngine* OmHandle;

@@ -262,6 +262,8 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl) {
   if (nscr < (R + 1) / 2) nscr = (R + 1) / 2;
   if (nscr < 32) nscr = 32;
   ly.scratch = take(off, 8, nscr);
+  // per-slot minima of the truck entries, used by the SPLIT kernels (valid within one kernel invocation only)
+  ly.slot_cache = take(off, 16, (T + 31) / 32);
   ly.u_rel_key = take(off, 4, U);
   ly.s_qtotal = take(off, 2, NS); ly.s_coming = take(off, 2, NS);
   ly.hot_bytes = (off + 15u) & ~15u;

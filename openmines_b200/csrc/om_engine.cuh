@@ -186,6 +186,7 @@ struct Sim {
   const double* tape_v;
   const uint8_t* tape_s;
   Philox4 ordw;   // words of the current order's Philox call (PHILOX mode)
+  uint32_t dirty; // slots (groups of 32 trucks) whose cached minimum is stale (see run())
   double rl_last, rl_last_prod, acc_wait, acc_shovel, acc_dumper, acc_move, acc_jam;   // RL only
 
   __device__ __forceinline__ Sim(unsigned char* sm_, unsigned char* blob, const RunParams& p, int lane_, long long inst_)
@@ -264,6 +265,7 @@ struct Sim {
     n_jams = h->n_jams; n_road_rep = h->n_road_rep; n_brk = h->n_brk; n_unrep = h->n_unrep;
     jam_count = h->jam_count; err = h->err; trace_count = h->trace_count; order_count = h->order_count;
     n_ticks = h->n_ticks; n_rel = h->n_rel;
+    dirty = 0xFFFFFFFFu;            // the slot cache is not part of the persistent state
     if (RL) {
       rl_last = h->rl_last_time; rl_last_prod = h->rl_last_prod; acc_wait = h->acc_wait; acc_shovel = h->acc_shovel;
       acc_dumper = h->acc_dumper; acc_move = h->acc_move; acc_jam = h->acc_jam;
@@ -358,6 +360,7 @@ struct Sim {
     uint4 e;
     e.x = (uint32_t)__double2loint(t); e.y = (uint32_t)__double2hiint(t); e.z = key; e.w = phase;
     *(uint4*)(sm + ly.t_time + (uint32_t)i * OM_ESTRIDE) = e;
+    if (SPLIT) dirty |= 1u << (((uint32_t)i >> 5) & 31u);
   }
   __device__ __forceinline__ void sched_truck(int i, double t, uint32_t prio, uint8_t phase) {
     set_entry(i, t, prio | seq, phase);
@@ -1092,11 +1095,13 @@ struct Sim {
     const int T = c.T, U = c.U, L = c.L, D = c.D, S = c.S;
     int pend_truck = -1, pend_kind = -1;
     for (;;) {
-      // ---- lane-local minimum over this lane's trucks and units (times are >= 0: compare bit patterns)
+      // ---- next pending entry.  Times are >= 0, so their bit patterns order as unsigned integers.
       uint32_t bhi = 0x7FF00000u, blo = 0u, bk = OM_KEY_SENTINEL;
       int bid = -1;
       bool dup = false;
-      {
+      const int nslot = (T + 31) >> 5;
+      if (!SPLIT) {
+        // every lane scans its truck entries (one LDS.128 each; 3 for north_pit)
         const uint4* ev = (const uint4*)(sm + ly.t_time) + lane;
         #pragma unroll 1
         for (int i = lane; i < T; i += 32, ev += 32) {
@@ -1106,6 +1111,45 @@ struct Sim {
           if (teq) dup = true;
           if (tlt) dup = false;
           if (tlt || (teq && e.z < bk)) { bhi = e.y; blo = e.x; bk = e.z; bid = i; }
+        }
+      } else {
+        // big mines (the SPLIT kernels): truck entries are cached per SLOT of 32 trucks -- {min time, its smallest key, that truck, "several
+        // entries share the slot's min time"} in shared memory, recomputed (one LDS.128 per lane + 4 redux + 1 ballot)
+        // only for the slots an entry of which changed since the last pop (one or two) instead of scanning all T
+        // entries: -10 % on the 500-truck mine.  Compiled only into the SPLIT kernels: on north_pit (3 slots) it saves
+        // nothing, and merely having the code in the hot loop cost 13 % (instruction-cache layout).
+        uint4* slots = (uint4*)(sm + ly.slot_cache);
+        uint32_t d = (nslot > 32) ? 0xFFFFFFFFu : (dirty & ((nslot == 32) ? 0xFFFFFFFFu : ((1u << nslot) - 1u)));
+        dirty = 0u;
+        #pragma unroll 1
+        while (d) {
+          const int b = __ffs(d) - 1;
+          d &= d - 1;
+          #pragma unroll 1
+          for (int sl = b; sl < nslot; sl += 32) {       // more than one trip only for T > 1024
+            const int idx = (sl << 5) + lane;
+            uint4 e;
+            e.x = 0u; e.y = 0x7FF00000u; e.z = OM_KEY_SENTINEL; e.w = 0u;
+            if (idx < T) e = *((const uint4*)(sm + ly.t_time) + idx);
+            uint32_t shi = __reduce_min_sync(OM_FULL, e.y);
+            uint32_t slo = __reduce_min_sync(OM_FULL, (e.y == shi) ? e.x : 0xFFFFFFFFu);
+            bool sc = (e.y == shi) && (e.x == slo);
+            uint32_t sk = __reduce_min_sync(OM_FULL, sc ? e.z : OM_KEY_SENTINEL);
+            uint32_t sid = __reduce_min_sync(OM_FULL, (sc && e.z == sk) ? (uint32_t)idx : 0x7FFFFFFFu);
+            uint32_t multi = (__popc(__ballot_sync(OM_FULL, sc)) > 1) ? 0x80000000u : 0u;
+            if (lane == 0) slots[sl] = make_uint4(slo, shi, sk, sid | multi);
+          }
+        }
+        __syncwarp();
+        #pragma unroll 1
+        for (int sl = lane; sl < nslot; sl += 32) {
+          const uint4 e = slots[sl];
+          bool teq = (e.y == bhi) && (e.x == blo);
+          bool tlt = (e.y < bhi) || (e.y == bhi && e.x < blo);
+          if (teq) dup = true;
+          if (tlt) dup = (e.w >> 31) != 0u;
+          else if (teq && (e.w >> 31)) dup = true;
+          if (tlt || (teq && e.z < bk)) { bhi = e.y; blo = e.x; bk = e.z; bid = (int)(e.w & 0x7FFFFFFFu); }
         }
       }
       if (n_rel != 0) {

@@ -561,43 +561,49 @@ struct Sim {
   // the six built-in dispatchers as device functions (dispatch_algorithms/*.py) behind
   // give_init_order / give_haul_order / give_back_order.  Returns the site index, or -1 on error.
   // ---------------------------------------------------------------------------------------------
+  // Every helper below (unit_est_all, site_est, road_load, argmin_lanes) has ONE call site: they are force-inlined,
+  // and duplicated copies of them used to make this function 14 KB of SASS in the middle of the hot order chain.
   __device__ __forceinline__ int decide(int kind, int i) {
     int r = 0;
     const int L = c.L, D = c.D;
+    const bool haul = kind == OM_ORDER_HAUL;
+    const int n = haul ? D : L;                 // candidate sites of this order
+    const int sbase_site = haul ? L : 0;        // site index of candidate 0
+    const bool est = (disp == OM_DISP_SPTF) | (disp == OM_DISP_SHORTESTTRIP);
+    double val = om_inf();                      // lane q < n: cost of candidate q (argmin dispatchers)
+    double wait = 0.0;                          // lane q < n: estimated_queue_wait_time of candidate q
+    if (est) {
+      unit_est_all(!haul);                      // dispatcher.update_mine (dispatcher.py:24-33) for the side that matters
+      if (lane < n) wait = site_est(sbase_site + lane);
+    }
     switch (disp) {
       case OM_DISP_NAIVE:
         r = 0;
         break;
       case OM_DISP_RANDOM: {
         // haul draws over len(load_sites), back over len(dump_sites)  (random_dispatcher.py:21-29)
-        int n = (kind == OM_ORDER_BACK) ? D : L;
-        r = draw_randint(U16A(t_epoch, i), (uint32_t)i, n);
+        r = draw_randint(U16A(t_epoch, i), (uint32_t)i, (kind == OM_ORDER_BACK) ? D : L);
         break;
       }
       case OM_DISP_NEAREST:
         if (kind == OM_ORDER_INIT) r = c.nearest_init;
-        else if (kind == OM_ORDER_HAUL) r = __ldg(&c.near_haul[U8A(t_cur, i) - 1]);
+        else if (haul) r = __ldg(&c.near_haul[U8A(t_cur, i) - 1]);
         else r = __ldg(&c.near_back[U8A(t_cur, i) - 1 - L]);
         break;
       case OM_DISP_FIXEDGROUP:
-        if (kind == OM_ORDER_HAUL) r = __ldg(&c.near_haul[U8A(t_cur, i) - 1]);
+        if (haul) r = __ldg(&c.near_haul[U8A(t_cur, i) - 1]);
         else r = __ldg(&c.fixed_group[i]);
         break;
       case OM_DISP_SPTF: {
-        if (kind == OM_ORDER_HAUL) {
+        if (haul) {
           // len(coming) + estimated_queue_wait_time   (sptf_dispatcher.py:40-57)
-          unit_est_all(false);
-          double v = om_inf();
           if (lane < D) {
             int site = L + lane;
             int coming = (int)U16A(s_coming, site) - ((U8A(t_tgt, i) == 1 + site) ? 1 : 0);
-            v = (double)coming + site_est(site);
+            val = (double)coming + wait;
           }
-          r = argmin_lanes(v, D);
         } else {
           // sum(cap/productivity for coming trucks, truck order) + estimated_queue_wait_time (:21-38)
-          unit_est_all(true);
-          double v = om_inf();
           PySum ps; ps.init();
           const bool neu = c.sum_mode != 0;
           #pragma unroll 1
@@ -617,21 +623,17 @@ struct Sim {
               ps.add(__ldg(&c.sptf_cost[__ldg(&c.ttype[base + b]) * L + lane]), neu);
             }
           }
-          if (lane < L) v = ps.result(neu) + site_est(lane);
-          r = argmin_lanes(v, L);
+          if (lane < L) val = ps.result(neu) + wait;
         }
-        __syncwarp();
         break;
       }
       case OM_DISP_SQ: {
         // coming trucks + minute-sampled total queue length (sq_dispatcher.py:18-100)
         int k = (int)now;   // int(env.now)
         if (k != tick_k) return -OM_IERR_SQ_KEYERROR;   // KeyError: queue_status['total'][int(now)] not sampled yet
-        int n = (kind == OM_ORDER_HAUL) ? D : L;
-        int base = (kind == OM_ORDER_HAUL) ? L : 0;
         uint32_t v = 0xFFFFFFFFu;
         if (lane < n) {
-          int site = base + lane;
+          int site = sbase_site + lane;
           uint32_t coming = (uint32_t)U16A(s_coming, site) - ((U8A(t_tgt, i) == 1 + site) ? 1u : 0u);
           v = ((coming + (uint32_t)U16A(s_qtotal, site)) << 8) | (uint32_t)lane;
         }
@@ -639,48 +641,40 @@ struct Sim {
         break;
       }
       case OM_DISP_SHORTESTTRIP: {
-        // shortest_trip_dispatcher.py:12-84: earliest expected finish of (travel | queue + on-road trucks) + service
+        // shortest_trip_dispatcher.py:12-84: earliest expected finish of (travel | queue + on-road trucks) + service.
+        // Trucks already on the road: for haul orders those from the current load site, for init AND back orders those
+        // on the charging-site roads (:71).
         const double v = __ldg(&c.speed[i]);
         const int cur = U8A(t_cur, i);
-        double val = om_inf();
-        if (kind == OM_ORDER_HAUL) {
-          unit_est_all(false);
-          int pc_, cnt;
-          double cs_;
-          road_load(cur, 1 + L, D, pc_, cnt, cs_);
-          if (lane < D) {
-            int site = L + lane, tgt = 1 + site;
-            int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
+        int pc_, cnt;
+        double capsum;
+        road_load(haul ? cur : 0, 1 + sbase_site, n, pc_, cnt, capsum);
+        if (lane < n) {
+          int site = sbase_site + lane, tgt = 1 + site;
+          int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
+          double reach = now + om_ddiv(60.0 * __ldg(&c.rdist[road_id(cur, tgt)]), v);
+          double busy, service_time;
+          if (haul) {
             double dt0 = __ldg(&c.dcycle[ub - c.S]);
-            double reach = now + om_ddiv(60.0 * __ldg(&c.rdist[road_id(cur, tgt)]), v);
-            double avail = (now + site_est(site)) + om_ddiv0((double)cnt, (double)(ue - ub)) * dt0;
-            double service = (avail > reach) ? avail : reach;      // np.maximum
-            val = (service + dt0) - now;
-          }
-          r = argmin_lanes(val, D);
-        } else {
-          unit_est_all(true);
-          int pc_, oc_;
-          double capsum;                                           // trucks on the charging-site road, also for back orders (:71)
-          road_load(0, 1, L, pc_, oc_, capsum);
-          if (lane < L) {
-            int tgt = 1 + lane;
-            int ub = __ldg(&c.ubeg[lane]), ue = __ldg(&c.ubeg[lane + 1]);
+            busy = om_ddiv0((double)cnt, (double)(ue - ub)) * dt0;
+            service_time = dt0;
+          } else {
             double prod = __ldg(&c.site_prod[lane]);
-            double dist = __ldg(&c.rdist[road_id(cur, tgt)]);
-            double reach = now + om_ddiv(60.0 * dist, v);
-            double avail = (now + site_est(lane)) + om_ddiv0(capsum, prod);
-            double service = (avail > reach) ? avail : reach;
-            double loading = om_ddiv(__ldg(&c.cap[i]), om_ddiv(prod, (double)(ue - ub)));
-            val = (service + loading) - now;
+            busy = om_ddiv0(capsum, prod);
+            service_time = om_ddiv(__ldg(&c.cap[i]), om_ddiv(prod, (double)(ue - ub)));
           }
-          r = argmin_lanes(val, L);
+          double avail = (now + wait) + busy;
+          double service = (avail > reach) ? avail : reach;        // np.maximum
+          val = (service + service_time) - now;
         }
-        __syncwarp();
         break;
       }
       default:
         return -OM_IERR_BAD_ORDER;
+    }
+    if (est) {
+      r = argmin_lanes(val, n);
+      __syncwarp();
     }
     return r;
   }
@@ -714,24 +708,16 @@ struct Sim {
     count_order(kind, site);
     U16A(t_epoch, i) = (uint16_t)(epoch + 1);
     double dist;
-    int tgt;
+    const int tgt = (kind == OM_ORDER_HAUL) ? 1 + L + site : 1 + site;
     if (kind == OM_ORDER_INIT) {
       U8A(t_status, i) = ST_MOVING;
-      tgt = 1 + site;
       dist = __ldg(&c.rdist[site]);      // charging_to_load[site]; no road events on this leg (truck.py:308)
-      set_target(i, tgt);
-      emit(K_INIT_ORDER, (uint32_t)i, (uint32_t)site, 0, dist, 0.0);
-    } else if (kind == OM_ORDER_HAUL) {
-      tgt = 1 + L + site;
-      dist = get_distance(i, U8A(t_cur, i), tgt, epoch);
-      set_target(i, tgt);
-      emit(K_ORDER_HAUL, (uint32_t)i, (uint32_t)site, 0, dist, 0.0);
     } else {
-      tgt = 1 + site;
       dist = get_distance(i, U8A(t_cur, i), tgt, epoch);
-      set_target(i, tgt);
-      emit(K_ORDER_BACK, (uint32_t)i, (uint32_t)site, 0, dist, 0.0);
     }
+    set_target(i, tgt);
+    emit((kind == OM_ORDER_INIT) ? K_INIT_ORDER : ((kind == OM_ORDER_HAUL) ? K_ORDER_HAUL : K_ORDER_BACK), (uint32_t)i,
+         (uint32_t)site, 0, dist, 0.0);
     F64(t_dist, i) = dist;
   }
 
@@ -1182,7 +1168,7 @@ struct Sim {
       if (!(tmin < until) || (err != OM_IERR_NONE && err != OM_IERR_TRACE_OVERFLOW)) break;
       now = tmin;
       n_hops++;
-      if (is_tick) { tick_block(); continue; }
+      if (__builtin_expect(is_tick, 0)) { tick_block(); continue; }   // 15 % of the pops: keep its 12 KB out of the main path
 
       const bool inl = now > 0.0;            // URGENT successors run inline
       const bool chain = unique && inl;      // same-time NORMAL successors run inline

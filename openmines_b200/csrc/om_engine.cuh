@@ -440,7 +440,7 @@ struct Sim {
       if (RNG != OM_RNG_DET) {
         double gap = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(ordw.x) / c.road_lambda
                                             : draw_exp(OM_S_ROAD_GAP, epoch, (uint32_t)i, 1.0 / c.road_lambda);   // expovariate(lambda)
-        if (now >= end + gap) {
+        if (__builtin_expect(now >= end + gap, 0)) {   // a new road repair starts: a handful per episode
           double d = draw_normal(OM_S_ROAD_DUR, epoch, (uint32_t)i, c.road_mu, c.road_sigma);
           double dur = (d > 0.0) ? d : 0.0;   // max(0, x)
           in_repair = true;
@@ -746,7 +746,7 @@ struct Sim {
       }
       F64(t_prejam, i) = pre;
     }
-    if (dead) {
+    if (__builtin_expect(dead, 0)) {
       n_unrep++;
       emit(K_UNREPAIRABLE, (uint32_t)i, 0, 0, 0.0, 0.0);
       U8A(t_status, i) = ST_UNREPAIRABLE;
@@ -765,7 +765,7 @@ struct Sim {
   // jam pool
   // ---------------------------------------------------------------------------------------------
   __device__ __forceinline__ void jam_append(int rid, double pos, double end) {
-    if (jam_count == (uint32_t)c.J) {   // drop expired entries, keep creation order
+    if (__builtin_expect(jam_count == (uint32_t)c.J, 0)) {   // drop expired entries, keep creation order
       uint32_t w = 0;
       #pragma unroll 1
       for (uint32_t j = 0; j < jam_count; ++j) {
@@ -869,7 +869,7 @@ struct Sim {
         if (out.site_queue_ticks != nullptr) out.site_queue_ticks[o] = (uint16_t)qtot;
         if (out.site_tons_ticks != nullptr) out.site_tons_ticks[o] = site_tons;
       }
-      if (out.unit_ticks != nullptr) {
+      if (__builtin_expect(out.unit_ticks != nullptr, 0)) {
 #pragma unroll 1
         for (int u = lane; u < c.U; u += 32) {
           OmUnitTick r;

@@ -515,7 +515,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000 * e2e_s / a.steps},
-            "gpu_launches": a.steps * 3,      # om_reset_kernel + om_run_kernel + om_stats_kernel per step
+            "gpu_launches": a.steps * 4,      # om_reset_kernel + om_order_kernel + om_run_kernel + om_stats_kernel per step
             "roofline": roofline}
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:

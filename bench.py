@@ -435,30 +435,31 @@ def main():
     episodes_per_s = total_instances / (ms_per_step / 1000.0)
 
     # ---- end-to-end arm: host buffers in, host results out, every step ------------------------
-    h_seeds = torch.from_numpy(seeds.view(np.int64)).pin_memory()
-    h_disp = torch.from_numpy(disp).pin_memory()
-    h_summary = torch.empty((n, 64), dtype=torch.uint8).pin_memory()
-    h_ticks = torch.empty((n, res.tick_capacity, 32), dtype=torch.uint8).pin_memory()
-    d_seeds, d_disp = torch.empty_like(mine.seeds), torch.empty_like(mine.dispatcher_ids)
+    # The public streaming API (openmines_b200.pipeline.EpisodePipeline): every step uploads its (seed, dispatcher)
+    # arrays from pinned host memory, resets, simulates, and brings summaries + per-minute KPI records back to pinned
+    # host memory, where they are read.  Outputs are double-buffered, so step k's device->host copy overlaps step k+1's
+    # kernel; all copies of all K steps are inside the timed region.
+    from openmines_b200.pipeline import EpisodePipeline
+    pipe = EpisodePipeline(mine, rng_mode=mode)
 
-    def step_e2e():
-        d_seeds.copy_(h_seeds, non_blocking=True)
-        d_disp.copy_(h_disp, non_blocking=True)
-        mine._ck(mine.lib.om_reset(mine.h, d_seeds.data_ptr(), d_disp.data_ptr(), om.engine.RNG_MODES[mode],
-                                   None, None, None, mine.state.data_ptr(), mine._stream()))
-        mine.run(result=res)
-        h_summary.copy_(res.summary, non_blocking=True)
-        h_ticks.copy_(res.ticks, non_blocking=True)
-        torch.cuda.current_stream().synchronize()         # the caller reads the production curves here
-        return float(h_summary.numpy().view(om.trace.SUMMARY_DTYPE)["reported_tons"].sum())
+    def e2e_steps(k):
+        tons = 0.0
+        for _ in range(k):
+            pipe.submit(disp, seeds)
+            if pipe.pending == pipe.depth:
+                summ, ticks = pipe.collect()
+                tons += float(summ["reported_tons"].sum()) + float(ticks["produced_tons"][:, -1].sum())   # the caller reads the curves
+        while pipe.pending:
+            summ, ticks = pipe.collect()
+            tons += float(summ["reported_tons"].sum()) + float(ticks["produced_tons"][:, -1].sum())
+        return tons
 
-    step_e2e()
+    e2e_steps(2)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        step_e2e()
+    e2e_steps(a.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -466,8 +467,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = total_events / (e2e_s / a.steps)
-    h2d = h_seeds.numel() * 8 + h_disp.numel() * 4
-    d2h = h_summary.numel() + h_ticks.numel()
+    h2d = pipe.h2d_bytes
+    d2h = pipe.d2h_bytes
 
     # ---- roofline of the dominant kernel (om_run_kernel) --------------------------------------
     peaks = {}

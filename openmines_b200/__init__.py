@@ -9,5 +9,6 @@ from .dispatcher import (BaseDispatcher, NaiveDispatcher, RandomDispatcher, Near
                          FixedGroupDispatcher, SPTFDispatcher, SQDispatcher, ShortestTripDispatcher, by_name)
 from .engine import BatchedMine, RunResult, DISPATCHER_IDS          # noqa: F401
 from .external import run_external, build_mine_view                 # noqa: F401
+from .pipeline import EpisodePipeline                               # noqa: F401
 
 __version__ = "0.1.0"

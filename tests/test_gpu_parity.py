@@ -242,3 +242,33 @@ def test_lean_and_rl_layouts_agree(north_pit):
     io = {"obs": torch.zeros((len(DISPATCHERS), lean.obs_dim()), device=lean.device)}
     with pytest.raises(RuntimeError, match="OM_CFG_RL_SURFACE"):
         lean.step(None, io)
+
+
+def test_episode_pipeline_matches_direct_runs(north_pit):
+    """EpisodePipeline (double-buffered outputs, copies on a side stream) returns, in submission order, exactly what
+    synchronous reset + run calls return."""
+    from openmines_b200.pipeline import EpisodePipeline
+    n = 96
+    ids = (np.arange(n) % 6).astype(np.int32)
+    mine = _mine(north_pit, n)
+    want = []
+    for b in range(4):
+        mine.reset(ids, seeds=np.arange(n) + 100 * b, rng_mode="philox")
+        r = mine.run()
+        want.append((r.summary_np().copy(), r.ticks_np().copy()))
+    pipe = EpisodePipeline(mine, rng_mode="philox")
+    got = []
+    for b in range(4):
+        pipe.submit(ids, np.arange(n, dtype=np.uint64) + 100 * b)
+        if pipe.pending == pipe.depth:
+            s, t = pipe.collect()
+            got.append((s.copy(), t.copy()))
+    while pipe.pending:
+        s, t = pipe.collect()
+        got.append((s.copy(), t.copy()))
+    assert len(got) == 4
+    for (ws, wt), (gs, gt) in zip(want, got):
+        assert np.array_equal(ws, gs) and np.array_equal(wt, gt)
+    with pytest.raises(RuntimeError):
+        for _ in range(3):
+            pipe.submit(ids, np.arange(n, dtype=np.uint64))

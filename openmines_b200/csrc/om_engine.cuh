@@ -147,6 +147,9 @@ __device__ __noinline__ double om_ddiv(double a, double b) { return a / b; }
 // 0 / b without the division: a zero (or denormal) numerator sends div.rn.f64 down its ~110-instruction slow path, and the
 // counts / tonnages divided on the RL surface are zero most of the time.  Same value (+0.0) for b > 0.
 __device__ __forceinline__ double om_ddiv0(double a, double b) { return (a == 0.0) ? 0.0 : om_ddiv(a, b); }
+// log(x) in fp64, out of line: the RL surface takes eight logs per env step, and one shared copy of the ~90-instruction body
+// stays in the instruction cache while eight inlined copies are streamed once each (the step kernel is fetch-bound)
+__device__ __noinline__ double om_dlog(double x) { return log(x); }
 
 // CPython >= 3.12 sum() step over exact floats (Neumaier), see oracle/des_oracle.py py_sum
 struct PySum {
@@ -563,7 +566,7 @@ struct Sim {
   // ---------------------------------------------------------------------------------------------
   // Every helper below (unit_est_all, site_est, road_load, argmin_lanes) has ONE call site: they are force-inlined,
   // and duplicated copies of them used to make this function 14 KB of SASS in the middle of the hot order chain.
-  __device__ __forceinline__ int decide(int kind, int i) {
+  __device__ __forceinline__ int decide(int kind, int i, bool est_ready = false) {
     int r = 0;
     const int L = c.L, D = c.D;
     const bool haul = kind == OM_ORDER_HAUL;
@@ -573,7 +576,8 @@ struct Sim {
     double val = om_inf();                      // lane q < n: cost of candidate q (argmin dispatchers)
     double wait = 0.0;                          // lane q < n: estimated_queue_wait_time of candidate q
     if (est) {
-      unit_est_all(!haul);                      // dispatcher.update_mine (dispatcher.py:24-33) for the side that matters
+      // dispatcher.update_mine (dispatcher.py:24-33) for the side that matters; the RL step has both sides in scratch already
+      if (!est_ready) unit_est_all(!haul);
       if (lane < n) wait = site_est(sbase_site + lane);
     }
     switch (disp) {
@@ -1420,7 +1424,7 @@ struct Sim {
     }
     double delta = reported_tons - rl_last_prod;   // mine.produce_tons is the minute-sampled value
     rl_last_prod = reported_tons;
-    double reward = -0.1 * w + -0.05 * service + -0.05 * jm + -0.01 * mv + 5.0 * log(delta + 1.0) + final_reward;
+    double reward = -0.1 * w + -0.05 * service + -0.05 * jm + -0.01 * mv + 5.0 * om_dlog(delta + 1.0) + final_reward;
     double dt = now - rl_last;
     if (dt > 0.0) reward += 0.1 * om_ddiv0(delta, dt + 1e-6);
     acc_wait = acc_shovel = acc_dumper = acc_move = acc_jam = 0.0;
@@ -1453,16 +1457,17 @@ struct Sim {
       }
       __syncwarp();
     }
-    unit_est_all(true);                             // dispatcher.update_mine (dispatcher.py:24-33)
-    unit_est_all(false);
+    // dispatcher.update_mine (dispatcher.py:24-33): both sides' wait estimates (one inlined copy, two trips)
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) unit_est_all(side == 0);
     if (lane == 0) {
       ob[0] = kind == OM_ORDER_INIT ? 1.f : 0.f; ob[1] = kind == OM_ORDER_HAUL ? 1.f : 0.f;
       ob[2] = kind == OM_ORDER_BACK ? 1.f : 0.f;
       ob[3] = (float)(now - rl_last);
       double time_now = om_ddiv0(now, c.sim_time);
       ob[4] = (float)time_now; ob[5] = (float)(1.0 - time_now);
-      ob[o2] = (float)log(F64(t_load, i) + 1.0);
-      ob[o2 + 1] = (float)log(F64(t_cycle, i) + 1.0);
+      ob[o2] = (float)om_dlog(F64(t_load, i) + 1.0);
+      ob[o2 + 1] = (float)om_dlog(F64(t_cycle, i) + 1.0);
     }
 #pragma unroll 1
     for (int q = lane; q < 1 + NS; q += 32) ob[o1 + q] = (q == cur) ? 1.f : 0.f;
@@ -1488,7 +1493,7 @@ struct Sim {
           } else {
             extra = om_ddiv0(capsum, __ldg(&c.site_prod[q]));
           }
-          sw = (float)log((site_est(site) + extra) + 1.0);
+          sw = (float)om_dlog((site_est(site) + extra) + 1.0);
         }
         ob[o3 + q] = tt; ob[o4 + q] = tc; ob[o7 + q] = sw;
       }
@@ -1496,11 +1501,11 @@ struct Sim {
     // per-site blocks
 #pragma unroll 1
     for (int s = lane; s < NS; s += 32) {
-      ob[o8 + s] = (float)log(site_est(s) + 1.0);
+      ob[o8 + s] = (float)om_dlog(site_est(s) + 1.0);
       ob[o9 + s] = (float)om_ddiv0((double)U16A(s_qtotal, s), tn);
-      ob[o10 + s] = (float)log(F64(s_cap, s) + 1.0);
+      ob[o10 + s] = (float)om_dlog(F64(s_cap, s) + 1.0);
       ob[o11 + s] = (float)F64(s_ability, s);
-      ob[o12 + s] = (float)log(F64(s_tons, s) + 1.0);
+      ob[o12 + s] = (float)om_dlog(F64(s_tons, s) + 1.0);
     }
     __syncwarp();
   }
@@ -1547,7 +1552,7 @@ struct Sim {
         int saved_disp = disp;
         uint32_t saved_err = err;
         disp = io.teacher;
-        sug = decide(pk, pt);
+        sug = decide(pk, pt, true);              // rl_observation() left both sides' wait estimates in scratch
         if (sug < 0) sug = -1;                       // the teacher raised (e.g. SQ before its minute's sample)
         disp = saved_disp; err = saved_err;
       }

@@ -150,6 +150,12 @@ __device__ __forceinline__ double om_ddiv0(double a, double b) { return (a == 0.
 // log(x) in fp64, out of line: the RL surface takes eight logs per env step, and one shared copy of the ~90-instruction body
 // stays in the instruction cache while eight inlined copies are streamed once each (the step kernel is fetch-bound)
 __device__ __noinline__ double om_dlog(double x) { return log(x); }
+// butterfly sum over the warp, out of line (five call sites in the reward)
+__device__ __noinline__ double om_warp_sum(double v) {
+#pragma unroll 1
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
 // CPython >= 3.12 sum() step over exact floats (Neumaier), see oracle/des_oracle.py py_sum
 struct PySum {
@@ -1387,12 +1393,6 @@ struct Sim {
   // RL step surface: dense reward (rl_dispatch.py:194-308), observation float32[obs_dim]
   // (rl_dispatch.py:309-509 + utils/feature_processing.py:3-75), teacher suggestion (:169-184)
   // ---------------------------------------------------------------------------------------------
-  __device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll 1
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(OM_FULL, v, o);
-    return v;
-  }
-
   __device__ __forceinline__ double rl_reward(bool final_step) {
     const int T = c.T;
     double w = 0.0, sh = 0.0, du = 0.0, mv = 0.0, jm = 0.0;
@@ -1413,10 +1413,10 @@ struct Sim {
       double lo = (st > rl_last) ? st : rl_last, hi = (en < now) ? en : now;
       if (lo < hi) jm += hi - lo;
     }
-    w = acc_wait + warp_sum(w);
-    double service = (acc_shovel + warp_sum(sh)) + (acc_dumper + warp_sum(du));
-    mv = acc_move + warp_sum(mv);
-    jm = acc_jam + warp_sum(jm);
+    w = acc_wait + om_warp_sum(w);
+    double service = (acc_shovel + om_warp_sum(sh)) + (acc_dumper + om_warp_sum(du));
+    mv = acc_move + om_warp_sum(mv);
+    jm = acc_jam + om_warp_sum(jm);
     double final_reward = 0.0;
     if (final_step && now != 0.0) {
       double ft = rl_last_prod - 10000.0;

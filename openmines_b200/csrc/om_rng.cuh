@@ -51,7 +51,7 @@ __device__ __forceinline__ float om_exp1(uint32_t x) { return -__logf(om_u01(x))
 
 // standard normal from two 32-bit words (Box-Muller on the MUFU log2 / rsqrt / cos units; live-mode draws are
 // distribution-level only): ~12 instructions inline
-__device__ __forceinline__ float om_normal_fast(uint32_t a, uint32_t b) {
+__device__ __noinline__ float om_normal_fast(uint32_t a, uint32_t b) {
   float x = -2.0f * __logf(om_u01(a));
   float r = x * rsqrtf(fmaxf(x, 1e-30f));
   return r * __cosf(6.283185307179586f * om_u01(b) - 3.14159265358979f);   // cos(2 pi u - pi) = -cos(2 pi u): same law

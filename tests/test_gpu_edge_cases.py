@@ -98,3 +98,28 @@ def test_integer_mine_tie_stress_vs_golden(integer_mine):
         diffs = engine_vs_ref(Golden("det_integer_mine_%s_s0" % d), mine, res, i, sptf=(d == "SPTFDispatcher"))
         assert not diffs, "%s: %s" % (d, diffs[:5])
     assert (res.summary_np()["err"] == 0).all()
+
+
+def test_ragged_mine_live_distribution_vs_reference(ragged_mine):
+    """Live RNG on the ragged mine, whose own road_event_params make road repairs and detours frequent (~10-20 per
+    episode instead of ~1 on north_pit): per-instance reported tons, truck events, jams, road repairs and truck
+    breakdowns must agree in distribution with 64 runs of the unmodified reference per dispatcher
+    (tests/golden/make_golden_dist_edge.py).  Welch z-test on the means, |z| < 4 (20 checks)."""
+    import os
+    from helpers import GOLDEN
+    ref = np.load(os.path.join(GOLDEN, "live_distribution_ragged_mine.npz"))
+    names = ["SQDispatcher", "SPTFDispatcher", "NearestDispatcher", "FixedGroupDispatcher"]
+    n = 2048
+    mine = _mine(ragged_mine, n * len(names))
+    mine.reset([d for d in names for _ in range(n)], seeds=np.tile(np.arange(n, dtype=np.uint64) + 77_000, len(names)),
+               rng_mode="philox")
+    s = mine.run().summary_np().reshape(len(names), n)
+    assert (s["err"] == 0).all()
+    for k, d in enumerate(names):
+        for field, key in (("reported_tons", "tons"), ("n_truck_events", "events"), ("n_jams", "jams"),
+                           ("n_road_repairs", "road_repairs"), ("n_truck_repairs", "breakdowns")):
+            a = s[k][field].astype(np.float64)
+            b = ref["%s_%s" % (d, key)]
+            z = (a.mean() - b.mean()) / np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+            print("%-22s %-13s engine %9.2f  reference %9.2f  z=%+.2f" % (d, key, a.mean(), b.mean(), z))
+            assert abs(z) < 4.0, "%s %s: engine mean %.2f vs reference %.2f (z=%.2f)" % (d, key, a.mean(), b.mean(), z)

@@ -241,6 +241,8 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
 int om_stats_reduce(OmHandle h, const OmSummary* summary, const int32_t* dispatcher,
                     double* stats_out, void* stream);
 
+#define OM_STEP_AUTO_RESET 1
+
 /* Batched gym-style step (replaces RLDispatcher._step + Mine.start_rl + preprocess_observation:
  * rl_dispatch.py:58-123,194-509, mine.py:397-476, utils/feature_processing.py:3-75).  Instances reset with
  * OM_DISP_EXTERNAL pause at every dispatch decision.  One call = apply `actions[n]` to instance n's pending
@@ -258,7 +260,14 @@ typedef struct OmStepIO {
   int32_t* sug_action;    /* [N] teacher's decision (info["sug_action"]), -1 when done / no teacher */
   double* info;           /* [N * 4] produce_tons, time, delta_time, reserved */
   int32_t teacher;        /* OM_DISP_* of the teacher (0..6), or -1 */
-  int32_t reserved;
+  int32_t flags;          /* OM_STEP_* */
+  /* per-env automatic reset (OM_STEP_AUTO_RESET), the behaviour of gym.vector.AsyncVectorEnv that the reference's
+   * trainers run under (test/cleanrl/ppo_single_net.py:593): on the step an episode ends the env reports the final
+   * reward and done = 1, then starts a fresh episode with seed += seed_stride in the same call and returns THAT
+   * episode's first observation / pending decision; the terminal observation goes to final_obs. */
+  float* final_obs;            /* [N * obs_dim] or NULL: rows are written on the step an episode ends */
+  uint64_t seed_stride;        /* added to an instance's seed at every automatic reset */
+  int64_t* episode_totals;     /* [N * 3] or NULL: finished episodes, their truck events, their decisions (accumulated) */
 } OmStepIO;
 int om_obs_dim(OmHandle h, int32_t* dim);
 int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* stream);

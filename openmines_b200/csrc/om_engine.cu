@@ -61,7 +61,8 @@ __global__ void om_reset_kernel(DevCfg c, OmStateLayout ly, unsigned char* state
                                 const int32_t* dispatcher, long long n) {
   long long inst = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (inst >= n) return;
-  om_init_state(state + (size_t)inst * ly.total_bytes, c, ly, threadIdx.x & 31, seeds[inst], dispatcher[inst]);
+  unsigned char* blob = state + (size_t)inst * ly.total_bytes;
+  om_init_state(blob, blob, ly.total_bytes, c, ly, threadIdx.x & 31, seeds[inst], dispatcher[inst]);
 }
 
 // Work-queue order of om_run: instance ids grouped by dispatcher id (counting sort, one CTA).  The episode kernel is

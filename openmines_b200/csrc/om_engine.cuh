@@ -175,6 +175,9 @@ struct PySum {
   }
 };
 
+__device__ __forceinline__ void om_init_state(unsigned char* sm, unsigned char* cold, uint32_t sm_bytes, const DevCfg& c,
+                                              const OmStateLayout& ly, int lane, uint64_t seed, int dispatcher);
+
 template <int RNG, bool TRACE, bool RL, bool SPLIT = false>
 struct Sim {
   unsigned char* sm;     // shared-memory image of the blob (SPLIT: only its first ly.hot_bytes)
@@ -1539,11 +1542,13 @@ struct Sim {
       }
       h->pending_truck = -1; h->pending_kind = -1;
     }
+    bool fresh = false;       // true once this call has auto-reset the env: the finished episode's outputs stay
+  L_RUN:
     run(p.until);
     pt = h->pending_truck; pk = h->pending_kind;
     const bool failed = (err != OM_IERR_NONE && err != OM_IERR_TRACE_OVERFLOW);
+    float* ob = io.obs + (size_t)inst * p.obs_dim;
     if (pt >= 0 && !failed) {
-      float* ob = io.obs + (size_t)inst * p.obs_dim;
       double delta_time = now - rl_last;
       rl_observation(pt, pk, ob);
       double reward = rl_reward(false);
@@ -1558,12 +1563,14 @@ struct Sim {
       }
       rl_last = now;
       if (lane == 0) {
-        if (io.reward) io.reward[inst] = reward;
-        if (io.done) io.done[inst] = 0;
+        if (!fresh) {
+          if (io.reward) io.reward[inst] = reward;
+          if (io.done) io.done[inst] = 0;
+          if (io.info) { io.info[inst * 4 + 0] = reported_tons; io.info[inst * 4 + 1] = now; io.info[inst * 4 + 2] = delta_time; io.info[inst * 4 + 3] = 0.0; }
+        }
         if (io.order_kind) io.order_kind[inst] = pk;
         if (io.truck) io.truck[inst] = pt;
         if (io.sug_action) io.sug_action[inst] = sug;
-        if (io.info) { io.info[inst * 4 + 0] = reported_tons; io.info[inst * 4 + 1] = now; io.info[inst * 4 + 2] = delta_time; io.info[inst * 4 + 3] = 0.0; }
         h->rl_steps++;
       }
     } else {
@@ -1572,15 +1579,38 @@ struct Sim {
       now = p.until;
       double reward = rl_reward(true);
       rl_last = now;
+      const bool again = (io.flags & OM_STEP_AUTO_RESET) && !fresh && !failed;
       if (lane == 0) {
-        if (io.reward) io.reward[inst] = reward;
-        if (io.done) io.done[inst] = 1;
+        if (!fresh) {
+          if (io.reward) io.reward[inst] = reward;
+          if (io.done) io.done[inst] = 1;
+          if (io.info) { io.info[inst * 4 + 0] = reported_tons; io.info[inst * 4 + 1] = now; io.info[inst * 4 + 2] = delta_time; io.info[inst * 4 + 3] = 0.0; }
+        }
         if (io.order_kind) io.order_kind[inst] = -1;
         if (io.truck) io.truck[inst] = -1;
         if (io.sug_action) io.sug_action[inst] = -1;
-        if (io.info) { io.info[inst * 4 + 0] = reported_tons; io.info[inst * 4 + 1] = now; io.info[inst * 4 + 2] = delta_time; io.info[inst * 4 + 3] = 0.0; }
-        h->finished = 1;
+        if (io.episode_totals) {
+          io.episode_totals[inst * 3 + 0] += 1;
+          io.episode_totals[inst * 3 + 1] += (long long)n_events;
+          io.episode_totals[inst * 3 + 2] += (long long)n_decisions;
+        }
+        h->finished = again ? 0u : 1u;
         h->rl_steps++;
+      }
+      if (again) {
+        // same-step automatic reset: keep the terminal observation, start the next episode of this env and hand out its
+        // first decision (the outputs of the finished episode -- reward, done, info -- are already written)
+        if (io.final_obs) {
+          float* fo = io.final_obs + (size_t)inst * p.obs_dim;
+#pragma unroll 1
+          for (int q = lane; q < p.obs_dim; q += 32) fo[q] = ob[q];
+        }
+        const uint64_t seed2 = (((uint64_t)k1 << 32) | (uint64_t)k0) + io.seed_stride;
+        __syncwarp();
+        om_init_state(sm, cold, SPLIT ? ly.hot_bytes : ly.total_bytes, c, ly, lane, seed2, OM_DISP_EXTERNAL);
+        load_hdr(p);
+        fresh = true;
+        goto L_RUN;
       }
     }
     __syncwarp();
@@ -1599,13 +1629,17 @@ struct Sim {
 // Initial state of one instance at t=0 (Mine.__init__/Truck.__init__/registration order of mine.py:357-389):
 // the monitor block's Initialize events are URGENT at 0 with the smallest eids, then one URGENT
 // Initialize(run) per truck in index order.
-__device__ __forceinline__ void om_init_state(unsigned char* sm, const DevCfg& c, const OmStateLayout& ly, int lane,
-                                              uint64_t seed, int dispatcher) {
+// `sm` addresses the first `sm_bytes` of the blob (the whole blob for the reset kernel, the staged part inside the step
+// kernel), `cold` the blob in HBM for everything behind it (== sm when nothing is behind).
+__device__ __forceinline__ void om_init_state(unsigned char* sm, unsigned char* cold, uint32_t sm_bytes, const DevCfg& c,
+                                              const OmStateLayout& ly, int lane, uint64_t seed, int dispatcher) {
   const double inf = om_inf();
-  unsigned char* cold = sm;   // the reset kernel writes the blob in place
+  (void)inf;
   // zero everything first
   #pragma unroll 1
-  for (uint32_t o = lane * 8; o < ly.total_bytes; o += 256) *(unsigned long long*)(sm + o) = 0ull;
+  for (uint32_t o = lane * 8; o < sm_bytes; o += 256) *(unsigned long long*)(sm + o) = 0ull;
+  #pragma unroll 1
+  for (uint32_t o = sm_bytes + lane * 8; o < ly.total_bytes; o += 256) *(unsigned long long*)(cold + o) = 0ull;
   __syncwarp();
   #pragma unroll 1
   for (int i = lane; i < c.T; i += 32) {

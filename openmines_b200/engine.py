@@ -32,7 +32,11 @@ class OmStepIOStruct(ctypes.Structure):
     _fields_ = [("actions", ctypes.c_void_p), ("obs", ctypes.c_void_p), ("reward", ctypes.c_void_p),
                 ("done", ctypes.c_void_p), ("order_kind", ctypes.c_void_p), ("truck", ctypes.c_void_p),
                 ("sug_action", ctypes.c_void_p), ("info", ctypes.c_void_p), ("teacher", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("flags", ctypes.c_int32), ("final_obs", ctypes.c_void_p), ("seed_stride", ctypes.c_uint64),
+                ("episode_totals", ctypes.c_void_p)]
+
+
+OM_STEP_AUTO_RESET = 1
 
 
 _LAYOUT_FIELDS = ["total_bytes", "hdr", "t_time", "t_load", "t_jstart", "t_prejam", "t_lastbrk", "t_repair",
@@ -235,9 +239,10 @@ class BatchedMine:
         self._ck(self.lib.om_obs_dim(self.h, ctypes.byref(d)))
         return d.value
 
-    def step(self, actions, io, until=None, teacher=-1):
+    def step(self, actions, io, until=None, teacher=-1, auto_reset=False, seed_stride=0):
         """One batched env step through ``om_step``; ``io`` is a dict of preallocated device tensors
-        (obs, reward, done, order_kind, truck, sug_action, info), ``actions`` an int32 device tensor or None."""
+        (obs, reward, done, order_kind, truck, sug_action, info; with ``auto_reset`` also final_obs and
+        episode_totals int64[N, 3]), ``actions`` an int32 device tensor or None."""
         s = OmStepIOStruct()
         ptr = lambda t: t.data_ptr() if t is not None else None
         s.actions = ptr(actions)
@@ -245,6 +250,9 @@ class BatchedMine:
         s.order_kind, s.truck = ptr(io.get("order_kind")), ptr(io.get("truck"))
         s.sug_action, s.info = ptr(io.get("sug_action")), ptr(io.get("info"))
         s.teacher = int(teacher)
+        s.flags = OM_STEP_AUTO_RESET if auto_reset else 0
+        s.final_obs, s.episode_totals = ptr(io.get("final_obs")), ptr(io.get("episode_totals"))
+        s.seed_stride = int(seed_stride)
         until = float(self.sim_time if until is None else until)
         self._ck(self.lib.om_step(self.h, until, ctypes.c_void_p(self.state.data_ptr()), ctypes.byref(s), self._stream()))
 

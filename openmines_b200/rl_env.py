@@ -36,6 +36,10 @@ class BatchedMineEnv:
             "sug_action": torch.full((n,), -1, dtype=torch.int32, device=dev),
             "info": torch.zeros((n, 4), dtype=torch.float64, device=dev),
         }
+        if auto_reset:
+            # per-env automatic reset on the device (gym.vector semantics, see OmStepIO in include/openmines_b200.h)
+            self.io["final_obs"] = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=dev)
+            self.io["episode_totals"] = torch.zeros((n, 3), dtype=torch.int64, device=dev)
         self._episode = 0
         self._seeds = None
         self._tapes = None
@@ -58,23 +62,34 @@ class BatchedMineEnv:
         self._seeds, self._tapes = seeds, tapes
         self._episode += 1
         self.mine.reset("external", seeds=seeds, rng_mode=self.rng_mode, tapes=tapes)
-        self.mine.step(None, self.io, teacher=self.teacher)
+        if self.auto_reset:
+            self.io["episode_totals"].zero_()
+        self._step(None)
         return self.io["obs"], self._info()
 
+    def _step(self, a):
+        self.mine.step(a, self.io, teacher=self.teacher, auto_reset=self.auto_reset, seed_stride=self.num_envs)
+
     def step(self, actions):
-        """actions: int tensor [N] on the env's device (int64 or int32)."""
+        """actions: int tensor [N] on the env's device (int64 or int32).
+
+        With ``auto_reset=True`` every env restarts by itself, inside the same ``om_step`` call, on the step its
+        episode ends (the behaviour of ``gym.vector.AsyncVectorEnv`` that the reference's trainers run under,
+        test/cleanrl/ppo_single_net.py:593): that step returns the final reward and ``terminated=True`` together with
+        the FIRST observation of the next episode; ``info["final_observation"]`` holds the terminal observation rows and
+        ``info["episode_totals"]`` the per-env counts of finished episodes / their truck events / their decisions.
+        The next episode's seed is the previous one + num_envs.  Without it, finished envs idle (reward 0,
+        ``terminated=True``) until the caller resets the batch."""
         torch = self.torch
         a = actions.to(device=self.mine.device, dtype=torch.int32).contiguous()
-        self.mine.step(a, self.io, teacher=self.teacher)
+        self._step(a)
         terminated = self.io["done"].bool()
         truncated = torch.zeros_like(terminated)
-        if self.auto_reset and bool(terminated.all()):
-            # every env of one config finishes at the same simulated time but not at the same step count;
-            # restart the whole batch once all are done (done envs idle with reward 0 until then)
-            obs_final, rew, info = self.io["obs"].clone(), self.io["reward"].clone(), self._info()
-            self.reset()
-            return self.io["obs"], rew, terminated, truncated, dict(info, final_observation=obs_final)
-        return self.io["obs"], self.io["reward"], terminated, truncated, self._info()
+        info = self._info()
+        if self.auto_reset:
+            info["final_observation"] = self.io["final_obs"]
+            info["episode_totals"] = self.io["episode_totals"]
+        return self.io["obs"], self.io["reward"], terminated, truncated, info
 
     def capture_rollout_step(self, policy, sample=None, warmup=3):
         """Capture ONE rollout iteration -- policy forward on the current observation, action sampling, ``om_step``
@@ -95,7 +110,7 @@ class BatchedMineEnv:
         def body():
             act = sample(policy(self.io["obs"]))
             self.last_actions.copy_(act)
-            self.mine.step(self.last_actions, self.io, teacher=self.teacher)
+            self._step(self.last_actions)
 
         side = torch.cuda.Stream(device=self.mine.device)
         side.wait_stream(torch.cuda.current_stream(self.mine.device))

@@ -159,3 +159,51 @@ def test_graphed_rollout_matches_eager(north_pit):
         outs.append((torch.stack(rewards).cpu(), env.io["obs"].clone().cpu(), env.io["info"].clone().cpu()))
         env.close()
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
+def test_per_env_auto_reset(north_pit):
+    """auto_reset=True: on the step an episode ends the env reports the final reward / terminated, restarts itself in the
+    same om_step call with seed + num_envs and returns the next episode's first observation; the second episode must be
+    identical to a fresh env reset with that seed, and the terminal observation lands in info['final_observation']."""
+    import torch
+    from openmines_b200.rl_env import BatchedMineEnv
+    n = 8
+    cfg = dict(north_pit)
+    cfg["sim_time"] = 40
+    lin = torch.nn.Linear(194, 5).cuda()
+    act_of = lambda o: lin(o).argmax(dim=1)
+
+    def rollout(env, seed, steps):
+        obs, info = env.reset(seed=seed)
+        log = []
+        with torch.no_grad():
+            for _ in range(steps):
+                prev = obs.clone()
+                obs, rew, term, trunc, info = env.step(act_of(obs))
+                log.append((prev.cpu(), rew.clone().cpu(), term.clone().cpu(), obs.clone().cpu(),
+                            info["order_kind"].clone().cpu(), info["sug_action"].clone().cpu()))
+        return log
+
+    auto = BatchedMineEnv(cfg, n, rng_mode="philox", auto_reset=True)
+    a = rollout(auto, 100, 260)
+    totals = auto.io["episode_totals"].cpu().numpy()
+    final_obs = auto.io["final_obs"].cpu()
+    assert (totals[:, 0] >= 1).all() and (totals[:, 1] > 0).all() and (totals[:, 2] > 0).all()
+    # env e: steps of its first episode, then its second episode must replay a fresh env seeded 100 + n + e
+    plain = BatchedMineEnv(cfg, n, rng_mode="philox")
+    b = rollout(plain, 100, 260)            # first episodes (no auto reset)
+    c = rollout(plain, 100 + n, 260)        # what the second episodes must look like
+    for e in range(n):
+        t_end = next(k for k, rec in enumerate(a) if bool(rec[2][e]))
+        for k in range(t_end + 1):          # first episode identical incl. the final reward
+            assert torch.equal(a[k][1][e], b[k][1][e]) and bool(a[k][2][e]) == bool(b[k][2][e])
+        for k in range(t_end):
+            assert torch.equal(a[k][3][e], b[k][3][e])
+        assert torch.equal(a[t_end][3][e], c[0][0][e])                 # obs returned with done = first obs of episode 2
+        assert int(a[t_end][4][e]) == 0                                 # pending decision of the new episode: an init order
+        if totals[e, 0] == 1:
+            assert torch.equal(final_obs[e], b[t_end][3][e])            # terminal observation of episode 1
+        m = min(len(a) - t_end - 1, 40)
+        for k in range(m):                  # second episode == fresh env with the next seed
+            assert torch.equal(a[t_end + 1 + k][1][e], c[k][1][e]), (e, k)
+            assert torch.equal(a[t_end + 1 + k][3][e], c[k][3][e]), (e, k)

@@ -13,5 +13,5 @@ import sys,json
 d=json.loads(sys.stdin.read().strip().split('\n')[-1]); print('c2', d['config']['launch'],'value %.4e'%d['value'],'kernel_ms %.2f'%d['roofline']['kernel_ms'], 'errs', d['instance_errors'])"
 timeout -k 10 300 python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
 import sys,json
-d=json.loads(sys.stdin.read().strip().split('\n')[-1]); print('c4 value %.4e'%d['value'],'decisions/s %.4e'%d['decisions_per_s'],'ms/step %.1f'%d['ms_per_step'],'kernel_ms %.4f'%d['roofline']['kernel_ms'],'frac %.3f'%d['roofline']['frac'])"
+d=json.loads(sys.stdin.read().strip().split('\n')[-1]); print('c4', d['config']['launch'], d['config']['state_bytes_per_instance'], 'value %.4e'%d['value'],'decisions/s %.4e'%d['decisions_per_s'],'ms/step %.1f'%d['ms_per_step'],'kernel_ms %.4f'%d['roofline']['kernel_ms'],'frac %.3f'%d['roofline']['frac'])"
 fi

@@ -1,7 +1,8 @@
 // Device-side engine: one warp simulates one mine instance.
 //
-// The per-instance state is a structure-of-arrays blob (layout: OmStateLayout) that lives in HBM
-// between calls and is staged into shared memory for the duration of om_run.  All "scalar" DES
+// The per-instance state is one blob (layout: OmStateLayout; 16-byte pending entries, per-truck and
+// per-unit records, a few structure-of-arrays sections -- see the accessor table in Sim) that lives in HBM
+// between calls and is staged into shared memory by a TMA bulk copy for the duration of om_run.  All "scalar" DES
 // logic (one truck's transition) is executed warp-uniformly -- every lane computes the same values
 // and performs the same shared-memory stores (same value, same address), so no intra-warp
 // synchronisation is needed around it; lane-parallel phases (next-event reduction, status counts,
@@ -12,6 +13,10 @@
 // (simpy.core.Environment.schedule; call sites listed in SURVEY.md section 2 row 10).  Pending
 // entries: one per truck (a truck waits on exactly one thing), one pending Release per
 // shovel/dumper, one monitor-block entry.
+//
+// The kernels built from this file are bound by instruction fetch and dependent-instruction latency, not by memory
+// (DESIGN.md section 4): loops are deliberately rolled, hot continuations are laid out in execution order, force-inlined
+// helpers have one call site, and nothing that a north_pit episode never executes is compiled into its hot loop.
 #pragma once
 #include <stdint.h>
 #include <math.h>

@@ -207,3 +207,42 @@ def test_per_env_auto_reset(north_pit):
         for k in range(m):                  # second episode == fresh env with the next seed
             assert torch.equal(a[t_end + 1 + k][1][e], c[k][1][e]), (e, k)
             assert torch.equal(a[t_end + 1 + k][3][e], c[k][3][e]), (e, k)
+
+
+@pytest.mark.parametrize("which", ["ragged", "scaled"])
+def test_rl_env_on_other_mines(which, ragged_mine):
+    """The batched env on mines with L != D (generalised observation layout) and on the 500-truck mine (SPLIT step
+    kernel, slot cache), with per-env auto reset: finite observations, valid pending decisions, teacher suggestions in
+    range, episodes finish and restart, no engine errors."""
+    import torch
+    from openmines_b200.rl_env import BatchedMineEnv
+    if which == "ragged":
+        cfg, n, jam = dict(ragged_mine), 64, 64
+        cfg["sim_time"] = 30
+    else:
+        from openmines_b200.synthetic import scaled_mine
+        cfg, n, jam = scaled_mine(sim_time=12), 16, 512
+    env = BatchedMineEnv(cfg, n, rng_mode="philox", auto_reset=True, jam_capacity=jam)
+    L, D = env.mine.pc.L, env.mine.pc.D
+    assert env.obs_dim == 6 + (1 + L + D) + 2 + 3 * max(L, D) + 2 * env.mine.pc.R + 5 * (L + D)
+    obs, info = env.reset(seed=9)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    steps = 1500 if which == "ragged" else 2500
+    for _ in range(steps):
+        kind = info["order_kind"]
+        nmax = torch.where(kind == 1, torch.tensor(D, device=kind.device), torch.tensor(L, device=kind.device))
+        a = (torch.rand(n, generator=g).to(kind.device) * nmax).long().clamp_(max=max(L, D) - 1)
+        obs, rew, term, trunc, info = env.step(a)
+        sug = info["sug_action"]
+        assert bool(((sug >= 0) & (sug < nmax_next(info, L, D))).all())
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    hdr = env.mine.headers()
+    assert (hdr["err"] == 0).all()
+    totals = env.io["episode_totals"].cpu().numpy()
+    assert (totals[:, 0] >= 1).all(), totals[:, 0]
+
+
+def nmax_next(info, L, D):
+    import torch
+    kind = info["order_kind"]
+    return torch.where(kind == 1, torch.tensor(D, device=kind.device), torch.tensor(L, device=kind.device))

@@ -111,3 +111,18 @@ def test_experiment_drivers(north_pit):
     assert sum(t["count"] for t in c["charging_site"]["trucks"]) == 40
     res = ex.scene_based_fleet_ablation(cfg, 20, 20, dispatchers=["NaiveDispatcher", "SQDispatcher"], n_seeds=8)
     assert res["SQDispatcher"]["fleet_sizes"] == [20] and res["SQDispatcher"]["productions"][0] > res["NaiveDispatcher"]["productions"][0]
+
+
+def test_result_json_tape_ragged_mine(ragged_mine):
+    """TickGenerator parity on the ragged mine (L != D, 1..9 units per site, 130 trucks, frequent road repairs): tape
+    replay of the reference's live SQ run (tests/golden/make_golden_ticks_edge.py)."""
+    import openmines_b200 as om
+    from openmines_b200.ticker import TickRecorder
+    ref = _load("ticks_ragged_mine_SQDispatcher_live_s5.json.gz")
+    z = np.load(os.path.join(GOLDEN, "live_ragged_mine_SQDispatcher_s5.npz"))
+    mine = om.BatchedMine(ragged_mine, 1)
+    mine.reset("SQDispatcher", rng_mode="tape", tapes=[(z["tape_sites"], z["tape_values"])])
+    res = mine.run(trace_capacity=8192, site_ticks=True, unit_ticks=True, order_capacity=2048)
+    ticks = TickRecorder(mine, res, "SQDispatcher").ticks(0)
+    problems = _compare(ticks, ref)
+    assert not problems, problems[:6]

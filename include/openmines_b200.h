@@ -242,6 +242,8 @@ int om_stats_reduce(OmHandle h, const OmSummary* summary, const int32_t* dispatc
                     double* stats_out, void* stream);
 
 #define OM_STEP_AUTO_RESET 1
+#define OM_STEP_SPARSE_REWARD 2 /* reward_mode="sparse" (rl_dispatch.py:186-192): 0 at every decision; the final step carries the
+                                   dense reward of Mine.start_rl (mine.py:456-459) with last_production never updated */
 
 /* Batched gym-style step (replaces RLDispatcher._step + Mine.start_rl + preprocess_observation:
  * rl_dispatch.py:58-123,194-509, mine.py:397-476, utils/feature_processing.py:3-75).  Instances reset with

@@ -1401,8 +1401,12 @@ struct Sim {
   // RL step surface: dense reward (rl_dispatch.py:194-308), observation float32[obs_dim]
   // (rl_dispatch.py:309-509 + utils/feature_processing.py:3-75), teacher suggestion (:169-184)
   // ---------------------------------------------------------------------------------------------
-  __device__ __forceinline__ double rl_reward(bool final_step) {
+  __device__ __forceinline__ double rl_reward(bool final_step, bool sparse = false) {
     const int T = c.T;
+    if (sparse && !final_step) {          // the reward function is not evaluated: only the window restarts
+      acc_wait = acc_shovel = acc_dumper = acc_move = acc_jam = 0.0;
+      return 0.0;
+    }
     double w = 0.0, sh = 0.0, du = 0.0, mv = 0.0, jm = 0.0;
 #pragma unroll 1
     for (int i = lane; i < T; i += 32) {           // intervals still open at this decision
@@ -1556,7 +1560,7 @@ struct Sim {
     if (pt >= 0 && !failed) {
       double delta_time = now - rl_last;
       rl_observation(pt, pk, ob);
-      double reward = rl_reward(false);
+      double reward = rl_reward(false, (io.flags & OM_STEP_SPARSE_REWARD) != 0);
       int sug = -1;
       if (io.teacher >= 0 && io.teacher != OM_DISP_RANDOM) {
         int saved_disp = disp;

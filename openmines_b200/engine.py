@@ -37,6 +37,7 @@ class OmStepIOStruct(ctypes.Structure):
 
 
 OM_STEP_AUTO_RESET = 1
+OM_STEP_SPARSE_REWARD = 2
 
 
 _LAYOUT_FIELDS = ["total_bytes", "hdr", "t_time", "t_load", "t_jstart", "t_prejam", "t_lastbrk", "t_repair",
@@ -239,7 +240,7 @@ class BatchedMine:
         self._ck(self.lib.om_obs_dim(self.h, ctypes.byref(d)))
         return d.value
 
-    def step(self, actions, io, until=None, teacher=-1, auto_reset=False, seed_stride=0):
+    def step(self, actions, io, until=None, teacher=-1, auto_reset=False, seed_stride=0, sparse_reward=False):
         """One batched env step through ``om_step``; ``io`` is a dict of preallocated device tensors
         (obs, reward, done, order_kind, truck, sug_action, info; with ``auto_reset`` also final_obs and
         episode_totals int64[N, 3]), ``actions`` an int32 device tensor or None."""
@@ -250,7 +251,7 @@ class BatchedMine:
         s.order_kind, s.truck = ptr(io.get("order_kind")), ptr(io.get("truck"))
         s.sug_action, s.info = ptr(io.get("sug_action")), ptr(io.get("info"))
         s.teacher = int(teacher)
-        s.flags = OM_STEP_AUTO_RESET if auto_reset else 0
+        s.flags = (OM_STEP_AUTO_RESET if auto_reset else 0) | (OM_STEP_SPARSE_REWARD if sparse_reward else 0)
         s.final_obs, s.episode_totals = ptr(io.get("final_obs")), ptr(io.get("episode_totals"))
         s.seed_stride = int(seed_stride)
         until = float(self.sim_time if until is None else until)

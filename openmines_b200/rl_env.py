@@ -16,7 +16,7 @@ from .engine import BatchedMine, DISPATCHER_IDS
 
 class BatchedMineEnv:
     def __init__(self, config, num_envs, device=0, rng_mode="philox", sug_dispatcher="ShortestTripDispatcher",
-                 auto_reset=False, jam_capacity=64):
+                 auto_reset=False, jam_capacity=64, reward_mode="dense"):
         import torch
         self.torch = torch
         self.mine = BatchedMine(config, num_envs, device=device, jam_capacity=jam_capacity, rl_surface=True)
@@ -24,6 +24,9 @@ class BatchedMineEnv:
         self.rng_mode = rng_mode
         self.teacher = DISPATCHER_IDS[sug_dispatcher] if sug_dispatcher else -1
         self.auto_reset = auto_reset
+        if reward_mode not in ("dense", "sparse"):
+            raise ValueError("Unknown reward mode: %s" % reward_mode)          # rl_dispatch.py:72
+        self.reward_mode = reward_mode                     # GymMineEnv(reward_mode=...), mine_env.py:55
         self.obs_dim = self.mine.obs_dim()
         self.n_actions = max(self.mine.pc.L, self.mine.pc.D)          # spaces.Discrete(max(L, D)), mine_env.py:217-221
         dev, n = self.mine.device, self.num_envs
@@ -68,7 +71,8 @@ class BatchedMineEnv:
         return self.io["obs"], self._info()
 
     def _step(self, a):
-        self.mine.step(a, self.io, teacher=self.teacher, auto_reset=self.auto_reset, seed_stride=self.num_envs)
+        self.mine.step(a, self.io, teacher=self.teacher, auto_reset=self.auto_reset, seed_stride=self.num_envs,
+                       sparse_reward=(self.reward_mode == "sparse"))
 
     def step(self, actions):
         """actions: int tensor [N] on the env's device (int64 or int32).

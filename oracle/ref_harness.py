@@ -496,7 +496,7 @@ def load_config(path):
 # RL surface of the unmodified reference (RLDispatcher + Mine.start_rl + preprocess_observation)
 # ----------------------------------------------------------------------------------------
 def run_reference_rl(config, policy, mode="det", seed=0, tape=None, teacher="ShortestTripDispatcher",
-                     sim_time=None, ref_root=REF_ROOT_DEFAULT):
+                     sim_time=None, ref_root=REF_ROOT_DEFAULT, reward_mode="dense"):
     """Drive the reference's own RL loop: ``prepare_env`` (utils/rl_env.py:29-104) runs in a thread exactly
     as ``ThreadMineEnv.reset`` starts it (mine_env.py:302-316); this thread plays the agent.
     policy(step_index, kind_code, obs194, n_choices) -> int.  Returns the per-step log."""
@@ -521,7 +521,7 @@ def run_reference_rl(config, policy, mode="det", seed=0, tape=None, teacher="Sho
 
     def target():
         try:
-            rl_env.prepare_env(obs_q, act_q, cfg, "dense", cfg["sim_time"], False, False, None)
+            rl_env.prepare_env(obs_q, act_q, cfg, reward_mode, cfg["sim_time"], False, False, None)
         except BaseException as e:   # surface crashes of the simulation thread
             err["e"] = e
             obs_q.put(None)

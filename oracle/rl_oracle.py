@@ -17,8 +17,9 @@ KINDS = {"init": 0, "haul": 1, "back": 2}
 
 
 class RlRecorder:
-    def __init__(self, oracle, policy, teacher="ShortestTripDispatcher"):
+    def __init__(self, oracle, policy, teacher="ShortestTripDispatcher", reward_mode="dense"):
         self.o = oracle
+        self.reward_mode = reward_mode
         self.policy = policy          # policy(step_index, kind_code, obs194, n_choices) -> int
         self.teacher = teacher
         # per truck, per record type, in creation order: the reference concatenates each truck's
@@ -146,7 +147,9 @@ class RlRecorder:
         o = self.o
         obs, dt = self.observation(kind, truck)
         self.current_obs = obs
-        reward = self.reward_dense(final=False)
+        # sparse mode (rl_dispatch.py:69-70,186-192): 0 at every decision -- the dense function is not called, so
+        # last_production stays 0 until Mine.start_rl calls the dense function once at the end (mine.py:456-459)
+        reward = self.reward_dense(final=False) if self.reward_mode == "dense" else 0.0
         sug = o._decide(self.teacher, kind, truck) if self.teacher else -1
         n = o.D if kind == "haul" else o.L
         action = int(self.policy(len(self.log), KINDS[kind], obs, n))
@@ -166,12 +169,13 @@ class RlRecorder:
                          "produce_tons": float(o.mine_produce_tons), "action": -1})
 
 
-def run_rl_oracle(config, policy, mode="det", seed=0, tape=None, teacher="ShortestTripDispatcher", sim_time=None):
+def run_rl_oracle(config, policy, mode="det", seed=0, tape=None, teacher="ShortestTripDispatcher", sim_time=None,
+                  reward_mode="dense"):
     cfg = dict(config)
     if sim_time is not None:
         cfg["sim_time"] = sim_time
     o = do.DesOracle(cfg, "external", mode, seed, tape)
-    o.rl = RlRecorder(o, policy, teacher)
+    o.rl = RlRecorder(o, policy, teacher, reward_mode)
     res = o.run()
     # env.run(until=T) leaves env.now == T (the stop event is processed at T)
     o.env._now = float(cfg["sim_time"])

@@ -40,6 +40,11 @@ def main():
         name = "rl_north_pit_mine_%s_s%d_%s_p%d.npz" % (mode, seed, teacher, pseed)
         save(os.path.join(HERE, name), log, tape, {"mode": mode, "seed": seed, "teacher": teacher, "policy_seed": pseed})
         print(name, len(log), sum(x["reward"] for x in log))
+    # sparse reward mode (rl_dispatch.py:186-192, mine.py:456-459)
+    log, tape = rh.run_reference_rl(cfg, ro.keyed_policy(4), "live", 23, teacher="ShortestTripDispatcher", reward_mode="sparse")
+    name = "rl_north_pit_mine_live_s23_ShortestTripDispatcher_p4_sparse.npz"
+    save(os.path.join(HERE, name), log, tape, {"mode": "live", "seed": 23, "teacher": "ShortestTripDispatcher", "policy_seed": 4})
+    print(name, len(log), sum(x["reward"] for x in log), log[-1]["reward"])
 
 
 if __name__ == "__main__":

@@ -63,16 +63,17 @@ def _compare(log, ref_obs, ref_reward, ref_kind, ref_sug, ref_done, ref_action):
 
 
 def test_rl_step_vs_reference_goldens(north_pit):
-    """det + two tape replays of the reference's own RL loop (ShortestTrip and SQ teachers)."""
+    """det + tape replays of the reference's own RL loop (ShortestTrip and SQ teachers; dense and sparse reward modes)."""
     import openmines_b200 as om
     from openmines_b200.rl_env import BatchedMineEnv
     from oracle import rl_oracle as ro
     names = ["rl_north_pit_mine_det_s0_ShortestTripDispatcher_p1", "rl_north_pit_mine_live_s21_ShortestTripDispatcher_p2",
-             "rl_north_pit_mine_live_s22_SQDispatcher_p3"]
+             "rl_north_pit_mine_live_s22_SQDispatcher_p3", "rl_north_pit_mine_live_s23_ShortestTripDispatcher_p4_sparse"]
     for name in names:
         z = np.load(os.path.join(GOLDEN, name + ".npz"))
         mode = "det" if str(z["mode"]) == "det" else "tape"
-        env = BatchedMineEnv(north_pit, 1, rng_mode=mode, sug_dispatcher=str(z["teacher"]))
+        env = BatchedMineEnv(north_pit, 1, rng_mode=mode, sug_dispatcher=str(z["teacher"]),
+                             reward_mode="sparse" if name.endswith("_sparse") else "dense")
         assert env.obs_dim == 194
         pol = {"fn": ro.keyed_policy(int(z["policy_seed"])), "seed": int(z["seed"]),
                "tape": (z["tape_sites"], z["tape_values"])}

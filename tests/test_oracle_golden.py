@@ -160,7 +160,8 @@ def test_oracle_sq_keyerror_is_reported(short_mine):
 
 @pytest.mark.parametrize("name", ["rl_north_pit_mine_det_s0_ShortestTripDispatcher_p1",
                                   "rl_north_pit_mine_live_s21_ShortestTripDispatcher_p2",
-                                  "rl_north_pit_mine_live_s22_SQDispatcher_p3"])
+                                  "rl_north_pit_mine_live_s22_SQDispatcher_p3",
+                                  "rl_north_pit_mine_live_s23_ShortestTripDispatcher_p4_sparse"])
 def test_rl_oracle_matches_reference_golden(name, north_pit):
     """The RL restatement (observation float32[194], dense reward, teacher suggestion, final step) is
     bit-identical to the reference's RLDispatcher / start_rl / preprocess_observation."""
@@ -169,11 +170,12 @@ def test_rl_oracle_matches_reference_golden(name, north_pit):
     from oracle import rl_oracle as ro
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     mode, seed, teacher, pseed = str(z["mode"]), int(z["seed"]), str(z["teacher"]), int(z["policy_seed"])
+    rmode = "sparse" if name.endswith("_sparse") else "dense"
     if mode == "live":   # replay the reference's own draws
         r = ro.run_rl_oracle(north_pit, ro.keyed_policy(pseed), "replay", tape=(z["tape_sites"], z["tape_values"]),
-                             teacher=teacher)
+                             teacher=teacher, reward_mode=rmode)
     else:
-        r = ro.run_rl_oracle(north_pit, ro.keyed_policy(pseed), mode, seed=seed, teacher=teacher)
+        r = ro.run_rl_oracle(north_pit, ro.keyed_policy(pseed), mode, seed=seed, teacher=teacher, reward_mode=rmode)
     log = r.rl_log
     assert len(log) == len(z["reward"])
     assert np.array_equal(np.stack([x["obs"] for x in log]), z["obs"])

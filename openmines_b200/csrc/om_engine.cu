@@ -267,6 +267,10 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl) {
   ly.slot_cache = take(off, 16, (T + 31) / 32);
   ly.u_rel_key = take(off, 4, U);
   ly.s_qtotal = take(off, 2, NS); ly.s_coming = take(off, 2, NS);
+  if (T > 128) {   // big mines run SPLIT: shared-memory helpers that keep the per-minute / per-departure scans out of HBM
+    ly.t_road = take(off, 2, T);       // current road of every truck (0xFFFF: not on a road), refreshed every minute
+    ly.r_jamcnt = take(off, 2, R);     // stored jams per road
+  }
   ly.hot_bytes = (off + 15u) & ~15u;
   off = ly.hot_bytes;
   // ---- cold part (truck records, jam pool): in shared memory too unless the engine runs split ----

@@ -747,8 +747,9 @@ struct Sim {
     double pre = 0.0;
     if (RNG != OM_RNG_DET && jam_count > 0) {
       int rid = road_id(cur, tgt);
+      const bool maybe = !(SPLIT && ly.r_jamcnt != 0) || ((const uint16_t*)(sm + ly.r_jamcnt))[rid] != 0;
       #pragma unroll 1
-      for (uint32_t base = 0; base < jam_count; base += 32) {
+      for (uint32_t base = 0; maybe && base < jam_count; base += 32) {
         uint32_t j = base + lane;
         bool hit = false;
         if (j < jam_count)
@@ -783,7 +784,15 @@ struct Sim {
   // jam pool
   // ---------------------------------------------------------------------------------------------
   __device__ __forceinline__ void jam_append(int rid, double pos, double end) {
+    // Big mines (SPLIT): per-road count of stored jams in shared memory, so a departure on a road without jams (most
+    // of them) does not scan the jam pool in HBM.  Exact after a compaction, an over-estimate (expired jams) between.
+    uint16_t* rjc = (SPLIT && ly.r_jamcnt != 0) ? (uint16_t*)(sm + ly.r_jamcnt) : nullptr;
     if (__builtin_expect(jam_count == (uint32_t)c.J, 0)) {   // drop expired entries, keep creation order
+      if (SPLIT && rjc != nullptr) {
+        #pragma unroll 1
+        for (int r = lane; r < c.R; r += 32) rjc[r] = 0;
+        __syncwarp();
+      }
       uint32_t w = 0;
       #pragma unroll 1
       for (uint32_t j = 0; j < jam_count; ++j) {
@@ -796,6 +805,7 @@ struct Sim {
             F64(j_pos, w) = F64(j_pos, j); if (RL) F64(j_start, w) = F64(j_start, j);
             F64(j_end, w) = F64(j_end, j); U16A(j_road, w) = U16A(j_road, j);
           }
+          if (SPLIT && rjc != nullptr) rjc[U16A(j_road, w)] = (uint16_t)(rjc[U16A(j_road, w)] + 1);
           w++;
         }
       }
@@ -804,6 +814,7 @@ struct Sim {
     if (jam_count == (uint32_t)c.J) { fail(OM_IERR_JAM_OVERFLOW); return; }
     F64(j_pos, jam_count) = pos; if (RL) F64(j_start, jam_count) = now; F64(j_end, jam_count) = end;
     U16A(j_road, jam_count) = (uint16_t)rid;
+    if (SPLIT && rjc != nullptr) rjc[rid] = (uint16_t)(rjc[rid] + 1);
     jam_count++;
   }
 
@@ -956,10 +967,15 @@ struct Sim {
     #pragma unroll 1
     for (int r = lane; r < R; r += 32) rcnt[r] = 0;
     __syncwarp();
+    // Big mines (SPLIT): the truck records live in HBM, so this pass also leaves every truck's current road in a
+    // shared-memory array for sample_jam_position(), which would otherwise re-read all records once per attempt.
+    uint16_t* troad = (SPLIT && ly.t_road != 0) ? (uint16_t*)(sm + ly.t_road) : nullptr;
     #pragma unroll 1
     for (int i = lane; i < T; i += 32) {
       int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
-      if (U8A(t_status, i) == ST_MOVING && cur != tgt) atomicAdd(&rcnt[road_id(cur, tgt)], 1u);
+      int rid = (U8A(t_status, i) == ST_MOVING && cur != tgt) ? road_id(cur, tgt) : -1;
+      if (rid >= 0) atomicAdd(&rcnt[rid], 1u);
+      if (SPLIT && troad != nullptr) troad[i] = (uint16_t)rid;
     }
     __syncwarp();
     // every candidate road flips its own keyed coin (road.py:179): lane l of the 64-road group g serves roads
@@ -1030,8 +1046,12 @@ struct Sim {
         int i = base + lane;
         bool on = false;
         if (i < T) {
-          int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
-          on = U8A(t_status, i) == ST_MOVING && cur != tgt && road_id(cur, tgt) == rid;
+          if (SPLIT && ly.t_road != 0) {
+            on = ((const uint16_t*)(sm + ly.t_road))[i] == (uint16_t)rid;      // written by jam_sampling() this minute
+          } else {
+            int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
+            on = U8A(t_status, i) == ST_MOVING && cur != tgt && road_id(cur, tgt) == rid;
+          }
         }
         unsigned m = __ballot_sync(OM_FULL, on);
         int cnt = __popc(m);

@@ -208,7 +208,9 @@ typedef struct OmStateLayout {
   uint32_t hot_bytes;          /* prefix of the blob the kernels stage in shared memory (== total_bytes unless split) */
   uint32_t hdr_bytes;          /* bytes of the per-instance header present in the blob */
   uint32_t slot_cache;         /* kernel-internal cache (16 B per 32 trucks); contents are meaningless between calls */
-  uint32_t t_road, r_jamcnt;   /* u16 [T] / u16 [R], big mines only (0 otherwise): current road per truck, stored jams per road */
+  uint32_t t_road, r_jamcnt;   /* u16 [T] / u16 [R], split layouts only (0 otherwise): current road per truck, stored jams per road */
+  uint32_t t_loc, t_lastbrk_hot; /* split layouts only (0 otherwise): {status, cur, tgt, -} u8[4] per truck and last breakdown time
+                                  f64 per truck in the hot part; t_status / t_cur / t_tgt / t_lastbrk then point here (strides 4 / 8) */
 } OmStateLayout;
 
 typedef struct OmEngine* OmHandle;

@@ -240,7 +240,7 @@ static uint32_t take(uint32_t& off, size_t elem, size_t count) {
   return r;
 }
 
-static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl) {
+static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl, bool split) {
   memset(&ly, 0, sizeof(ly));
   uint32_t off = 0;
   const size_t T = c.T, U = c.U, R = c.R, J = c.J, NS = c.NS;
@@ -267,9 +267,11 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl) {
   ly.slot_cache = take(off, 16, (T + 31) / 32);
   ly.u_rel_key = take(off, 4, U);
   ly.s_qtotal = take(off, 2, NS); ly.s_coming = take(off, 2, NS);
-  if (T > 128) {   // big mines run SPLIT: shared-memory helpers that keep the per-minute / per-departure scans out of HBM
-    ly.t_road = take(off, 2, T);       // current road of every truck (0xFFFF: not on a road), refreshed every minute
-    ly.r_jamcnt = take(off, 2, R);     // stored jams per road
+  if (split) {   // shared-memory helpers that keep the per-minute / per-departure scans of a big mine out of HBM
+    ly.t_lastbrk_hot = take(off, 8, T);  // last breakdown time per truck (instead of the record field)
+    ly.t_loc = take(off, 4, T);          // {status, current, target, -} per truck (instead of the record fields)
+    ly.t_road = take(off, 2, T);         // current road of every truck (0xFFFF: not on a road), refreshed every minute
+    ly.r_jamcnt = take(off, 2, R);       // stored jams per road
   }
   ly.hot_bytes = (off + 15u) & ~15u;
   off = ly.hot_bytes;
@@ -280,6 +282,9 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl) {
   ly.t_rng = ly.t_rec + 64; ly.t_svc = ly.t_rec + 68; ly.t_epoch = ly.t_rec + 70;
   ly.t_next = ly.t_rec + 72; ly.t_unit = ly.t_rec + 74; ly.t_status = ly.t_rec + 77;
   ly.t_cur = ly.t_rec + 78; ly.t_tgt = ly.t_rec + 79;
+  if (split) {   // published offsets follow the data (strides: t_loc_stride / 8)
+    ly.t_status = ly.t_loc + 0; ly.t_cur = ly.t_loc + 1; ly.t_tgt = ly.t_loc + 2; ly.t_lastbrk = ly.t_lastbrk_hot;
+  }
   if (rl) ly.t_since = take(off, 8, T);
   ly.j_pos = take(off, 8, J); ly.j_end = take(off, 8, J);
   if (rl) ly.j_start = take(off, 8, J);
@@ -360,16 +365,18 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
   }
   if (rc == OM_OK) {
     h->rl = (cfg->flags & OM_CFG_RL_SURFACE) != 0;
-    build_layout(c, h->ly, h->rl);
+    build_layout(c, h->ly, h->rl, false);
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     int maxsm = 0;
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     int limit = maxsm < OM_SMEM_LIMIT ? maxsm : OM_SMEM_LIMIT;
     // Whole blob in shared memory when that leaves at least 8 resident warps per SM; otherwise only the hot part
-    // (pending entries, unit records, roads) is staged and truck records / the jam pool are accessed in place.
+    // (pending entries, unit records, roads, per-truck location / breakdown arrays) is staged and truck records / the
+    // jam pool are accessed in place.  The layout depends on the decision (split layouts carry extra hot arrays).
     h->split = (limit / (int)h->ly.total_bytes) < 8;
     if (const char* ev = getenv("OM_SPLIT")) h->split = atoi(ev) != 0;   // tuning knob
+    if (h->split) build_layout(c, h->ly, h->rl, true);
     const int staged = (int)(h->split ? h->ly.hot_bytes : h->ly.total_bytes);
     int w = limit / staged;
     if (w > OM_MAX_WARPS_PER_CTA) w = OM_MAX_WARPS_PER_CTA;

@@ -229,7 +229,8 @@ struct Sim {
 #define OM_A_t_load(type, i) OM_TREC(type, 0, i)
 #define OM_A_t_jstart(type, i) OM_TREC(type, 8, i)
 #define OM_A_t_prejam(type, i) OM_TREC(type, 16, i)
-#define OM_A_t_lastbrk(type, i) OM_TREC(type, 24, i)
+#define OM_THOT(type, field, esz, off, i) (*(type*)(sm + ly.field + (uint32_t)(i) * (esz) + (off)))
+#define OM_A_t_lastbrk(type, i) (*((SPLIT && ly.t_lastbrk_hot) ? &OM_THOT(type, t_lastbrk_hot, 8u, 0, i) : &OM_TREC(type, 24, i)))
 #define OM_A_t_repair(type, i) OM_TREC(type, 32, i)
 #define OM_A_t_total(type, i) OM_TREC(type, 40, i)
 #define OM_A_t_cycle(type, i) OM_TREC(type, 48, i)
@@ -240,9 +241,9 @@ struct Sim {
 #define OM_A_t_epoch(type, i) OM_TREC(type, 70, i)
 #define OM_A_t_next(type, i) OM_TREC(type, 72, i)
 #define OM_A_t_unit(type, i) OM_TREC(type, 74, i)
-#define OM_A_t_status(type, i) OM_TREC(type, 77, i)
-#define OM_A_t_cur(type, i) OM_TREC(type, 78, i)
-#define OM_A_t_tgt(type, i) OM_TREC(type, 79, i)
+#define OM_A_t_status(type, i) (*((SPLIT && ly.t_loc) ? &OM_THOT(type, t_loc, 4u, 0, i) : &OM_TREC(type, 77, i)))
+#define OM_A_t_cur(type, i) (*((SPLIT && ly.t_loc) ? &OM_THOT(type, t_loc, 4u, 1, i) : &OM_TREC(type, 78, i)))
+#define OM_A_t_tgt(type, i) (*((SPLIT && ly.t_loc) ? &OM_THOT(type, t_loc, 4u, 2, i) : &OM_TREC(type, 79, i)))
 #define OM_A_u_rel_key(type, i) OM_SOA(type, u_rel_key, i)
 #define OM_A_u_last_start(type, i) OM_UREC(type, 0, i)
 #define OM_A_u_last_done(type, i) OM_UREC(type, 8, i)
@@ -1664,6 +1665,7 @@ __device__ __forceinline__ void om_init_state(unsigned char* sm, unsigned char* 
                                               const OmStateLayout& ly, int lane, uint64_t seed, int dispatcher) {
   const double inf = om_inf();
   (void)inf;
+  const bool SPLIT = true;   // accessors: follow the layout (ly.t_loc != 0 <=> the handle runs the SPLIT kernels)
   // zero everything first
   #pragma unroll 1
   for (uint32_t o = lane * 8; o < sm_bytes; o += 256) *(unsigned long long*)(sm + o) = 0ull;

@@ -45,7 +45,7 @@ _LAYOUT_FIELDS = ["total_bytes", "hdr", "t_time", "t_load", "t_jstart", "t_preja
                   "t_status", "t_cur", "t_tgt", "u_last_start", "u_last_done", "u_tons", "u_lastbrk",
                   "u_rel_key", "u_svc", "u_user", "u_head", "u_tail", "u_qlen", "u_repair", "r_repair_end",
                   "j_pos", "j_start", "j_end", "j_road", "s_qtotal", "s_coming", "s_tons", "s_cap", "s_ability", "scratch",
-                  "t_rec", "u_rec", "t_stride", "u_stride", "e_stride", "hot_bytes", "hdr_bytes", "slot_cache", "t_road", "r_jamcnt"]
+                  "t_rec", "u_rec", "t_stride", "u_stride", "e_stride", "hot_bytes", "hdr_bytes", "slot_cache", "t_road", "r_jamcnt", "t_loc", "t_lastbrk_hot"]
 _ENTRY_FIELDS = {"t_time", "t_key", "t_phase"}                # the truck's 16-byte pending entry
 _SOA_FIELDS = {"u_rel_key", "u_lastbrk", "t_since"}            # every other t_* / u_* field lives in a record
 
@@ -288,7 +288,11 @@ class BatchedMine:
             off = getattr(ly, field)
             item = np.dtype(dtype).itemsize
             stride = item
-            if field in _ENTRY_FIELDS:
+            if ly.t_loc and field in ("t_status", "t_cur", "t_tgt"):
+                stride = 4                                  # split layouts: {status, cur, tgt, -} per truck in the hot part
+            elif ly.t_lastbrk_hot and field == "t_lastbrk":
+                stride = 8
+            elif field in _ENTRY_FIELDS:
                 stride = ly.e_stride
             elif field not in _SOA_FIELDS and field[:2] in ("t_", "u_"):
                 stride = ly.t_stride if field[0] == "t" else ly.u_stride

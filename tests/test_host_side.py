@@ -70,7 +70,7 @@ def test_struct_sizes_match_header():
     from openmines_b200.engine import OmOutputsStruct, OmStateLayoutStruct
     from openmines_b200.trace import SUMMARY_DTYPE, TICK_DTYPE, TRACE_DTYPE
     assert ctypes.sizeof(OmOutputsStruct) == 72
-    assert ctypes.sizeof(OmStateLayoutStruct) == 4 * 54
+    assert ctypes.sizeof(OmStateLayoutStruct) == 4 * 56
     assert ctypes.sizeof(cfgmod.OmConfigStruct) == 12 * 4 + 14 * 8 + 14 * 8
     assert (TRACE_DTYPE.itemsize, TICK_DTYPE.itemsize, SUMMARY_DTYPE.itemsize) == (32, 32, 64)
 

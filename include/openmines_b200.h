@@ -220,7 +220,8 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
 int om_destroy(OmHandle h);
 const char* om_last_error(OmHandle h);
 
-/* Size / layout of one instance's state blob; the caller allocates n_instances * bytes. */
+/* Size / layout of one instance's state blob; the caller allocates n_instances * bytes, 16-byte aligned (the kernels
+ * move blobs with TMA bulk copies). */
 int om_state_bytes(OmHandle h, size_t* per_instance);
 int om_state_layout(OmHandle h, OmStateLayout* out);
 

@@ -470,6 +470,7 @@ int om_reset(OmHandle h, const uint64_t* seeds, const int32_t* dispatcher, int r
 int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* stream) {
   if (!h || !state) return set_err(h, OM_E_INVALID, "om_run: null argument");
   if (!h->reset_done) return set_err(h, OM_E_INVALID, "om_run: om_reset has not been called on this handle (the state blobs are uninitialised)");
+  if (((uintptr_t)state & 15u) != 0) return set_err(h, OM_E_INVALID, "om_run: state must be 16-byte aligned (TMA bulk copies)");
   CK(cudaSetDevice(h->device));
   RunParams p;
   memset(&p, 0, sizeof(p));
@@ -515,6 +516,7 @@ int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* str
   if (!h || !state || !io || !io->obs) return set_err(h, OM_E_INVALID, "om_step: null argument");
   if (!h->reset_done) return set_err(h, OM_E_INVALID, "om_step: om_reset has not been called on this handle (the state blobs are uninitialised)");
   if (!h->rl) return set_err(h, OM_E_INVALID, "om_step: the handle was created without OM_CFG_RL_SURFACE (OmConfig.flags)");
+  if (((uintptr_t)state & 15u) != 0) return set_err(h, OM_E_INVALID, "om_step: state must be 16-byte aligned (TMA bulk copies)");
   CK(cudaSetDevice(h->device));
   RunParams p;
   memset(&p, 0, sizeof(p));

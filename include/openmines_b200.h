@@ -229,7 +229,9 @@ int om_state_layout(OmHandle h, OmStateLayout* out);
  * (mine.py:30-48, 357-389): writes the t=0 state of every instance.
  *   seeds       device [N]  Philox key per instance
  *   dispatcher  device [N]  OM_DISP_* per instance
- *   tape_values/tape_sites/tape_offsets: device, only for OM_RNG_TAPE (offsets has N+1 entries) */
+ *   tape_values/tape_sites/tape_offsets: device, only for OM_RNG_TAPE (offsets has N+1 entries); the handle keeps the
+ *     pointers, so the buffers must stay valid until the last om_run / om_step of this episode batch has completed.
+ * Also computes the work-queue order of om_run (instances grouped by dispatcher, most expensive group first). */
 int om_reset(OmHandle h, const uint64_t* seeds, const int32_t* dispatcher, int rng_mode,
              const double* tape_values, const uint8_t* tape_sites, const int64_t* tape_offsets,
              void* state, void* stream);

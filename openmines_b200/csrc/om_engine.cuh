@@ -155,13 +155,6 @@ __device__ __forceinline__ double om_ddiv0(double a, double b) { return (a == 0.
 // log(x) in fp64, out of line: the RL surface takes eight logs per env step, and one shared copy of the ~90-instruction body
 // stays in the instruction cache while eight inlined copies are streamed once each (the step kernel is fetch-bound)
 __device__ __noinline__ double om_dlog(double x) { return log(x); }
-// butterfly sum over the warp, out of line (five call sites in the reward)
-__device__ __noinline__ double om_warp_sum(double v) {
-#pragma unroll 1
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 // CPython >= 3.12 sum() step over exact floats (Neumaier), see oracle/des_oracle.py py_sum
 struct PySum {
   double s, c;
@@ -1446,10 +1439,19 @@ struct Sim {
       double lo = (st > rl_last) ? st : rl_last, hi = (en < now) ? en : now;
       if (lo < hi) jm += hi - lo;
     }
-    w = acc_wait + om_warp_sum(w);
-    double service = (acc_shovel + om_warp_sum(sh)) + (acc_dumper + om_warp_sum(du));
-    mv = acc_move + om_warp_sum(mv);
-    jm = acc_jam + om_warp_sum(jm);
+    // one butterfly for the five partial sums (same xor order per value as five separate reductions)
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+      w += __shfl_xor_sync(OM_FULL, w, o);
+      sh += __shfl_xor_sync(OM_FULL, sh, o);
+      du += __shfl_xor_sync(OM_FULL, du, o);
+      mv += __shfl_xor_sync(OM_FULL, mv, o);
+      jm += __shfl_xor_sync(OM_FULL, jm, o);
+    }
+    w = acc_wait + w;
+    double service = (acc_shovel + sh) + (acc_dumper + du);
+    mv = acc_move + mv;
+    jm = acc_jam + jm;
     double final_reward = 0.0;
     if (final_step && now != 0.0) {
       double ft = rl_last_prod - 10000.0;

@@ -196,11 +196,12 @@ struct Sim {
   const double* tape_v;
   const uint8_t* tape_s;
   Philox4 ordw;   // words of the current order's Philox call (PHILOX mode)
+  bool ordw_ready; // ordw already holds them (computed alongside the load draw earlier in this chain)
   uint32_t dirty; // slots (groups of 32 trucks) whose cached minimum is stale (see run())
   double rl_last, rl_last_prod, acc_wait, acc_shovel, acc_dumper, acc_move, acc_jam;   // RL only
 
   __device__ __forceinline__ Sim(unsigned char* sm_, unsigned char* blob, const RunParams& p, int lane_, long long inst_)
-      : sm(sm_), cold(SPLIT ? blob : sm_), c(p.c), ly(p.ly), out(p.out), lane(lane_), inst(inst_) {}
+      : sm(sm_), cold(SPLIT ? blob : sm_), c(p.c), ly(p.ly), out(p.out), lane(lane_), inst(inst_), ordw_ready(false) {}
 
   // State accessors.  Per-truck and per-unit scalars live in fixed-size records (array of structures): the scalar
   // DES code touches many fields of ONE truck / unit, so a record base + compile-time field offsets costs one
@@ -559,11 +560,12 @@ struct Sim {
       unsigned my_on = my_pair & mvmask;
       pair_cnt += __popc(my_pair);
       on_cnt += __popc(my_on);
+      const double mycap = (o < T) ? __ldg(&c.cap[o]) : 0.0;   // values reach the candidate's lane by shuffle, in truck order
 #pragma unroll 1
-      while (my_on) {
-        int b = __ffs(my_on) - 1;
+      for (int left = __reduce_max_sync(OM_FULL, __popc(my_on)); left > 0; --left) {
+        double x = __shfl_sync(OM_FULL, mycap, __ffs(my_on) - 1);
+        if (my_on) capsum += x;
         my_on &= my_on - 1;
-        capsum += __ldg(&c.cap[base + b]);
       }
     }
   }
@@ -616,12 +618,17 @@ struct Sim {
           }
         } else {
           // sum(cap/productivity for coming trucks, truck order) + estimated_queue_wait_time (:21-38)
+          // Lanes run over trucks: every lane fetches its own truck's cost at the site it is heading to (parallel loads, off
+          // the summation chain); lane s then adds the costs of the trucks coming to site s in truck order, taking each value
+          // from its owner by shuffle.
           PySum ps; ps.init();
           const bool neu = c.sum_mode != 0;
           #pragma unroll 1
           for (int base = 0; base < c.T; base += 32) {
             int o = base + lane;
             int tg = (o < c.T && o != i) ? (int)U8A(t_tgt, o) : 0;
+            double mycost = 0.0;
+            if (tg >= 1 && tg <= L) mycost = __ldg(&c.sptf_cost[__ldg(&c.ttype[o]) * L + (tg - 1)]);
             unsigned mine_mask = 0;
             #pragma unroll 1
             for (int s = 0; s < L; ++s) {
@@ -629,10 +636,11 @@ struct Sim {
               if (lane == s) mine_mask = m;
             }
             #pragma unroll 1
-            while (mine_mask) {                      // lane s walks the trucks coming to site s, in truck order
-              int b = __ffs(mine_mask) - 1;
+            for (int left = __reduce_max_sync(OM_FULL, __popc(mine_mask)); left > 0; --left) {
+              int b = __ffs(mine_mask) - 1;          // -1 (-> lane 31, value unused) once this lane's list is done
+              double x = __shfl_sync(OM_FULL, mycost, b);
+              if (mine_mask) ps.add(x, neu);
               mine_mask &= mine_mask - 1;
-              ps.add(__ldg(&c.sptf_cost[__ldg(&c.ttype[base + b]) * L + lane]), neu);
             }
           }
           if (lane < L) val = ps.result(neu) + wait;
@@ -713,8 +721,10 @@ struct Sim {
     const int L = c.L;
     uint32_t epoch = U16A(t_epoch, i);
     if (RNG == OM_RNG_PHILOX) {
-      // one call per order: x -> road-repair gap (haul/back), y -> unrepairable gap of the move that follows
-      ordw = px(epoch, (uint32_t)i, OM_S_ROAD_GAP);
+      // one call per order: x -> road-repair gap (haul/back), y -> unrepairable gap of the move that follows.  A haul
+      // order issued in the same chain as its LOAD_DONE got these words from the load's call (ordw_ready).
+      if (!ordw_ready) ordw = px(epoch, (uint32_t)i, OM_S_ROAD_GAP);
+      ordw_ready = false;
       U32A(t_rng, i) = ordw.y;
     }
     count_order(kind, site);
@@ -1206,6 +1216,7 @@ struct Sim {
       const bool chain = unique && inl;      // same-time NORMAL successors run inline
       int i = id;
       int rel_u = -1;                        // Release created in this chain, not yet popped (kept in registers)
+      ordw_ready = false;
       uint32_t rel_key = 0;
       int kind = 0, u = 0;
       uint32_t ph0 = 0;
@@ -1313,8 +1324,15 @@ struct Sim {
       if (!dump) {
         double jit;
         if (RNG == OM_RNG_PHILOX) {
-          // one call per load: x -> load jitter, y -> shovel-maintenance gap (read at LOAD_RET)
-          Philox4 r = px(U16A(t_epoch, i), (uint32_t)i, OM_S_LOAD_JITTER);
+          // one call per load: x -> load jitter, y -> shovel-maintenance gap (read at LOAD_RET).  Odd lanes compute the
+          // call of the haul order that follows with the same epoch instead (same counters as apply_order would use), so
+          // a chain that runs on to that order in this pop does not pay a second Philox call.
+          Philox4 r = px(U16A(t_epoch, i), (uint32_t)i, (lane & 1) ? OM_S_ROAD_GAP : OM_S_LOAD_JITTER);
+          ordw.x = __shfl_sync(OM_FULL, r.x, 1);
+          ordw.y = __shfl_sync(OM_FULL, r.y, 1);
+          ordw_ready = chain;
+          r.x = __shfl_sync(OM_FULL, r.x, 0);
+          r.y = __shfl_sync(OM_FULL, r.y, 0);
           jit = -0.1 + 0.2 * (double)om_u01(r.x);
           U32A(t_rng, i) = r.y;
         } else {

@@ -272,3 +272,68 @@ def test_episode_pipeline_matches_direct_runs(north_pit):
     with pytest.raises(RuntimeError):
         for _ in range(3):
             pipe.submit(ids, np.arange(n, dtype=np.uint64))
+
+
+def test_c3_full_shard_properties(north_pit):
+    """BASELINE configs[2] at its full per-GPU size (8192 seeds x {SQ, SPTF}, stochastic events on, 16384 instances):
+    no oracle finishes that in seconds, so the check is through size-independent properties --
+    * placement independence: the same (dispatcher, seed) pairs in a shuffled instance order and in a smaller batch
+      give bit-identical summaries and production curves (Philox streams are keyed by seed, not by warp or slot);
+    * conservation: tons dumped == sum over dumpers == sum over trucks (a load counts once at the dumper and once at the
+      truck), reported tons == the last sampled point of the production curve <= dumped tons;
+    * monotone production curves, one sample per simulated minute, truck state counts within the fleet size;
+    * no instance ends with an engine error."""
+    n_seeds = 8192
+    names = ["SQDispatcher", "SPTFDispatcher"] * n_seeds
+    seeds = np.repeat(np.arange(n_seeds, dtype=np.int64), 2)
+    n = len(names)
+    T = int(north_pit["sim_time"])
+    mine = _mine(north_pit, n)
+    mine.reset(names, seeds=seeds, rng_mode="philox")
+    res = mine.run()
+    s, ticks = res.summary_np(), res.ticks_np()
+    assert (s["err"] == 0).all()
+    assert (s["n_ticks"] == T).all()
+
+    # placement independence
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(n)
+    mine_b = _mine(north_pit, n)
+    mine_b.reset([names[j] for j in perm], seeds=seeds[perm], rng_mode="philox")
+    res_b = mine_b.run()
+    s_b, ticks_b = res_b.summary_np(), res_b.ticks_np()
+    assert s_b.tobytes() == s[perm].tobytes()
+    assert ticks_b.tobytes() == ticks[perm].tobytes()
+    sub = perm[:1000]
+    mine_c = _mine(north_pit, len(sub))
+    mine_c.reset([names[j] for j in sub], seeds=seeds[sub], rng_mode="philox")
+    res_c = mine_c.run()
+    assert res_c.summary_np().tobytes() == s[sub].tobytes()
+    assert res_c.ticks_np().tobytes() == ticks[sub].tobytes()
+
+    # production curves
+    prod = ticks["produced_tons"][:, :T]
+    assert (np.diff(prod, axis=1) >= 0).all()
+    assert (prod[:, -1] == s["reported_tons"]).all()
+    assert (s["reported_tons"] <= s["dumped_tons"] * (1 + 1e-12)).all()     # the two sums run in different orders
+    n_trucks = mine.pc.T
+    for f in ("working", "waiting", "load_unload", "moving", "repairing"):
+        assert (ticks[f][:, :T] <= n_trucks).all(), f
+    assert (s["n_truck_events"] >= s["n_decisions"]).all()
+    assert (s["n_decisions"] >= n_trucks).all()            # every truck got at least its init order
+
+    # conservation, on a sample of instances (the state blobs are decoded on the host)
+    S = mine.pc.S
+    for j in rng.choice(n, size=48, replace=False):
+        st = mine.state_arrays(int(j))
+        dumped = float(s["dumped_tons"][j])
+        assert abs(st["u_tons"][S:].sum() - dumped) <= 1e-9 * max(1.0, dumped)
+        assert abs(st["t_total"].sum() - dumped) <= 1e-9 * max(1.0, dumped)
+        loaded = st["u_tons"][:S].sum()
+        carried = st["t_load"].sum()                       # loaded but not yet dumped
+        assert abs(loaded - carried - dumped) <= 1e-9 * max(1.0, loaded)
+        assert int(st["u_svc"][S:].sum()) == int(st["t_svc"].sum())
+
+    # the two dispatchers see the same mines but decide differently
+    sq, sptf = s[0::2], s[1::2]
+    assert sq["reported_tons"].mean() != sptf["reported_tons"].mean()

@@ -247,3 +247,40 @@ def nmax_next(info, L, D):
     import torch
     kind = info["order_kind"]
     return torch.where(kind == 1, torch.tensor(D, device=kind.device), torch.tensor(L, device=kind.device))
+
+
+def test_c4_full_size_teacher_rollout_equals_episode_kernel(north_pit):
+    """BASELINE configs[3] at its full size (16384 envs, stochastic events on).  Size-independent property: a rollout
+    that always plays the teacher's suggestion (ShortestTrip, computed inside om_step) must reproduce, env by env and bit
+    for bit, the episode kernel running ShortestTripDispatcher as a built-in device dispatcher on the same seeds -- the
+    pause / resume of the step path, the RL-surface state layout and the per-step staging of the blobs change nothing in
+    the simulated trajectory."""
+    import torch
+    import openmines_b200 as om
+    from openmines_b200.rl_env import BatchedMineEnv
+    n = 16384
+    env = BatchedMineEnv(north_pit, n, rng_mode="philox")
+    obs, info = env.reset(seed=0)
+    steps, returns = 0, torch.zeros(n, dtype=torch.float64, device=env.mine.device)
+    while True:
+        a = info["sug_action"].clamp(min=0)                 # finished envs report -1 and ignore the action
+        obs, r, term, trunc, info = env.step(a)
+        returns += r
+        steps += 1
+        if steps % 64 == 0 and bool(term.all()):
+            break
+        assert steps < 4096, "episodes do not finish"
+    assert bool(torch.isfinite(obs).all()) and bool(torch.isfinite(returns).all())
+    h = env.mine.headers()
+    assert (h["err"] == 0).all() and (h["finished"] == 1).all()
+
+    mine = om.BatchedMine(north_pit, n)
+    mine.reset(["ShortestTripDispatcher"] * n, seeds=np.arange(n, dtype=np.int64), rng_mode="philox")
+    s = mine.run().summary_np()
+    assert (s["err"] == 0).all()
+    assert (h["reported_tons"] == s["reported_tons"]).all()
+    assert (h["n_events"] == s["n_truck_events"]).all()
+    assert (h["n_decisions"] == s["n_decisions"]).all()
+    assert (h["n_jams"] == s["n_jams"]).all() and (h["n_brk"] == s["n_truck_repairs"]).all()
+    assert (h["rl_steps"] == s["n_decisions"] + 1).all()    # one env step per dispatch decision + the terminal step
+    assert len(np.unique(s["reported_tons"])) > n // 2      # the seeds really differ

@@ -274,21 +274,11 @@ def test_episode_pipeline_matches_direct_runs(north_pit):
             pipe.submit(ids, np.arange(n, dtype=np.uint64))
 
 
-def test_c3_full_shard_properties(north_pit):
-    """BASELINE configs[2] at its full per-GPU size (8192 seeds x {SQ, SPTF}, stochastic events on, 16384 instances):
-    no oracle finishes that in seconds, so the check is through size-independent properties --
-    * placement independence: the same (dispatcher, seed) pairs in a shuffled instance order and in a smaller batch
-      give bit-identical summaries and production curves (Philox streams are keyed by seed, not by warp or slot);
-    * conservation: tons dumped == sum over dumpers == sum over trucks (a load counts once at the dumper and once at the
-      truck), reported tons == the last sampled point of the production curve <= dumped tons;
-    * monotone production curves, one sample per simulated minute, truck state counts within the fleet size;
-    * no instance ends with an engine error."""
-    n_seeds = 8192
-    names = ["SQDispatcher", "SPTFDispatcher"] * n_seeds
-    seeds = np.repeat(np.arange(n_seeds, dtype=np.int64), 2)
+def _shard_properties(cfg, names, seeds, n_sub, n_decode, **mine_kw):
+    """Size-independent properties of one per-GPU shard of live (Philox) instances -- see the two tests below."""
     n = len(names)
-    T = int(north_pit["sim_time"])
-    mine = _mine(north_pit, n)
+    T = int(cfg["sim_time"])
+    mine = _mine(cfg, n, **mine_kw)
     mine.reset(names, seeds=seeds, rng_mode="philox")
     res = mine.run()
     s, ticks = res.summary_np(), res.ticks_np()
@@ -298,14 +288,13 @@ def test_c3_full_shard_properties(north_pit):
     # placement independence
     rng = np.random.default_rng(7)
     perm = rng.permutation(n)
-    mine_b = _mine(north_pit, n)
+    mine_b = _mine(cfg, n, **mine_kw)
     mine_b.reset([names[j] for j in perm], seeds=seeds[perm], rng_mode="philox")
     res_b = mine_b.run()
-    s_b, ticks_b = res_b.summary_np(), res_b.ticks_np()
-    assert s_b.tobytes() == s[perm].tobytes()
-    assert ticks_b.tobytes() == ticks[perm].tobytes()
-    sub = perm[:1000]
-    mine_c = _mine(north_pit, len(sub))
+    assert res_b.summary_np().tobytes() == s[perm].tobytes()
+    assert res_b.ticks_np().tobytes() == ticks[perm].tobytes()
+    sub = perm[:n_sub]
+    mine_c = _mine(cfg, len(sub), **mine_kw)
     mine_c.reset([names[j] for j in sub], seeds=seeds[sub], rng_mode="philox")
     res_c = mine_c.run()
     assert res_c.summary_np().tobytes() == s[sub].tobytes()
@@ -324,7 +313,7 @@ def test_c3_full_shard_properties(north_pit):
 
     # conservation, on a sample of instances (the state blobs are decoded on the host)
     S = mine.pc.S
-    for j in rng.choice(n, size=48, replace=False):
+    for j in rng.choice(n, size=n_decode, replace=False):
         st = mine.state_arrays(int(j))
         dumped = float(s["dumped_tons"][j])
         assert abs(st["u_tons"][S:].sum() - dumped) <= 1e-9 * max(1.0, dumped)
@@ -333,7 +322,31 @@ def test_c3_full_shard_properties(north_pit):
         carried = st["t_load"].sum()                       # loaded but not yet dumped
         assert abs(loaded - carried - dumped) <= 1e-9 * max(1.0, loaded)
         assert int(st["u_svc"][S:].sum()) == int(st["t_svc"].sum())
+    return s
 
+
+def test_c3_full_shard_properties(north_pit):
+    """BASELINE configs[2] at its full per-GPU size (8192 seeds x {SQ, SPTF}, stochastic events on, 16384 instances):
+    no oracle finishes that in seconds, so the check is through size-independent properties --
+    * placement independence: the same (dispatcher, seed) pairs in a shuffled instance order and in a smaller batch
+      give bit-identical summaries and production curves (Philox streams are keyed by seed, not by warp or slot);
+    * conservation: tons dumped == sum over dumpers == sum over trucks (a load counts once at the dumper and once at the
+      truck), reported tons == the last sampled point of the production curve <= dumped tons;
+    * monotone production curves, one sample per simulated minute, truck state counts within the fleet size;
+    * no instance ends with an engine error."""
+    n_seeds = 8192
+    names = ["SQDispatcher", "SPTFDispatcher"] * n_seeds
+    seeds = np.repeat(np.arange(n_seeds, dtype=np.int64), 2)
+    s = _shard_properties(north_pit, names, seeds, n_sub=1000, n_decode=48)
     # the two dispatchers see the same mines but decide differently
-    sq, sptf = s[0::2], s[1::2]
-    assert sq["reported_tons"].mean() != sptf["reported_tons"].mean()
+    assert s[0::2]["reported_tons"].mean() != s[1::2]["reported_tons"].mean()
+
+
+def test_c5_full_shard_properties():
+    """BASELINE configs[4] at its per-GPU size (500 trucks, 20 load sites, 10 dump sites; 1024 live instances, the split
+    state mode with its shared-memory helper arrays and cached slot minima): the same properties."""
+    from openmines_b200.synthetic import scaled_mine
+    n = 1024
+    names = ["SQDispatcher", "SPTFDispatcher"] * (n // 2)
+    seeds = np.arange(n, dtype=np.int64)
+    _shard_properties(scaled_mine(), names, seeds, n_sub=100, n_decode=8, jam_capacity=512)

@@ -639,7 +639,7 @@ struct Sim {
             for (int left = __reduce_max_sync(OM_FULL, __popc(mine_mask)); left > 0; --left) {
               int b = __ffs(mine_mask) - 1;          // -1 (-> lane 31, value unused) once this lane's list is done
               double x = __shfl_sync(OM_FULL, mycost, b);
-              if (mine_mask) ps.add(x, neu);
+              ps.add(mine_mask ? x : 0.0, neu);      // + 0.0 leaves both the sum and the compensation unchanged
               mine_mask &= mine_mask - 1;
             }
           }

@@ -273,6 +273,42 @@ def run_c4(a):
     n_episodes, n_events, n_dec = float(delta[0]), float(delta[1]), float(delta[2])
     ms_per_step = ms / a.steps
     sec = ms / 1000.0
+    # ---- end to end with the policy on the HOST (the reference's trainers: actions arrive from host memory, observations,
+    # rewards and flags go back to it every env step through the public env.step())
+    e2e_steps = 200
+    h_act = torch.zeros(n, dtype=torch.int32).pin_memory()
+    h_obs = torch.empty((n, env.obs_dim), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(n, dtype=torch.float64).pin_memory()
+    h_done = torch.empty(n, dtype=torch.bool).pin_memory()
+    table = torch.randint(0, env.n_actions, (16, n), dtype=torch.int32)      # the host "policy": pre-drawn random actions
+
+    def host_loop(k):
+        sink = 0.0
+        for q in range(k):
+            h_act.copy_(table[q & 15])
+            o, r, term, _, _ = env.step(h_act.to(dev, non_blocking=True))
+            h_obs.copy_(o, non_blocking=True); h_rew.copy_(r, non_blocking=True); h_done.copy_(term, non_blocking=True)
+            torch.cuda.synchronize()
+            sink += float(h_rew[0]) + float(h_obs[0, 3]) + float(h_done[0])       # the host reads the step's results
+        return sink
+
+    host_loop(20)
+    if dist is not None:
+        dist.barrier()
+    t_before = totals()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    host_loop(e2e_steps)
+    h1.record()
+    torch.cuda.synchronize()
+    e2e_ms = h0.elapsed_time(h1)
+    e2e_delta = totals() - t_before
+    e2e_tot = torch.tensor([e2e_ms, e2e_delta[1], e2e_delta[2]], dtype=torch.float64, device=dev)
+    if dist is not None:
+        mx = e2e_tot[:1].clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = e2e_tot[1:].clone(); dist.all_reduce(sm)
+        e2e_tot = torch.cat([mx, sm])
+    e2e_ms, e2e_events, e2e_dec = [float(x) for x in e2e_tot.cpu()]
     # kernel-only timing of om_step for the HBM roofline (same steady state, constant action)
     act = torch.zeros(n, dtype=torch.int32, device=dev)
     for _ in range(20):
@@ -307,9 +343,13 @@ def run_c4(a):
             "decisions_per_s": n_dec / sec,
             "env_steps_per_s": n * world * a.steps * steps_per / sec,
             "clocks": clocks,
-            "e2e": {"value": n_events / sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "note": "observations, actions, rewards and resets stay on the device by design (policy and env share the GPU); "
-                            "nothing crosses PCIe inside the rollout loop"},
+            "e2e": {"value": e2e_events / (e2e_ms / 1000.0), "unit": UNIT,
+                    "decisions_per_s": e2e_dec / (e2e_ms / 1000.0),
+                    "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": n * (env.obs_dim * 4 + 8 + 1),
+                    "note": "policy on the HOST: per env step the actions come from pinned host memory and observations, rewards "
+                            "and done flags go back to it (env.step of the public BatchedMineEnv, %d steps, one synchronisation "
+                            "per step); `value` is the device-resident rollout (policy and env share the GPU, nothing crosses "
+                            "PCIe)" % e2e_steps},
             "gpu_launches": a.steps * steps_per,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "kernel": "om_step_kernel<philox>", "kernel_ms": step_ms,

@@ -350,3 +350,24 @@ def test_c5_full_shard_properties():
     names = ["SQDispatcher", "SPTFDispatcher"] * (n // 2)
     seeds = np.arange(n, dtype=np.int64)
     _shard_properties(scaled_mine(), names, seeds, n_sub=100, n_decode=8, jam_capacity=512)
+
+
+def test_c_program_through_the_c_abi_vs_golden(tmp_path):
+    """examples/c_api_demo.c: a plain C program (gcc, CUDA runtime only -- no Python, no PyTorch in the process) packs the
+    one-truck mine by hand, runs it through om_create / om_reset / om_run and must print the unmodified reference's
+    tonnage, event count and production curve for that mine."""
+    import re
+    import subprocess
+    from test_host_side import _build_c_demo
+    exe = _build_c_demo(tmp_path)
+    r = subprocess.run([exe, "3"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    g = Golden("det_one_truck_mine_NaiveDispatcher_s0")
+    rows = re.findall(r"instance (\d+): reported_tons (\S+) dumped_tons (\S+) truck_events (\d+) decisions (\d+) ticks (\d+) "
+                      r"err (\d+) tons@60min (\S+)", r.stdout)
+    assert len(rows) == 3, r.stdout
+    for row in rows:
+        assert float(row[1]) == float(g.reported_tons)
+        assert int(row[3]) == int(g.n_truck_events)
+        assert int(row[5]) == int(g.n_ticks) and int(row[6]) == 0
+        assert float(row[7]) == float(g.tick["produced_tons"][60])

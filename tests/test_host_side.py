@@ -8,6 +8,8 @@ import pytest
 import openmines_b200 as om
 from openmines_b200 import _lib, config as cfgmod
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_packer_static_anchors(north_pit):
     """SURVEY.md Appendix D anchors, recomputed with the reference's arithmetic."""
@@ -111,3 +113,35 @@ def test_external_runner_needs_a_gpu(north_pit):
             return 0
     with pytest.raises(RuntimeError):
         om.run_external(D, north_pit, n_instances=1)
+
+
+def _build_c_demo(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    libdir = os.path.join(ROOT, "openmines_b200")
+    exe = str(tmp_path / "c_api_demo")
+    cmd = ["gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(cuda, "include"),
+           os.path.join(ROOT, "examples", "c_api_demo.c"), "-o", exe, "-L" + libdir, "-lopenmines_b200",
+           "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-lm", "-Wl,-rpath," + libdir,
+           "-Wl,-rpath," + os.path.join(cuda, "lib64")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_abi_compiles_as_plain_c_and_fails_loudly_without_gpu(tmp_path):
+    """include/openmines_b200.h is a C header (no C++, no torch types): examples/c_api_demo.c builds with gcc -Wall -Werror
+    against the shared library; without a GPU om_create reports OM_E_CUDA instead of falling back to anything."""
+    import subprocess
+    import torch
+    from openmines_b200 import _lib
+    _lib.load()
+    exe = _build_c_demo(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([exe, "2"], capture_output=True, text=True)
+    assert r.returncode == 3
+    assert "no CUDA device" in r.stderr

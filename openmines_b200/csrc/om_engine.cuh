@@ -873,19 +873,23 @@ struct Sim {
     }
     double produce = pm.result(neu);
     reported_tons = produce;
-    uint32_t n_work = 0, n_wait = 0, n_lu = 0, n_mov = 0, n_rep = 0;
+    // truck status counts (mine.py:69-86): every lane counts its trucks in two packed accumulators (16 bits per class),
+    // two warp sums at the end.  A truck turns unrepairable once and stays (truck.py:545-547), so the count of trucks
+    // still in service is T - n_unrep.
+    const uint32_t WAIT_SET = (1u << ST_WAIT_INIT) | (1u << ST_WAIT_SHOVEL) | (1u << ST_WAIT_HAUL) | (1u << ST_WAIT_DUMPER) |
+                              (1u << ST_WAIT_BACK);
+    const uint32_t LU_SET = (1u << ST_LOADING) | (1u << ST_UNLOADING);
+    uint32_t acc_a = 0, acc_b = 0;                 // {waiting, loading/unloading}, {moving, repairing}
     #pragma unroll 1
-    for (int base = 0; base < T; base += 32) {
-      int i = base + lane;
-      uint8_t st = (i < T) ? U8A(t_status, i) : (uint8_t)0xFF;
-      bool valid = i < T;
-      n_work += __popc(__ballot_sync(OM_FULL, valid && st != ST_UNREPAIRABLE));
-      n_wait += __popc(__ballot_sync(OM_FULL, st == ST_WAIT_INIT || st == ST_WAIT_SHOVEL || st == ST_WAIT_HAUL ||
-                                                   st == ST_WAIT_DUMPER || st == ST_WAIT_BACK));
-      n_lu += __popc(__ballot_sync(OM_FULL, st == ST_LOADING || st == ST_UNLOADING));
-      n_mov += __popc(__ballot_sync(OM_FULL, st == ST_MOVING));
-      n_rep += __popc(__ballot_sync(OM_FULL, st == ST_REPAIRING));
+    for (int i = lane; i < T; i += 32) {
+      const uint32_t st = U8A(t_status, i);
+      acc_a += ((WAIT_SET >> st) & 1u) | (((LU_SET >> st) & 1u) << 16);
+      acc_b += (st == ST_MOVING ? 1u : 0u) | (st == ST_REPAIRING ? 0x10000u : 0u);
     }
+    acc_a = __reduce_add_sync(OM_FULL, acc_a);
+    acc_b = __reduce_add_sync(OM_FULL, acc_b);
+    const uint32_t n_work = (uint32_t)T - n_unrep, n_wait = acc_a & 0xFFFFu, n_lu = acc_a >> 16, n_mov = acc_b & 0xFFFFu,
+                   n_rep = acc_b >> 16;
     if (out.ticks != nullptr && k < out.tick_capacity) {
       if (lane == 0) {
         // OmTickRecord (32 B) packed in registers and written as two 16-byte stores

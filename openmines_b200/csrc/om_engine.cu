@@ -345,6 +345,25 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
     rc = upload(h, svc.data(), svc.size(), &c.svc_time);
   }
   if (rc == OM_OK) {
+    // undisturbed trip time per (speed class, road): (distance / speed) * 60 with the reference's operation order (truck.py:153)
+    std::vector<double> speeds;
+    std::vector<int32_t> sc(T);
+    for (int t = 0; t < T; ++t) {
+      size_t k = 0;
+      while (k < speeds.size() && speeds[k] != cfg->truck_speed[t]) ++k;
+      if (k == speeds.size()) speeds.push_back(cfg->truck_speed[t]);
+      sc[t] = (int32_t)k;
+    }
+    std::vector<double> trip(speeds.size() * (size_t)c.R);
+    for (size_t k = 0; k < speeds.size(); ++k)
+      for (int r = 0; r < c.R; ++r) {
+        volatile double q = cfg->road_distance[r] / speeds[k];      // no contraction / reassociation across the two steps
+        trip[k * (size_t)c.R + r] = q * 60.0;
+      }
+    rc = upload(h, sc.data(), sc.size(), &c.sclass);
+    if (rc == OM_OK) rc = upload(h, trip.data(), trip.size(), &c.trip60);
+  }
+  if (rc == OM_OK) {
     std::vector<int32_t> rb(c.NS + 1);
     rb[0] = -1;
     for (int cur = 1; cur <= c.NS; ++cur)

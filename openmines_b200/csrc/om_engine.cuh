@@ -80,6 +80,8 @@ struct DevCfg {
   const double* load_time;
   const int32_t* rbase;     // [NS+1] road_id(cur, tgt) = rbase[cur] + tgt
   const double* svc_time;   // [NT*U] load_time for shovels, dumper cycle for dumpers (built in om_create)
+  const int32_t* sclass;    // [T] speed class of the truck (built in om_create)
+  const double* trip60;     // [n speed classes * R] (road_distance / speed) * 60: the undisturbed trip time, truck.py:153
   const double* sptf_cost;
   const double* jam_chance;
   const int32_t* near_haul;
@@ -747,10 +749,12 @@ struct Sim {
   __device__ __forceinline__ void move_depart(int i, bool dead) {
     int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
     double dist = F64(t_dist, i);
-    double duration = om_ddiv(dist, __ldg(&c.speed[i])) * 60.0;
+    const int rid = road_id(cur, tgt);
+    // (distance / speed) * 60: tabulated per (speed class, road) for the road's own length; only a detour divides
+    double duration = __ldg(&c.trip60[__ldg(&c.sclass[i]) * c.R + rid]);
+    if (__builtin_expect(dist != __ldg(&c.rdist[rid]), 0)) duration = om_ddiv(dist, __ldg(&c.speed[i])) * 60.0;
     double pre = 0.0;
     if (RNG != OM_RNG_DET && jam_count > 0) {
-      int rid = road_id(cur, tgt);
       const bool maybe = !(SPLIT && ly.r_jamcnt != 0) || ((const uint16_t*)(sm + ly.r_jamcnt))[rid] != 0;
       #pragma unroll 1
       for (uint32_t base = 0; maybe && base < jam_count; base += 32) {
@@ -1042,7 +1046,6 @@ struct Sim {
   __device__ __forceinline__ double sample_jam_position(int k, int rid, uint32_t n_on) {
     const int T = c.T;
     const float sd = (float)c.jam_sd, h = 1.0f / 999.0f;
-    const double base_dist = __ldg(&c.rdist[rid]);
     float x = 0.5f;
 #pragma unroll 1
     for (uint32_t it = 0; it < 64; ++it) {
@@ -1073,7 +1076,7 @@ struct Sim {
         }
       }
       if (found < 0) break;                                 // cannot happen: n_on trucks are on the road
-      float cv = coverage(found, base_dist);
+      float cv = coverage(found, rid);
       float xx = cv + sd * om_normal_fast(r.y, r.z);
       if (xx >= -0.5f * h && xx <= 1.0f + 0.5f * h) { x = xx; break; }
     }
@@ -1083,8 +1086,8 @@ struct Sim {
   }
 
   // Truck.get_route_coverage (truck.py:496-520)
-  __device__ __forceinline__ float coverage(int i, double base_dist) {
-    double total = om_ddiv(base_dist, __ldg(&c.speed[i])) * 60.0 + F64(t_prejam, i) + F64(t_repair, i);
+  __device__ __forceinline__ float coverage(int i, int rid) {
+    double total = __ldg(&c.trip60[__ldg(&c.sclass[i]) * c.R + rid]) + F64(t_prejam, i) + F64(t_repair, i);
     double cov = om_ddiv0(now - F64(t_jstart, i), total);
     if (cov > 1.0) cov = 1.0;
     return (float)cov;

@@ -211,6 +211,30 @@ def test_scaled_mine_c5_vs_oracle():
     assert not diffs, diffs[:5]
 
 
+def test_mine_with_more_than_1024_trucks_vs_oracle():
+    """1100 trucks: more than 32 slots of 32 pending entries, so the cached slot minima of the SPLIT kernels take their
+    multi-trip paths (and 160 units / 420 roads span several lane trips everywhere).  det SQ / SPTF bit-exact vs the
+    oracle, plus a tape replay of a live oracle run."""
+    from oracle import des_oracle as do
+    from openmines_b200.synthetic import scaled_mine
+    cfg = scaled_mine(n_trucks=(400, 400, 300), sim_time=40)
+    cases = [("SQDispatcher", "det", 0), ("SPTFDispatcher", "det", 0)]
+    oracles = [do.run_oracle(cfg, d, m, seed=s) for d, m, s in cases]
+    mine = _mine(cfg, len(cases), jam_capacity=1024)
+    assert mine.pc.T == 1100 and mine.layout.hot_bytes < mine.layout.total_bytes        # split mode
+    mine.reset([d for d, _, _ in cases], seeds=[s for _, _, s in cases], rng_mode="det")
+    res = mine.run(trace_capacity=16384, site_ticks=True, order_capacity=8192)
+    for i, (d, m, s) in enumerate(cases):
+        diffs = engine_vs_ref(oracles[i], mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s: %s" % (d, diffs[:5])
+    live = do.run_oracle(cfg, "SQDispatcher", "live", seed=1)
+    mine = _mine(cfg, 1, jam_capacity=1024)
+    mine.reset("SQDispatcher", rng_mode="tape", tapes=[live.tape])
+    res = mine.run(trace_capacity=16384, site_ticks=True, order_capacity=8192)
+    diffs = engine_vs_ref(live, mine, res, 0)
+    assert not diffs, diffs[:5]
+
+
 def test_run_before_reset_is_an_error_not_a_hang(north_pit):
     """om_run / om_step before om_reset must fail on the host (a never-written blob could make the kernel spin)."""
     import torch

@@ -123,3 +123,29 @@ def test_ragged_mine_live_distribution_vs_reference(ragged_mine):
             z = (a.mean() - b.mean()) / np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
             print("%-22s %-13s engine %9.2f  reference %9.2f  z=%+.2f" % (d, key, a.mean(), b.mean(), z))
             assert abs(z) < 4.0, "%s %s: engine mean %.2f vs reference %.2f (z=%.2f)" % (d, key, a.mean(), b.mean(), z)
+
+
+def test_limits_mine_32_sites_32_units_per_site_vs_oracle():
+    """The engine's stated maxima at once: L + D = 32 sites, 32 shovels at one load site and 32 dumpers at one dump site
+    (unit selection and the wait estimates run one lane per unit of a site).  det Naive (every truck to the 32-shovel
+    site) / SQ / SPTF bit-exact vs the oracle and a tape replay of a live run."""
+    from oracle import des_oracle as do
+    from helpers import engine_vs_ref
+    from test_host_side import _limits_mine
+    import openmines_b200 as om
+    cfg = _limits_mine()
+    cases = [("NaiveDispatcher", 0), ("SQDispatcher", 0), ("SPTFDispatcher", 0), ("NearestDispatcher", 0)]
+    oracles = [do.run_oracle(cfg, d, "det", seed=s) for d, s in cases]
+    mine = om.BatchedMine(cfg, len(cases), jam_capacity=256)
+    assert mine.pc.L + mine.pc.D == 32
+    mine.reset([d for d, _ in cases], seeds=[s for _, s in cases], rng_mode="det")
+    res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=4096)
+    for i, (d, s) in enumerate(cases):
+        diffs = engine_vs_ref(oracles[i], mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s: %s" % (d, diffs[:5])
+    live = do.run_oracle(cfg, "SQDispatcher", "live", seed=1)
+    mine = om.BatchedMine(cfg, 1, jam_capacity=256)
+    mine.reset("SQDispatcher", rng_mode="tape", tapes=[live.tape])
+    res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=4096)
+    diffs = engine_vs_ref(live, mine, res, 0)
+    assert not diffs, diffs[:5]

@@ -145,3 +145,39 @@ def test_c_abi_compiles_as_plain_c_and_fails_loudly_without_gpu(tmp_path):
     r = subprocess.run([exe, "2"], capture_output=True, text=True)
     assert r.returncode == 3
     assert "no CUDA device" in r.stderr
+
+
+def _limits_mine(n_load=16, n_dump=16, units_site0=32):
+    from openmines_b200.synthetic import scaled_mine
+    cfg = scaled_mine(n_trucks=(60, 80, 60), n_load=n_load, n_dump=n_dump, sim_time=60)
+    sh = cfg["load_sites"][0]["shovels"]
+    cfg["load_sites"][0]["shovels"] = [dict(sh[1], name="LS1-Shovel-%d" % (k + 1)) for k in range(units_site0)]
+    cfg["dump_sites"][0]["dumpers"][0]["count"] = units_site0
+    for j in range(1, n_dump):
+        cfg["dump_sites"][j]["dumpers"][0]["count"] = 1
+    return cfg
+
+
+def test_om_create_rejects_mines_beyond_the_engine_limits():
+    """More than 32 sites or more than 32 shovels / dumpers at one site: OM_E_UNSUPPORTED with a message, checked before
+    any CUDA call (so this runs without a GPU); an ABI version mismatch and an empty mine: OM_E_INVALID."""
+    lib = _lib.load()
+
+    def create(cfg=None, mutate=None):
+        pc = om.pack_config(cfg if cfg is not None else _limits_mine())
+        s = pc.c_struct()
+        if mutate:
+            mutate(s)
+        h = ctypes.c_void_p()
+        return lib.om_create(ctypes.byref(s), 2, 0, ctypes.byref(h)), lib.om_last_error(None)
+
+    rc, msg = create(_limits_mine(n_load=17, n_dump=16))
+    assert rc == -4 and b"L + D <= 32" in msg
+    rc, msg = create(_limits_mine(units_site0=33))
+    assert rc == -4 and b"1..32" in msg
+    rc, msg = create(mutate=lambda s: setattr(s, "abi_version", 1))
+    assert rc == -1 and b"ABI" in msg
+    rc, msg = create(mutate=lambda s: setattr(s, "n_trucks", 0))
+    assert rc == -1 and b"empty mine" in msg
+    rc, msg = create(mutate=lambda s: setattr(s, "jam_capacity", 0))
+    assert rc == -4

@@ -14,6 +14,29 @@ import numpy as np
 from .engine import BatchedMine, DISPATCHER_IDS
 
 
+class _Space:
+    """Minimal stand-in for ``gymnasium.spaces.Discrete`` / ``Box`` (gymnasium is optional): what vector-env trainers read
+    (``single_action_space.n``, ``single_observation_space.shape`` / ``.dtype`` / ``.low`` / ``.high``)."""
+
+    def __init__(self, shape, dtype, n=None, low=None, high=None):
+        self.shape, self.dtype, self.n, self.low, self.high = tuple(shape), np.dtype(dtype), n, low, high
+
+    def __repr__(self):
+        return "Discrete(%d)" % self.n if self.n is not None else "Box(%r, %r, %r, %s)" % (self.low, self.high, self.shape,
+                                                                                            self.dtype)
+
+
+def _spaces(n_actions, obs_dim):
+    """(action space, observation space) of one env: Discrete(max(L, D)), Box(0, inf, (obs_dim,), float32)
+    (mine_env.py:217-226); real gymnasium spaces when the package is importable."""
+    try:
+        from gymnasium import spaces
+        return spaces.Discrete(n_actions), spaces.Box(low=0.0, high=np.inf, shape=(obs_dim,), dtype=np.float32)
+    except Exception:
+        return (_Space((), np.int64, n=int(n_actions)),
+                _Space((obs_dim,), np.float32, low=0.0, high=float("inf")))
+
+
 class BatchedMineEnv:
     def __init__(self, config, num_envs, device=0, rng_mode="philox", sug_dispatcher="ShortestTripDispatcher",
                  auto_reset=False, jam_capacity=64, reward_mode="dense"):
@@ -29,6 +52,7 @@ class BatchedMineEnv:
         self.reward_mode = reward_mode                     # GymMineEnv(reward_mode=...), mine_env.py:55
         self.obs_dim = self.mine.obs_dim()
         self.n_actions = max(self.mine.pc.L, self.mine.pc.D)          # spaces.Discrete(max(L, D)), mine_env.py:217-221
+        self.single_action_space, self.single_observation_space = _spaces(self.n_actions, self.obs_dim)
         dev, n = self.mine.device, self.num_envs
         self.io = {
             "obs": torch.zeros((n, self.obs_dim), dtype=torch.float32, device=dev),

@@ -260,6 +260,8 @@ def test_c4_full_size_teacher_rollout_equals_episode_kernel(north_pit):
     from openmines_b200.rl_env import BatchedMineEnv
     n = 16384
     env = BatchedMineEnv(north_pit, n, rng_mode="philox")
+    assert env.single_action_space.n == 5 and env.single_observation_space.shape == (194,)      # mine_env.py:217-226
+    assert np.dtype(env.single_observation_space.dtype) == np.float32
     obs, info = env.reset(seed=0)
     steps, returns = 0, torch.zeros(n, dtype=torch.float64, device=env.mine.device)
     while True:

@@ -6,9 +6,14 @@
   ``config['dispatcher']['type']`` -> ``states_dict`` (what ``Charter.draw`` consumes).
 * ``scene_based_fleet_ablation(config, lo, hi)`` -- cli/run.py:283-370: production vs fleet size for every dispatcher,
   10 fleet sizes, truck types scaled by their original ratios; each point is the mean over ``n_seeds`` instances.
+* ``algo_based_fleet_ablation(scenes, baseline, target, lo, hi)`` -- cli/run.py:363-472: for every scene (a directory of
+  mine JSONs, or a list of paths / dicts) the production ratio target / baseline over the same 10 fleet sizes; one
+  batch per (scene, fleet size) holds both dispatchers' instances.
 """
 import copy
+import glob
 import math
+import os
 
 import numpy as np
 
@@ -93,3 +98,39 @@ def scene_based_fleet_ablation(config_file, min_truck, max_truck, dispatchers=No
             results[n]["std"].append(float(s[k]["reported_tons"].std()))
         mine.close()
     return results
+
+
+def algo_based_fleet_ablation(scenes, baseline, target, min_truck=1, max_truck=160, n_seeds=32, stochastic=True, device=0):
+    """``scenes``: directory with ``*.json`` mine configs (the reference's ``-d``), or a list of paths / config dicts.
+    Returns ``{scene name: {"fleet_sizes": [...], "ratios": [...], "baseline": [...], "target": [...]}}`` -- the
+    ``scenes_data`` that ``Charter.draw_algo_based_fleet_ablation_experiment`` plots (ratio 0 where the baseline produced
+    nothing, cli/run.py:461-463) plus the two mean productions."""
+    if isinstance(scenes, (str, os.PathLike)):
+        paths = sorted(glob.glob(os.path.join(str(scenes), "*.json")))
+        scenes = [(os.path.splitext(os.path.basename(p))[0], load_config(p)) for p in paths]
+    else:
+        named = []
+        for k, sc in enumerate(scenes):
+            cfg = load_config(sc)
+            name = os.path.splitext(os.path.basename(sc))[0] if isinstance(sc, (str, os.PathLike)) else \
+                cfg.get("mine", {}).get("name", "scene%d" % k)
+            named.append((name, cfg))
+        scenes = named
+    ids = np.repeat([DISPATCHER_IDS[by_name(baseline).name], DISPATCHER_IDS[by_name(target).name]], n_seeds).astype(np.int32)
+    seeds = np.tile(np.arange(n_seeds, dtype=np.uint64), 2)
+    out = {}
+    for name, cfg in scenes:
+        data = {"fleet_sizes": [], "ratios": [], "baseline": [], "target": []}
+        for fs in fleet_sizes_for(min_truck, max_truck):
+            c = scaled_fleet_config(cfg, fs)
+            c["charging_site"]["trucks"] = [t for t in c["charging_site"]["trucks"] if t["count"] > 0]
+            mine = BatchedMine(c, 2 * n_seeds, device=device)
+            mine.reset(ids, seeds=seeds, rng_mode="philox" if stochastic else "det")
+            tons = mine.run(ticks=True).summary_np()["reported_tons"].reshape(2, n_seeds).mean(axis=1)
+            mine.close()
+            data["fleet_sizes"].append(fs)
+            data["baseline"].append(float(tons[0]))
+            data["target"].append(float(tons[1]))
+            data["ratios"].append(float(tons[1] / tons[0]) if tons[0] > 1e-9 else 0.0)
+        out[name] = data
+    return out

@@ -92,7 +92,7 @@ def test_result_json_tape_sptf(north_pit):
 
 
 def test_experiment_drivers(north_pit):
-    """run_dispatch_sim / run_simulation / fleet ablation facades (cli/run.py:48-112,115-273,283-370)."""
+    """run_dispatch_sim / run_simulation / fleet ablation facades (cli/run.py:48-112,115-273,283-370,363-472)."""
     from openmines_b200 import experiments as ex
     import openmines_b200 as om
     cfg = dict(north_pit, sim_time=60)
@@ -111,6 +111,19 @@ def test_experiment_drivers(north_pit):
     assert sum(t["count"] for t in c["charging_site"]["trucks"]) == 40
     res = ex.scene_based_fleet_ablation(cfg, 20, 20, dispatchers=["NaiveDispatcher", "SQDispatcher"], n_seeds=8)
     assert res["SQDispatcher"]["fleet_sizes"] == [20] and res["SQDispatcher"]["productions"][0] > res["NaiveDispatcher"]["productions"][0]
+    # algo-based ablation (cli/run.py:363-472): ratio target / baseline per scene and fleet size; a directory of scene JSONs works too
+    data = ex.algo_based_fleet_ablation([cfg, dict(cfg, mine={"name": "SecondScene"})], "NaiveDispatcher", "SQDispatcher",
+                                        min_truck=15, max_truck=33, n_seeds=4, stochastic=False)
+    assert set(data) == {north_pit["mine"]["name"], "SecondScene"}
+    first = data[north_pit["mine"]["name"]]
+    assert first["fleet_sizes"] == ex.fleet_sizes_for(15, 33) and len(first["ratios"]) == 10
+    assert all(r > 1.0 for r in first["ratios"])                   # SQ out-produces Naive at every fleet size
+    assert first["ratios"] == data["SecondScene"]["ratios"]        # det mode: same mine, same numbers
+    assert abs(first["ratios"][3] - first["target"][3] / first["baseline"][3]) < 1e-15
+    scene_dir = os.path.join(GOLDEN, "configs")
+    by_dir = ex.algo_based_fleet_ablation(scene_dir, "NaiveDispatcher", "NearestDispatcher", min_truck=5, max_truck=5, n_seeds=2,
+                                          stochastic=False)
+    assert "north_pit_mine" in by_dir and by_dir["north_pit_mine"]["fleet_sizes"] == [5]
 
 
 def test_result_json_tape_ragged_mine(ragged_mine):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OM_ABI_VERSION 3
+#define OM_ABI_VERSION 4
 
 /* OmConfig.flags */
 #define OM_CFG_RL_SURFACE 1 /* allocate the fields om_step needs (reward windows, minute-sampled site values): bigger
@@ -175,7 +175,33 @@ typedef struct OmOutputs {
   int32_t order_capacity;
   int32_t reserved;
   OmUnitTick* unit_ticks;     /* [N * tick_capacity * (S+M)] per-minute shovel/dumper samples; NULL to skip */
+  /* Draw-tape export (OM_RNG_PHILOX only; NULL to skip): every random value the reference would have drawn, post-transform,
+   * in the reference's call order with its site id (OM_DRAW_*) -- replaying this tape through the reference
+   * (oracle/ref_harness.py RngControl "replay") or its CPU restatement reproduces the instance's trajectory bit for bit.
+   * The per-minute truck-breakdown block reserves two slots per truck (gap, repair time); a slot whose draw the reference
+   * would not have made carries site OM_DRAW_SKIP and must be dropped by the reader.  Overflow sets
+   * OM_IERR_TRACE_OVERFLOW (the simulation itself is unaffected). */
+  double* draw_values;        /* [N * draw_capacity] */
+  uint8_t* draw_sites;        /* [N * draw_capacity] */
+  uint32_t* draw_count;       /* [N] slots used (including OM_DRAW_SKIP ones) */
+  int64_t draw_capacity;      /* slots per instance */
 } OmOutputs;
+
+/* draw-site ids of the tape formats (OM_RNG_TAPE input, draw-tape export): one per random call site of the reference */
+#define OM_DRAW_LOAD_JITTER 0   /* truck.py:230  np.random.uniform(-0.1, 0.1) */
+#define OM_DRAW_MAINT_GAP 1     /* truck.py:358  np.random.exponential(1440) */
+#define OM_DRAW_MAINT_DUR 2     /* truck.py:362  np.random.normal(45, 5) */
+#define OM_DRAW_BREAK_GAP 3     /* truck.py:528  np.random.exponential(360) */
+#define OM_DRAW_BREAK_DUR 4     /* truck.py:532  np.random.normal(10, 3) */
+#define OM_DRAW_UNREPAIRABLE 5  /* truck.py:545  random.expovariate(1/70560) */
+#define OM_DRAW_ROAD_GAP 6      /* road.py:253   random.expovariate(lambda_repair) */
+#define OM_DRAW_ROAD_DUR 7      /* road.py:256   np.random.normal(mu, sigma) */
+#define OM_DRAW_DETOUR 8        /* road.py:329   np.random.normal(0.4, 0.1) */
+#define OM_DRAW_JAM_COIN 9      /* road.py:179   random.random() */
+#define OM_DRAW_JAM_POS 10      /* road.py:203   np.random.choice(1000, p) -> the chosen grid value */
+#define OM_DRAW_JAM_DUR 11      /* road.py:212   np.random.weibull(2) */
+#define OM_DRAW_DISPATCH 12     /* random_dispatcher.py:16,22,29  RandomState.randint */
+#define OM_DRAW_SKIP 255
 
 /* Byte offsets of the per-instance state arrays inside one state blob (om_state_bytes).  Truck
  * arrays have n_trucks elements, unit arrays n_shovels+n_dumpers, road arrays R. */
@@ -220,6 +246,11 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
 int om_destroy(OmHandle h);
 const char* om_last_error(OmHandle h);
 
+/* ABI self-description for FFI bindings: writes up to n of {OM_ABI_VERSION, sizeof OmConfig, OmOutputs, OmStepIO,
+ * OmStateLayout, OmSummary, OmTickRecord, OmTraceRecord, OmUnitTick, per-instance header, stats rows, stats columns} and
+ * returns how many values exist.  A binding compares them with its own mirrors before the first call (_lib.py). */
+int om_abi_info(int32_t* out, int32_t n);
+
 /* Size / layout of one instance's state blob; the caller allocates n_instances * bytes, 16-byte aligned (the kernels
  * move blobs with TMA bulk copies). */
 int om_state_bytes(OmHandle h, size_t* per_instance);
@@ -242,8 +273,12 @@ int om_reset(OmHandle h, const uint64_t* seeds, const int32_t* dispatcher, int r
 int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* stream);
 
 /* Local partial statistics for the cross-GPU all-reduce (issued by the caller with NCCL):
- * stats_out device [6*16] doubles = per dispatcher id {count, sum tons, sum tons^2, sum events,
- * sum decisions, sum jams, sum road repairs, sum truck repairs, sum unrepairable, n_err, ...}. */
+ * stats_out device [7*16] doubles, one row per device dispatcher id (0..6), every entry an INTEGER so that sums are exact
+ * and order-independent (bit-identical totals on 1 or 8 GPUs over the same global instance ids):
+ *   0 count, 1/2 reported tons in units of 2^-24 t (value >> 25, value & (2^25-1)), 3 truck events, 4 decisions, 5 jams,
+ *   6 road repairs, 7 truck repairs, 8 unrepairable, 9 instances with an engine error, 10 scheduler hops,
+ *   11/12 dumped tons (as 1/2), 13/14 sum of (tons rounded to 2^-8 t)^2 in units of 2^-16 t^2 (value >> 32, value & (2^32-1)).
+ * Decoder: openmines_b200.parallel.describe. */
 int om_stats_reduce(OmHandle h, const OmSummary* summary, const int32_t* dispatcher,
                     double* stats_out, void* stream);
 

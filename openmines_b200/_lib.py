@@ -1,8 +1,10 @@
 """Loader of the C-ABI shared library ``libopenmines_b200.so`` (include/openmines_b200.h).
 
 There is no CPU fallback: if the library has not been built (``python -c "import
-__graft_entry__ as g; g.build()"`` or ``python -m openmines_b200.build``) importing the engine
-raises.  The library is built in-tree next to this file so it travels with the repo snapshot.
+__graft_entry__ as g; g.build()"``, which calls ``build()`` below) loading the engine raises.  The
+library is built in-tree next to this file so it travels with the repo snapshot.  A library older
+than its sources is rebuilt when nvcc is available and refused otherwise, and the sizes of the ABI
+structs it was compiled with are compared with the ctypes mirrors before the first call.
 """
 import ctypes
 import os
@@ -53,6 +55,13 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("openmines_b200: %s is missing -- build it first (__graft_entry__.build()); "
                            "the engine has no CPU fallback" % LIB_PATH)
+    if needs_build():
+        # a stale binary with changed struct layouts would corrupt memory silently
+        import shutil
+        if shutil.which(os.environ.get("NVCC", "nvcc")) is None:
+            raise RuntimeError("openmines_b200: %s is older than its sources and nvcc is not available to rebuild it"
+                               % LIB_PATH)
+        build(force=True)
     lib = ctypes.CDLL(LIB_PATH)
     vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
     lib.om_last_error.restype = ctypes.c_char_p
@@ -70,9 +79,44 @@ def load():
     for f in ("om_create", "om_destroy", "om_state_bytes", "om_state_layout", "om_launch_info", "om_reset",
               "om_run", "om_stats_reduce", "om_obs_dim", "om_step"):
         getattr(lib, f).restype = ctypes.c_int
+    lib.om_abi_info.argtypes = [ctypes.POINTER(i32), i32]
+    lib.om_abi_info.restype = i32
     _lib = lib
+    _check_abi()
     return lib
 
 
-EXPORTED_SYMBOLS = ["om_create", "om_destroy", "om_last_error", "om_state_bytes", "om_state_layout", "om_reset",
+ABI_INFO_FIELDS = ["abi_version", "sizeof_OmConfig", "sizeof_OmOutputs", "sizeof_OmStepIO", "sizeof_OmStateLayout",
+                   "sizeof_OmSummary", "sizeof_OmTickRecord", "sizeof_OmTraceRecord", "sizeof_OmUnitTick", "sizeof_InstHdr",
+                   "stats_rows", "stats_cols"]
+
+
+def abi_info():
+    """What the loaded binary was compiled with (``om_abi_info``)."""
+    lib = load()
+    buf = (ctypes.c_int32 * len(ABI_INFO_FIELDS))()
+    n = lib.om_abi_info(buf, len(ABI_INFO_FIELDS))
+    return {k: int(buf[i]) for i, k in enumerate(ABI_INFO_FIELDS[:n])}
+
+
+def _check_abi():
+    global _lib
+    from . import config, engine, trace, parallel
+    info = abi_info()
+    want = {"abi_version": config.OM_ABI_VERSION, "sizeof_OmConfig": ctypes.sizeof(config.OmConfigStruct),
+            "sizeof_OmOutputs": ctypes.sizeof(engine.OmOutputsStruct), "sizeof_OmStepIO": ctypes.sizeof(engine.OmStepIOStruct),
+            "sizeof_OmStateLayout": ctypes.sizeof(engine.OmStateLayoutStruct), "sizeof_OmSummary": trace.SUMMARY_DTYPE.itemsize,
+            "sizeof_OmTickRecord": trace.TICK_DTYPE.itemsize, "sizeof_OmTraceRecord": trace.TRACE_DTYPE.itemsize,
+            "sizeof_OmUnitTick": trace.UNIT_TICK_DTYPE.itemsize, "stats_rows": parallel.N_DISPATCHERS,
+            "stats_cols": parallel.STATS_WIDTH}
+    bad = {k: (info.get(k), v) for k, v in want.items() if info.get(k) != v}
+    if info.get("sizeof_InstHdr", 0) > engine.HDR_DTYPE.itemsize:
+        bad["sizeof_InstHdr"] = (info["sizeof_InstHdr"], engine.HDR_DTYPE.itemsize)
+    if bad:
+        _lib = None
+        raise RuntimeError("openmines_b200: %s does not match the Python bindings (binary, bindings): %r -- rebuild it"
+                           % (LIB_PATH, bad))
+
+
+EXPORTED_SYMBOLS = ["om_create", "om_destroy", "om_last_error", "om_abi_info", "om_state_bytes", "om_state_layout", "om_reset",
                     "om_run", "om_stats_reduce", "om_launch_info", "om_obs_dim", "om_step"]

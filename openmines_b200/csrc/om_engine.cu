@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
         p.out.summary[inst] = r;
       }
     }
+    if (TRACE && RNG == OM_RNG_PHILOX && p.out.draw_count != nullptr && lane == 0) p.out.draw_count[inst] = (uint32_t)s.tape_pos;
     om_stage_out(g, sm, staged, lane);
   }
 }
@@ -165,25 +166,73 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_step_kernel(c
 }
 
 #define OM_STATS_PER_DISP 16
-__global__ void om_stats_kernel(const OmSummary* summary, const int32_t* dispatcher, long long n, double* stats) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int d = dispatcher[i];
-  if (d < 0 || d > 5) return;
-  const OmSummary& s = summary[i];
-  double* o = stats + d * OM_STATS_PER_DISP;
-  atomicAdd(o + 0, 1.0);
-  atomicAdd(o + 1, s.reported_tons);
-  atomicAdd(o + 2, s.reported_tons * s.reported_tons);
-  atomicAdd(o + 3, (double)s.n_truck_events);
-  atomicAdd(o + 4, (double)s.n_decisions);
-  atomicAdd(o + 5, (double)s.n_jams);
-  atomicAdd(o + 6, (double)s.n_road_repairs);
-  atomicAdd(o + 7, (double)s.n_truck_repairs);
-  atomicAdd(o + 8, (double)s.n_unrepairable);
-  atomicAdd(o + 9, (s.err != 0 && s.err != OM_IERR_TRACE_OVERFLOW) ? 1.0 : 0.0);
-  atomicAdd(o + 10, (double)s.n_hops);
-  atomicAdd(o + 11, s.dumped_tons);
+#define OM_STATS_DISPATCHERS 7   /* the seven device dispatchers (OM_DISP_NAIVE .. OM_DISP_SHORTESTTRIP) */
+// Per-dispatcher statistics for the cross-GPU all-reduce.  Every entry is an INTEGER (held in a double on the way out):
+// counts as they are, tonnages in fixed point -- reported / dumped tons in units of 2^-24 t split into a high and a low
+// word at bit 25, the squared tons (of tons rounded to 2^-8 t) split at bit 32.  Integer sums are associative, so the
+// totals do not depend on the order blocks, warps or ranks add them in: the same global instance ids give bit-identical
+// statistics on 1 or 8 GPUs, and every partial sum stays below 2^53 (exact in the fp64 all-reduce) for up to 2^20
+// instances per dispatcher.  openmines_b200/parallel.py holds the host mirror and the decoder.
+__device__ __forceinline__ void om_stats_split(double tons, unsigned long long* hi, unsigned long long* lo) {
+  double x = tons * 16777216.0;                       // 2^24
+  x = (x < 0.0) ? 0.0 : ((x > 1.0e18) ? 1.0e18 : x);  // tonnages are >= 0; NaN -> 0
+  const unsigned long long q = (unsigned long long)__double2ll_rn(x);
+  *hi = q >> 25; *lo = q & 0x1FFFFFFull;
+}
+__global__ void __launch_bounds__(256) om_stats_kernel(const OmSummary* summary, const int32_t* dispatcher, long long n,
+                                                       unsigned long long* acc, unsigned int* blocks_done, double* stats) {
+  __shared__ unsigned long long sacc[OM_STATS_DISPATCHERS * OM_STATS_PER_DISP];
+  __shared__ bool last;
+  for (int k = threadIdx.x; k < OM_STATS_DISPATCHERS * OM_STATS_PER_DISP; k += blockDim.x) sacc[k] = 0ull;
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int d = -1;
+  unsigned long long v[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) v[k] = 0ull;
+  if (i < n) {
+    d = dispatcher[i];
+    if (d < 0 || d >= OM_STATS_DISPATCHERS) d = -1;
+    const OmSummary s = summary[i];
+    v[0] = 1ull;
+    om_stats_split(s.reported_tons, &v[1], &v[2]);
+    v[3] = s.n_truck_events; v[4] = s.n_decisions; v[5] = s.n_jams; v[6] = s.n_road_repairs; v[7] = s.n_truck_repairs;
+    v[8] = s.n_unrepairable; v[9] = (s.err != 0 && s.err != OM_IERR_TRACE_OVERFLOW) ? 1ull : 0ull; v[10] = s.n_hops;
+    om_stats_split(s.dumped_tons, &v[11], &v[12]);
+    double t8 = s.reported_tons * 256.0;
+    t8 = (t8 < 0.0) ? 0.0 : ((t8 > 4.0e9) ? 4.0e9 : t8);
+    const unsigned long long q8 = (unsigned long long)__double2ll_rn(t8), sq = q8 * q8;
+    v[13] = sq >> 32; v[14] = sq & 0xFFFFFFFFull;
+  }
+  // every value is < 2^32 (hops of one instance, 25-bit words, ...): 32 of them add up in 64 bits, word by word
+#pragma unroll 1
+  for (int dd = 0; dd < OM_STATS_DISPATCHERS; ++dd) {
+    const bool mine = d == dd;
+    if (!__any_sync(OM_FULL, mine)) continue;
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+      const unsigned long long x = mine ? v[k] : 0ull;
+      const unsigned int lo = __reduce_add_sync(OM_FULL, (unsigned int)(x & 0xFFFFull));
+      const unsigned int mid = __reduce_add_sync(OM_FULL, (unsigned int)((x >> 16) & 0xFFFFull));
+      const unsigned int hi = __reduce_add_sync(OM_FULL, (unsigned int)(x >> 32));
+      if ((threadIdx.x & 31) == 0)
+        atomicAdd(&sacc[dd * OM_STATS_PER_DISP + k], (unsigned long long)lo + ((unsigned long long)mid << 16) + ((unsigned long long)hi << 32));
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < OM_STATS_DISPATCHERS * OM_STATS_PER_DISP; k += blockDim.x)
+    if (sacc[k] != 0ull) atomicAdd(&acc[k], sacc[k]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(blocks_done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {     // the last block to finish publishes the totals and clears the accumulators for the next call
+    __threadfence();
+    for (int k = threadIdx.x; k < OM_STATS_DISPATCHERS * OM_STATS_PER_DISP; k += blockDim.x) {
+      stats[k] = (double)atomicExch(&acc[k], 0ull);
+    }
+    if (threadIdx.x == 0) *blocks_done = 0u;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -197,6 +246,8 @@ struct OmEngine {
   std::vector<void*> dev_allocs;
   unsigned long long* counter = nullptr;
   int32_t* order = nullptr;   // [n] instance ids grouped by dispatcher (written by om_reset)
+  unsigned long long* stats_acc = nullptr;   // [7 * 16] integer accumulators of om_stats_reduce (zero between calls)
+  unsigned int* stats_done = nullptr;
   int rng_mode = OM_RNG_DET;
   const double* tape_values = nullptr;
   const uint8_t* tape_sites = nullptr;
@@ -296,6 +347,17 @@ extern "C" {
 
 const char* om_last_error(OmHandle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
+int om_abi_info(int32_t* out, int32_t n) {
+  const int32_t v[] = {OM_ABI_VERSION, (int32_t)sizeof(OmConfig), (int32_t)sizeof(OmOutputs), (int32_t)sizeof(OmStepIO),
+                       (int32_t)sizeof(OmStateLayout), (int32_t)sizeof(OmSummary), (int32_t)sizeof(OmTickRecord),
+                       (int32_t)sizeof(OmTraceRecord), (int32_t)sizeof(OmUnitTick), (int32_t)sizeof(InstHdr),
+                       OM_STATS_DISPATCHERS, OM_STATS_PER_DISP};
+  const int32_t m = (int32_t)(sizeof(v) / sizeof(v[0]));
+  if (!out || n <= 0) return m;
+  for (int32_t k = 0; k < n && k < m; ++k) out[k] = v[k];
+  return m;
+}
+
 int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* out) {
   OmEngine* h = nullptr;
   if (!cfg || !out) return set_err(h, OM_E_INVALID, "om_create: null argument");
@@ -306,10 +368,24 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
     return set_err(h, OM_E_INVALID, "om_create: empty mine (mine.py:346-351 asserts)");
   if (T >= 0xFFFF || L + D > 32 || L + D >= 0xFF || cfg->jam_capacity <= 0 || cfg->jam_capacity > 4096)
     return set_err(h, OM_E_UNSUPPORTED, "om_create: need T < 65535, L + D <= 32, 0 < jam_capacity <= 4096");
+  if (S + M >= 0xFFFF) return set_err(h, OM_E_UNSUPPORTED, "om_create: need fewer than 65535 shovels + dumpers");
   for (int s = 0; s < L + D; ++s) {
     int nu = cfg->site_unit_begin[s + 1] - cfg->site_unit_begin[s];
-    if (nu <= 0 || nu > 32) return set_err(h, OM_E_UNSUPPORTED, "om_create: each site needs 1..32 shovels/dumpers");
+    if (nu <= 0) return set_err(h, OM_E_INVALID, "om_create: every site needs at least one shovel / dumper");
   }
+  // index tables: out-of-range entries would become out-of-bounds device reads
+  if (cfg->site_unit_begin[0] != 0 || cfg->site_unit_begin[L] != S || cfg->site_unit_begin[L + D] != S + M)
+    return set_err(h, OM_E_INVALID, "om_create: site_unit_begin must run 0 .. S .. S+M over the load sites then the dump sites");
+  for (int t = 0; t < T; ++t)
+    if (cfg->truck_type[t] < 0 || cfg->truck_type[t] >= cfg->n_truck_types || cfg->fixed_group[t] < 0 || cfg->fixed_group[t] >= L ||
+        !(cfg->truck_speed[t] > 0.0) || !(cfg->truck_capacity[t] > 0.0))
+      return set_err(h, OM_E_INVALID, "om_create: truck_type / fixed_group out of range, or non-positive truck speed / capacity");
+  for (int i = 0; i < L; ++i)
+    if (cfg->nearest_haul[i] < 0 || cfg->nearest_haul[i] >= D) return set_err(h, OM_E_INVALID, "om_create: nearest_haul out of range");
+  for (int j = 0; j < D; ++j)
+    if (cfg->nearest_back[j] < 0 || cfg->nearest_back[j] >= L) return set_err(h, OM_E_INVALID, "om_create: nearest_back out of range");
+  if (cfg->nearest_init < 0 || cfg->nearest_init >= L) return set_err(h, OM_E_INVALID, "om_create: nearest_init out of range");
+  if (cfg->sum_mode != 0 && cfg->sum_mode != 1) return set_err(h, OM_E_INVALID, "om_create: sum_mode must be 0 (naive) or 1 (Neumaier)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return set_err(h, OM_E_CUDA, "om_create: no CUDA device (this engine has no CPU fallback)");
@@ -378,6 +454,17 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
   }
   if (rc == OM_OK) {
     void* d = nullptr;
+    const size_t nb = sizeof(unsigned long long) * OM_STATS_DISPATCHERS * OM_STATS_PER_DISP + 16;
+    e = cudaMalloc(&d, nb);
+    if (e == cudaSuccess) e = cudaMemset(d, 0, nb);
+    if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, cudaGetErrorString(e));
+    else {
+      h->stats_acc = (unsigned long long*)d; h->dev_allocs.push_back(d);
+      h->stats_done = (unsigned int*)(h->stats_acc + OM_STATS_DISPATCHERS * OM_STATS_PER_DISP);
+    }
+  }
+  if (rc == OM_OK) {
+    void* d = nullptr;
     e = cudaMalloc(&d, sizeof(int32_t) * (size_t)n_instances);
     if (e != cudaSuccess) rc = set_err(h, OM_E_NOMEM, cudaGetErrorString(e));
     else { h->order = (int32_t*)d; h->dev_allocs.push_back(d); }
@@ -422,7 +509,8 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
           (const void*)om_step_kernel<OM_RNG_TAPE, false>, (const void*)om_step_kernel<OM_RNG_DET, true>,
           (const void*)om_step_kernel<OM_RNG_PHILOX, true>, (const void*)om_step_kernel<OM_RNG_TAPE, true>};
       for (size_t i = 0; i < sizeof(fns) / sizeof(fns[0]) && rc == OM_OK; ++i) {
-        e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
+        // the same value for every handle (a per-handle value would lower the limit under older, larger handles)
+        e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
         if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
       }
     }
@@ -502,7 +590,11 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
   p.order = h->order;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
-  const bool trace = p.out.trace != nullptr || p.out.orders != nullptr;   // event-trace / order-log variant
+  if (p.out.draw_values != nullptr && (p.out.draw_sites == nullptr || p.out.draw_capacity <= 0))
+    return set_err(h, OM_E_INVALID, "om_run: draw_values needs draw_sites and draw_capacity > 0");
+  if (p.out.draw_values != nullptr && h->rng_mode != OM_RNG_PHILOX)
+    return set_err(h, OM_E_INVALID, "om_run: the draw-tape export exists in OM_RNG_PHILOX mode only");
+  const bool trace = p.out.trace != nullptr || p.out.orders != nullptr || p.out.draw_values != nullptr;   // event-trace / order-log / draw-tape variant
 #define OM_LAUNCH(MODE)                                                                             \
   do {                                                                                              \
     if (h->split) {                                                                                 \
@@ -567,9 +659,8 @@ int om_stats_reduce(OmHandle h, const OmSummary* summary, const int32_t* dispatc
   if (!h || !summary || !dispatcher || !stats_out) return set_err(h, OM_E_INVALID, "om_stats_reduce: null argument");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaMemsetAsync(stats_out, 0, sizeof(double) * 6 * OM_STATS_PER_DISP, st));
   long long blocks = (h->n + 255) / 256;
-  om_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(summary, dispatcher, h->n, stats_out);
+  om_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(summary, dispatcher, h->n, h->stats_acc, h->stats_done, stats_out);
   CK(cudaGetLastError());
   return OM_OK;
 }

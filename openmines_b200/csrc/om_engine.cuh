@@ -23,6 +23,9 @@
 #include "../../include/openmines_b200.h"
 #include "om_rng.cuh"
 
+static_assert(OM_S_LOAD_JITTER == OM_DRAW_LOAD_JITTER && OM_S_BREAK_GAP == OM_DRAW_BREAK_GAP && OM_S_ROAD_GAP == OM_DRAW_ROAD_GAP &&
+              OM_S_JAM_COIN == OM_DRAW_JAM_COIN && OM_S_JAM_DUR == OM_DRAW_JAM_DUR && OM_S_DISPATCH == OM_DRAW_DISPATCH,
+              "draw-site ids of om_rng.cuh and include/openmines_b200.h");
 #define OM_FULL 0xffffffffu
 #define OM_NONE16 0xFFFFu
 #define OM_NOLOC 0xFFu
@@ -302,7 +305,7 @@ struct Sim {
       h->rl_last_time = rl_last; h->rl_last_prod = rl_last_prod; h->acc_wait = acc_wait; h->acc_shovel = acc_shovel;
       h->acc_dumper = acc_dumper; h->acc_move = acc_move; h->acc_jam = acc_jam;
     }
-    h->tape_pos = (RNG == OM_RNG_TAPE) ? tape_pos - (unsigned long long)p.tape_offsets[inst] : 0ull;
+    h->tape_pos = (RNG == OM_RNG_TAPE) ? tape_pos - (unsigned long long)p.tape_offsets[inst] : (TAPE_OUT ? tape_pos : 0ull);
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -342,6 +345,26 @@ struct Sim {
     tape_pos++;
     return v;
   }
+  // Draw-tape export (TRACE variants in PHILOX mode, OmOutputs.draw_values != NULL): every value the reference would have
+  // drawn at this point -- post-transform, in the reference's call order, with its site id -- is appended to the instance's
+  // tape, so that the CPU restatement can replay the very trajectory the Philox kernel produced (tests/test_gpu_draw_tape.py).
+  // Values are written where they are CONSUMED (the merged Philox calls produce several draws ahead of their use).
+  static constexpr bool TAPE_OUT = TRACE && (RNG == OM_RNG_PHILOX);
+  __device__ __forceinline__ bool tape_on() const { return TAPE_OUT && out.draw_values != nullptr; }
+  __device__ __forceinline__ void tape_put_at(unsigned long long pos, int site, double v) {
+    if (pos < (unsigned long long)out.draw_capacity) {
+      const long long o = inst * (long long)out.draw_capacity + (long long)pos;
+      out.draw_values[o] = v;
+      out.draw_sites[o] = (uint8_t)site;
+    }
+  }
+  __device__ __forceinline__ void tape_put(int site, double v) {
+    if (TAPE_OUT && out.draw_values != nullptr) {
+      if (tape_pos >= (unsigned long long)out.draw_capacity) { if (err == OM_IERR_NONE) err = OM_IERR_TRACE_OVERFLOW; }
+      else if (lane == 0) tape_put_at(tape_pos, site, v);
+      tape_pos++;
+    }
+  }
   __device__ __forceinline__ Philox4 px(uint32_t epoch, uint32_t entity, uint32_t site, uint32_t stream = 0) const {
     return om_philox(epoch, entity, site, stream, k0, k1);
   }
@@ -349,21 +372,29 @@ struct Sim {
   __device__ __forceinline__ double draw_exp(int site, uint32_t epoch, uint32_t entity, double mean) {
     if (RNG == OM_RNG_DET) return om_inf();
     if (RNG == OM_RNG_TAPE) return tape_next(site);
-    return (double)om_exp1(px(epoch, entity, site).x) * mean;
+    double v = (double)om_exp1(px(epoch, entity, site).x) * mean;
+    tape_put(site, v);
+    return v;
   }
   __device__ __forceinline__ double draw_normal(int site, uint32_t epoch, uint32_t entity, double mu, double sigma) {
     if (RNG == OM_RNG_TAPE) return tape_next(site);
     Philox4 r = px(epoch, entity, site);
-    return mu + sigma * (double)om_normal_fast(r.x, r.y);
+    double v = mu + sigma * (double)om_normal_fast(r.x, r.y);
+    tape_put(site, v);
+    return v;
   }
   __device__ __forceinline__ double draw_jitter(uint32_t epoch, uint32_t entity) {
     if (RNG == OM_RNG_DET) return 0.0;
     if (RNG == OM_RNG_TAPE) return tape_next(OM_S_LOAD_JITTER);
-    return -0.1 + 0.2 * (double)om_u01(px(epoch, entity, OM_S_LOAD_JITTER).x);
+    double v = -0.1 + 0.2 * (double)om_u01(px(epoch, entity, OM_S_LOAD_JITTER).x);
+    tape_put(OM_S_LOAD_JITTER, v);
+    return v;
   }
   __device__ __forceinline__ int draw_randint(uint32_t epoch, uint32_t entity, int n) {
     if (RNG == OM_RNG_TAPE) return (int)tape_next(OM_S_DISPATCH);
-    return (int)om_randint(px(epoch, entity, OM_S_DISPATCH).x, (uint32_t)n);   // also in DET mode (keyed, exact)
+    int v = (int)om_randint(px(epoch, entity, OM_S_DISPATCH).x, (uint32_t)n);   // also in DET mode (keyed, exact)
+    tape_put(OM_S_DISPATCH, (double)v);
+    return v;
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -426,15 +457,22 @@ struct Sim {
   // get_available_shovel / get_available_dumper (load_site.py:209-220, dump_site.py:105-116):
   // first idle unit, else first unit with the shortest queue.  Lane-parallel over the site's units.
   __device__ __forceinline__ int pick_unit(int site) {
-    int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
-    int u = ub + lane;
-    bool valid = u < ue;
-    bool idle = valid && U16A(u_user, u) == OM_NONE16;
-    unsigned m = __ballot_sync(OM_FULL, idle);
-    if (m) return ub + __ffs(m) - 1;
-    uint32_t v = valid ? (((uint32_t)U16A(u_qlen, u) << 8) | (uint32_t)lane) : 0xFFFFFFFFu;
-    uint32_t best = __reduce_min_sync(OM_FULL, v);
-    return ub + (int)(best & 0xFFu);
+    const int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
+    int u0 = ub;
+    uint32_t best = 0xFFFFFFFFu;
+    #pragma unroll 1
+    do {                                           // one trip per 32 units of the site (north_pit: always one)
+      const int u = u0 + lane;
+      const bool valid = u < ue;
+      const bool idle = valid && U16A(u_user, u) == OM_NONE16;
+      const unsigned m = __ballot_sync(OM_FULL, idle);
+      if (m) return u0 + __ffs(m) - 1;
+      const uint32_t v = valid ? (((uint32_t)U16A(u_qlen, u) << 16) | (uint32_t)(u - ub)) : 0xFFFFFFFFu;
+      const uint32_t b = __reduce_min_sync(OM_FULL, v);
+      best = b < best ? b : best;
+      u0 += 32;
+    } while (__builtin_expect(u0 < ue, 0));
+    return ub + (int)(best & 0xFFFFu);
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -454,6 +492,7 @@ struct Sim {
       if (RNG != OM_RNG_DET) {
         double gap = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(ordw.x) / c.road_lambda
                                             : draw_exp(OM_S_ROAD_GAP, epoch, (uint32_t)i, 1.0 / c.road_lambda);   // expovariate(lambda)
+        if (RNG == OM_RNG_PHILOX) tape_put(OM_S_ROAD_GAP, gap);
         if (__builtin_expect(now >= end + gap, 0)) {   // a new road repair starts: a handful per episode
           double d = draw_normal(OM_S_ROAD_DUR, epoch, (uint32_t)i, c.road_mu, c.road_sigma);
           double dur = (d > 0.0) ? d : 0.0;   // max(0, x)
@@ -900,8 +939,9 @@ struct Sim {
         uint4 a, b;
         a.x = (uint32_t)__double2loint(produce); a.y = (uint32_t)__double2hiint(produce);
         a.z = (uint32_t)svc_total; a.w = (n_work & 0xFFFFu) | (n_wait << 16);
-        b.x = (n_lu & 0xFFFFu) | (n_mov << 16); b.y = (n_rep & 0xFFFFu) | (n_jams << 16);
-        b.z = (n_road_rep & 0xFFFFu) | (n_brk << 16); b.w = n_unrep & 0xFFFFu;
+        // the cumulative event counters saturate at 65535 instead of wrapping
+        b.x = (n_lu & 0xFFFFu) | (n_mov << 16); b.y = (n_rep & 0xFFFFu) | (min(n_jams, 0xFFFFu) << 16);
+        b.z = min(n_road_rep, 0xFFFFu) | (min(n_brk, 0xFFFFu) << 16); b.w = n_unrep & 0xFFFFu;
         uint4* dst = (uint4*)(out.ticks + inst * (long long)out.tick_capacity + k);
         dst[0] = a; dst[1] = b;
       }
@@ -938,6 +978,12 @@ struct Sim {
         // the lane's first breakdown in this minute comes from word w and the gap words' unused low bytes, a second
         // or third one (rare) draws its own call.  Rolled loops on purpose (instruction-fetch bound).
         const int C = (T + 2) / 3;
+        // tape export: the reference draws truck by truck (gap, then the repair time if the breakdown fires); lanes work on
+        // trucks out of order, so the minute reserves two slots per truck and leaves 0xFF in the second when nothing fired
+        const bool tp = tape_on();
+        const unsigned long long tbase = tape_pos;
+        if (tp && tbase + 2ull * (unsigned long long)T > (unsigned long long)out.draw_capacity && err == OM_IERR_NONE)
+          err = OM_IERR_TRACE_OVERFLOW;
         #pragma unroll 1
         for (int q = lane; q < C; q += 32) {
           Philox4 r = px((uint32_t)k, (uint32_t)q, OM_S_BREAK_GAP);
@@ -949,6 +995,10 @@ struct Sim {
             uint32_t word = (w == 0) ? r.x : ((w == 1) ? r.y : r.z);
             if (i < T) {
               double gap = (double)om_exp1(word) * c.breakdown_mean;
+              if (TAPE_OUT && tp) {
+                tape_put_at(tbase + 2ull * (unsigned long long)i, OM_S_BREAK_GAP, gap);
+                tape_put_at(tbase + 2ull * (unsigned long long)i + 1ull, OM_DRAW_SKIP, 0.0);
+              }
               if (now >= F64(t_lastbrk, i) + gap) {
                 if (used) {
                   Philox4 r2 = px((uint32_t)k, (uint32_t)i, OM_S_BREAK_DUR);
@@ -956,12 +1006,14 @@ struct Sim {
                 }
                 used = true;
                 double d = c.repair_mu + c.repair_sigma * (double)om_normal_fast(na, nb2);
+                if (TAPE_OUT && tp) tape_put_at(tbase + 2ull * (unsigned long long)i + 1ull, OM_S_BREAK_DUR, d);
                 F64(t_repair, i) = (0.0 > d) ? 0.0 : d;
                 F64(t_lastbrk, i) = now;
               }
             }
           }
         }
+        if (TAPE_OUT && tp) tape_pos = tbase + 2ull * (unsigned long long)T;
         __syncwarp();
       }
       // (4) jam sampling per road in monitor order (mine.py:138-154, road.py:137-233)
@@ -1000,6 +1052,7 @@ struct Sim {
       uint32_t n_on = (r < R) ? rcnt[r] : 0u;
       bool candidate = n_on >= 2u;                          // road.py:148-176: >= 2 moving trucks
       bool hit = candidate;
+      double coin = 0.0;
       const bool second = (base & 32) != 0;
       if (RNG == OM_RNG_PHILOX) {
         if (!second) {
@@ -1007,16 +1060,22 @@ struct Sim {
           if (__any_sync(OM_FULL, candidate || n2 >= 2u)) rr = px((uint32_t)k, (uint32_t)r, OM_S_JAM_COIN);
         }
         uint32_t cw = second ? rr.y : rr.x;
-        double coin = (double)((float)(cw >> 8) * 5.9604644775390625e-08f);   // [0,1)
+        coin = (double)((float)(cw >> 8) * 5.9604644775390625e-08f);   // [0,1)
         hit = candidate && coin < __ldg(&c.jam_chance[candidate ? n_on : 0u]);
       }
-      unsigned m = __ballot_sync(OM_FULL, hit);
+      // tape export: the reference flips the coin of every candidate road, in road order, whether or not a jam follows
+      const bool tp = tape_on();
+      unsigned m = __ballot_sync(OM_FULL, (TAPE_OUT && tp) ? candidate : hit);
       #pragma unroll 1
       while (m) {
         int b = __ffs(m) - 1;
         m &= m - 1;
         int rid = base + b;
         double pos, dur;
+        if (TAPE_OUT && tp) {
+          tape_put(OM_S_JAM_COIN, __shfl_sync(OM_FULL, coin, b));
+          if (!__shfl_sync(OM_FULL, (int)hit, b)) continue;
+        }
         if (RNG == OM_RNG_TAPE) {
           uint32_t n = __shfl_sync(OM_FULL, n_on, b);
           double coin = tape_next(OM_S_JAM_COIN);
@@ -1026,7 +1085,10 @@ struct Sim {
         } else {
           uint32_t wz = __shfl_sync(OM_FULL, second ? rr.w : rr.z, b);
           pos = sample_jam_position(k, rid, __shfl_sync(OM_FULL, n_on, b));
-          dur = (double)sqrtf(om_exp1(wz)) * c.jam_scale;                         // Weibull(shape 2) * scale
+          const double wb = (double)sqrtf(om_exp1(wz));                           // Weibull(shape 2)
+          dur = wb * c.jam_scale;
+          tape_put(OM_S_JAM_POS, pos);
+          tape_put(OM_S_JAM_DUR, wb);
         }
         double end = now + dur;
         jam_append(rid, pos, end);
@@ -1341,6 +1403,7 @@ struct Sim {
           r.x = __shfl_sync(OM_FULL, r.x, 0);
           r.y = __shfl_sync(OM_FULL, r.y, 0);
           jit = -0.1 + 0.2 * (double)om_u01(r.x);
+          tape_put(OM_S_LOAD_JITTER, jit);
           U32A(t_rng, i) = r.y;
         } else {
           jit = draw_jitter(U16A(t_epoch, i), (uint32_t)i);
@@ -1371,6 +1434,7 @@ struct Sim {
         if (RNG != OM_RNG_DET) {
           double gap = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(U32A(t_rng, i)) * c.maint_mean
                                               : draw_exp(OM_S_MAINT_GAP, U16A(t_epoch, i), (uint32_t)i, c.maint_mean);
+          if (RNG == OM_RNG_PHILOX) tape_put(OM_S_MAINT_GAP, gap);
           if (__builtin_expect(now >= F64(u_lastbrk, u) + gap, 0)) { shovel_maintenance(i, u); continue; }
         }
       }
@@ -1398,6 +1462,7 @@ struct Sim {
       if (RNG != OM_RNG_DET) {
         double g = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(U32A(t_rng, i)) * c.unrepairable_mean
                                           : draw_exp(OM_S_UNREPAIRABLE, U16A(t_epoch, i), (uint32_t)i, c.unrepairable_mean);
+        if (RNG == OM_RNG_PHILOX) tape_put(OM_S_UNREPAIRABLE, g);
         dead = now >= g;                                               // check_vehicle_availability, truck.py:538-547
       }
       double rep = F64(t_repair, i);

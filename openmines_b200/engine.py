@@ -25,7 +25,8 @@ class OmOutputsStruct(ctypes.Structure):
     _fields_ = [("summary", ctypes.c_void_p), ("ticks", ctypes.c_void_p), ("tick_capacity", ctypes.c_int32),
                 ("trace_capacity", ctypes.c_int32), ("trace", ctypes.c_void_p), ("site_queue_ticks", ctypes.c_void_p),
                 ("site_tons_ticks", ctypes.c_void_p), ("orders", ctypes.c_void_p), ("order_capacity", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("unit_ticks", ctypes.c_void_p)]
+                ("reserved", ctypes.c_int32), ("unit_ticks", ctypes.c_void_p), ("draw_values", ctypes.c_void_p),
+                ("draw_sites", ctypes.c_void_p), ("draw_count", ctypes.c_void_p), ("draw_capacity", ctypes.c_int64)]
 
 
 class OmStepIOStruct(ctypes.Structure):
@@ -38,6 +39,7 @@ class OmStepIOStruct(ctypes.Structure):
 
 OM_STEP_AUTO_RESET = 1
 OM_STEP_SPARSE_REWARD = 2
+DRAW_SKIP = 255      # OM_DRAW_SKIP: slot reserved in the draw tape for a draw the reference would not have made
 
 
 _LAYOUT_FIELDS = ["total_bytes", "hdr", "t_time", "t_load", "t_jstart", "t_prejam", "t_lastbrk", "t_repair",
@@ -87,7 +89,8 @@ class RunResult:
     def __init__(self):
         self.summary = self.ticks = self.trace = self.site_queue_ticks = self.site_tons_ticks = self.orders = None
         self.unit_ticks = None
-        self.tick_capacity = self.trace_capacity = self.order_capacity = 0
+        self.draw_values = self.draw_sites = self.draw_count = None
+        self.tick_capacity = self.trace_capacity = self.order_capacity = self.draw_capacity = 0
 
     def summary_np(self):
         return self.summary.cpu().numpy().view(SUMMARY_DTYPE).reshape(-1)
@@ -102,6 +105,18 @@ class RunResult:
 
     def orders_np(self):
         return self.orders.cpu().numpy()
+
+    def draw_tape(self, inst):
+        """(sites uint8[], values float64[]) of instance ``inst``: every draw of the Philox run in the reference's call order
+        (``run(draw_capacity=...)``), reserved-but-undrawn slots (OM_DRAW_SKIP) removed.  Feeding it back as a tape
+        (``reset(rng_mode="tape", tapes=[...])``, or the reference under ``oracle/ref_harness.py``) replays the trajectory."""
+        n = int(self.draw_count[inst].item())
+        if n > self.draw_capacity:
+            raise RuntimeError("draw tape of instance %d overflowed: %d slots needed, capacity %d" % (inst, n, self.draw_capacity))
+        sites = self.draw_sites[inst, :n].cpu().numpy()
+        values = self.draw_values[inst, :n].cpu().numpy()
+        keep = sites != DRAW_SKIP
+        return sites[keep].copy(), values[keep].copy()
 
 
 class BatchedMine:
@@ -134,6 +149,7 @@ class BatchedMine:
         self._ck(self.lib.om_state_layout(self.h, ctypes.byref(self.layout)))
         self.state = torch.zeros((self.n, self.state_bytes), dtype=torch.uint8, device=self.device)
         self.dispatcher_ids = None
+        self.has_external = False
         self.seeds = None
         self._tape = None
         self.sim_time = self.pc.sim_time
@@ -182,6 +198,7 @@ class BatchedMine:
         seeds = np.asarray(seeds, dtype=np.uint64)
         assert seeds.shape == (self.n,)
         self.dispatcher_ids = torch.from_numpy(ids).to(self.device)
+        self.has_external = bool((ids == DISPATCHER_IDS["external"]).any())
         self.seeds = torch.from_numpy(seeds.view(np.int64)).to(self.device)
         mode = RNG_MODES[rng_mode]
         tv = ts = to = None
@@ -202,9 +219,15 @@ class BatchedMine:
         return self
 
     def run(self, until=None, ticks=True, trace_capacity=0, site_ticks=False, order_capacity=0, result=None,
-            unit_ticks=False):
-        """Advance every instance to simulated time ``until`` (default: the config's sim_time)."""
+            unit_ticks=False, draw_capacity=0):
+        """Advance every instance to simulated time ``until`` (default: the config's sim_time).
+        ``draw_capacity`` > 0 (rng_mode="philox" only): export every instance's draw tape (``RunResult.draw_tape``);
+        ``draw_tape_slots()`` gives a safe size."""
         torch = self.torch
+        if getattr(self, "has_external", False):
+            raise RuntimeError("BatchedMine.run: the batch holds instances of a host-side dispatcher (device id 255); om_run "
+                               "would pause them at their first order and return empty results -- use "
+                               "openmines_b200.run_external(dispatcher, ...) or BatchedMineEnv / step() for those")
         until = float(self.sim_time if until is None else until)
         r = result if result is not None else RunResult()
         if r.summary is None:
@@ -225,8 +248,15 @@ class BatchedMine:
         if order_capacity and r.orders is None:
             r.orders = torch.full((self.n, order_capacity), -1, dtype=torch.int16, device=self.device)
             r.order_capacity = int(order_capacity)
+        if draw_capacity and r.draw_values is None:
+            r.draw_values = torch.zeros((self.n, int(draw_capacity)), dtype=torch.float64, device=self.device)
+            r.draw_sites = torch.full((self.n, int(draw_capacity)), DRAW_SKIP, dtype=torch.uint8, device=self.device)
+            r.draw_count = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+            r.draw_capacity = int(draw_capacity)
         o = OmOutputsStruct()
         ptr = lambda t: t.data_ptr() if t is not None else None
+        o.draw_values, o.draw_sites, o.draw_count = ptr(r.draw_values), ptr(r.draw_sites), ptr(r.draw_count)
+        o.draw_capacity = r.draw_capacity
         o.summary, o.ticks, o.trace = ptr(r.summary), ptr(r.ticks), ptr(r.trace)
         o.tick_capacity, o.trace_capacity = r.tick_capacity, r.trace_capacity
         o.site_queue_ticks, o.site_tons_ticks = ptr(r.site_queue_ticks), ptr(r.site_tons_ticks)
@@ -234,6 +264,13 @@ class BatchedMine:
         o.unit_ticks = ptr(r.unit_ticks)
         self._ck(self.lib.om_run(self.h, until, ctypes.c_void_p(self.state.data_ptr()), ctypes.byref(o), self._stream()))
         return r
+
+    def draw_tape_slots(self, until=None):
+        """Upper estimate of the draw-tape slots one instance needs up to ``until``: two per truck per minute (breakdown
+        block), up to three per road per minute (jam coin / position / duration) and six per truck cycle."""
+        until = float(self.sim_time if until is None else until)
+        minutes = int(np.ceil(until)) + 1
+        return minutes * (2 * self.pc.T + 3 * self.pc.R) + 6 * self.pc.T * (minutes // 4 + 4)
 
     def obs_dim(self):
         d = ctypes.c_int32()
@@ -258,9 +295,10 @@ class BatchedMine:
         self._ck(self.lib.om_step(self.h, until, ctypes.c_void_p(self.state.data_ptr()), ctypes.byref(s), self._stream()))
 
     def stats(self, result):
-        """Per-dispatcher partial sums [6, 16] (float64 device tensor) for the cross-GPU all-reduce."""
+        """Per-dispatcher partial sums [7, 16] (float64 device tensor, integer-valued: exact and order-independent) for the
+        cross-GPU all-reduce; ``openmines_b200.parallel.describe`` decodes them."""
         torch = self.torch
-        out = torch.zeros((6, 16), dtype=torch.float64, device=self.device)
+        out = torch.zeros((7, 16), dtype=torch.float64, device=self.device)
         self._ck(self.lib.om_stats_reduce(self.h, ctypes.c_void_p(result.summary.data_ptr()),
                                           ctypes.c_void_p(self.dispatcher_ids.data_ptr()),
                                           ctypes.c_void_p(out.data_ptr()), self._stream()))

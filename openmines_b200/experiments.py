@@ -21,20 +21,55 @@ from .config import load_config
 from .dispatcher import BUILTIN, by_name
 from .engine import BatchedMine, DISPATCHER_IDS
 from .ticker import TickRecorder
+from .trace import IERR_NAMES
+
+OM_IERR_TRACE_OVERFLOW = 5
 
 
-def run_dispatch_sim(dispatcher, config_file, n_seeds=1, stochastic=True, seeds=None, device=0, want_ticks=True):
-    """N independent runs of ``dispatcher`` (a BaseDispatcher object or a built-in name) on the mine."""
+def default_jam_capacity(config):
+    """Jam-pool size for a mine: 64 entries hold every simultaneously active jam of the 71-truck north_pit mine with margin
+    (tools/jam_capacity_sweep.py); more trucks on the same roads keep more jams alive, so the pool grows with the fleet."""
+    n_trucks = sum(int(t["count"]) for t in load_config(config)["charging_site"]["trucks"])
+    return int(min(4096, max(64, 64 * ((n_trucks + 63) // 64) * 2)))
+
+
+def check_instance_errors(summary, what):
+    """Raise if any instance stopped on an engine error (jam-pool overflow ...) or where the reference itself raises (SQ's
+    KeyError, an out-of-range order): their truncated tonnage must not be averaged into a curve."""
+    bad = np.nonzero((summary["err"] != 0) & (summary["err"] != OM_IERR_TRACE_OVERFLOW))[0]
+    if len(bad):
+        codes = sorted(set(int(e) for e in summary["err"][bad]))
+        raise RuntimeError("%s: %d of %d instances stopped early: %s (first: instance %d)" % (
+            what, len(bad), len(summary), "; ".join("%d = %s" % (c, IERR_NAMES.get(c, "?")) for c in codes), int(bad[0])))
+
+
+def run_dispatch_sim(dispatcher, config_file, n_seeds=1, stochastic=True, seeds=None, device=0, want_ticks=True,
+                     jam_capacity=None):
+    """N independent runs of ``dispatcher`` (a BaseDispatcher object or a built-in name) on the mine.  A user-defined
+    ``BaseDispatcher`` subclass (no device function) is routed to the host-decision path (``run_external``)."""
     cfg = load_config(config_file)
     if isinstance(dispatcher, str):
         dispatcher = by_name(dispatcher)
     seeds = np.arange(n_seeds, dtype=np.uint64) if seeds is None else np.asarray(seeds, dtype=np.uint64)
-    mine = BatchedMine(cfg, len(seeds), device=device)
+    jam_capacity = jam_capacity or default_jam_capacity(cfg)
+    if int(getattr(dispatcher, "device_id", 255)) == DISPATCHER_IDS["external"]:
+        from .external import run_external
+        ext = run_external(dispatcher, cfg, n_instances=len(seeds), seeds=seeds, rng_mode="philox" if stochastic else "det",
+                           device=device, jam_capacity=jam_capacity)
+        bad = np.nonzero((ext["headers"]["err"] != 0) & (ext["headers"]["err"] != OM_IERR_TRACE_OVERFLOW))[0]
+        if len(bad):
+            raise RuntimeError("run_dispatch_sim(%s): instance %d stopped early: %s" % (
+                getattr(dispatcher, "name", type(dispatcher).__name__), int(bad[0]),
+                IERR_NAMES.get(int(ext["headers"]["err"][bad[0]]), "?")))
+        return {"ticks": None, "summary": None, "headers": ext["headers"], "produced_tons": ext["produced_tons"],
+                "mine": ext["mine"], "result": None, "dispatchers": ext["dispatchers"]}
+    mine = BatchedMine(cfg, len(seeds), device=device, jam_capacity=jam_capacity)
     mine.reset(dispatcher, seeds=seeds, rng_mode="philox" if stochastic else "det")
     trace_cap = 16384 if want_ticks else 0
     res = mine.run(trace_capacity=trace_cap, site_ticks=want_ticks, unit_ticks=want_ticks,
                    order_capacity=8192 if want_ticks else 0)
     summary = res.summary_np()
+    check_instance_errors(summary, "run_dispatch_sim(%s)" % dispatcher.name)
     ticks = None
     if want_ticks:
         ticks = TickRecorder(mine, res, dispatcher.name).ticks(0)
@@ -80,18 +115,22 @@ def scaled_fleet_config(config, fleet_size):
     return cfg
 
 
-def scene_based_fleet_ablation(config_file, min_truck, max_truck, dispatchers=None, n_seeds=32, stochastic=True, device=0):
+def scene_based_fleet_ablation_serial(config_file, min_truck, max_truck, dispatchers=None, n_seeds=32, stochastic=True,
+                                      device=0, jam_capacity=None):
+    """One launch per fleet size (the round-1 driver; kept as the baseline the one-launch sweep is measured against)."""
     cfg = load_config(config_file)
     names = dispatchers or [n for n in cfg["dispatcher"]["type"] if n in DISPATCHER_IDS]
     results = {n: {"fleet_sizes": [], "productions": [], "std": []} for n in names}
     for fs in fleet_sizes_for(min_truck, max_truck):
         c = scaled_fleet_config(cfg, fs)
         c["charging_site"]["trucks"] = [t for t in c["charging_site"]["trucks"] if t["count"] > 0]
-        mine = BatchedMine(c, n_seeds * len(names), device=device)
+        mine = BatchedMine(c, n_seeds * len(names), device=device, jam_capacity=jam_capacity or default_jam_capacity(c))
         ids = np.repeat([DISPATCHER_IDS[n] for n in names], n_seeds).astype(np.int32)
         mine.reset(ids, seeds=np.tile(np.arange(n_seeds, dtype=np.uint64), len(names)),
                    rng_mode="philox" if stochastic else "det")
-        s = mine.run(ticks=True).summary_np().reshape(len(names), n_seeds)
+        s = mine.run(ticks=True).summary_np()
+        check_instance_errors(s, "scene_based_fleet_ablation(fleet size %d)" % fs)
+        s = s.reshape(len(names), n_seeds)
         for k, n in enumerate(names):
             results[n]["fleet_sizes"].append(fs)
             results[n]["productions"].append(float(s[k]["reported_tons"].mean()))

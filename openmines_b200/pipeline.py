@@ -59,6 +59,7 @@ class EpisodePipeline:
         self.d_seeds[s].copy_(self.h_seeds[s], non_blocking=True)
         self.d_disp[s].copy_(self.h_disp[s], non_blocking=True)
         mine.dispatcher_ids, mine.seeds = self.d_disp[s], self.d_seeds[s]
+        mine.has_external = bool((self.h_disp[s].numpy() == 255).any())
         mine._ck(mine.lib.om_reset(mine.h, self.d_seeds[s].data_ptr(), self.d_disp[s].data_ptr(), self.mode,
                                    None, None, None, mine.state.data_ptr(), mine._stream()))
         if len(self.results) <= s:

@@ -39,8 +39,14 @@ def _spaces(n_actions, obs_dim):
 
 class BatchedMineEnv:
     def __init__(self, config, num_envs, device=0, rng_mode="philox", sug_dispatcher="ShortestTripDispatcher",
-                 auto_reset=False, jam_capacity=64, reward_mode="dense"):
+                 auto_reset=False, jam_capacity=64, reward_mode="dense", copy_outputs=False):
+        """``copy_outputs``: ``reset()`` / ``step()`` return the engine's OWN output buffers (``env.io[...]``), which the next
+        ``step()`` overwrites in place -- zero-copy, what a fused rollout loop wants, but a trainer that stores the returned
+        ``obs`` / ``reward`` / ``terminated`` / ``info`` tensors in a rollout buffer without ``.clone()`` would see every
+        stored step turn into the latest one.  ``copy_outputs=True`` returns fresh tensors every call instead (one extra
+        device copy of N x (obs_dim x 4 + 41) bytes per step)."""
         import torch
+        self.copy_outputs = bool(copy_outputs)
         self.torch = torch
         self.mine = BatchedMine(config, num_envs, device=device, jam_capacity=jam_capacity, rl_surface=True)
         self.num_envs = int(num_envs)
@@ -71,10 +77,14 @@ class BatchedMineEnv:
         self._seeds = None
         self._tapes = None
 
+    def _out(self, t):
+        return t.clone() if self.copy_outputs else t
+
     def _info(self):
-        io = self.io
-        return {"produce_tons": io["info"][:, 0], "time": io["info"][:, 1], "delta_time": io["info"][:, 2],
-                "sug_action": io["sug_action"], "order_kind": io["order_kind"], "truck": io["truck"],
+        io, o = self.io, self._out
+        info = o(io["info"])
+        return {"produce_tons": info[:, 0], "time": info[:, 1], "delta_time": info[:, 2],
+                "sug_action": o(io["sug_action"]), "order_kind": o(io["order_kind"]), "truck": o(io["truck"]),
                 "load_num": self.mine.pc.L, "unload_num": self.mine.pc.D}
 
     def reset(self, seed=None, tapes=None):
@@ -92,7 +102,7 @@ class BatchedMineEnv:
         if self.auto_reset:
             self.io["episode_totals"].zero_()
         self._step(None)
-        return self.io["obs"], self._info()
+        return self._out(self.io["obs"]), self._info()
 
     def _step(self, a):
         self.mine.step(a, self.io, teacher=self.teacher, auto_reset=self.auto_reset, seed_stride=self.num_envs,
@@ -107,7 +117,10 @@ class BatchedMineEnv:
         the FIRST observation of the next episode; ``info["final_observation"]`` holds the terminal observation rows and
         ``info["episode_totals"]`` the per-env counts of finished episodes / their truck events / their decisions.
         The next episode's seed is the previous one + num_envs.  Without it, finished envs idle (reward 0,
-        ``terminated=True``) until the caller resets the batch."""
+        ``terminated=True``) until the caller resets the batch.
+
+        ALIASING: unless the env was built with ``copy_outputs=True`` the returned tensors are views of ``env.io`` and are
+        overwritten by the next ``step()``; ``.clone()`` what you keep."""
         torch = self.torch
         a = actions.to(device=self.mine.device, dtype=torch.int32).contiguous()
         self._step(a)
@@ -115,9 +128,9 @@ class BatchedMineEnv:
         truncated = torch.zeros_like(terminated)
         info = self._info()
         if self.auto_reset:
-            info["final_observation"] = self.io["final_obs"]
-            info["episode_totals"] = self.io["episode_totals"]
-        return self.io["obs"], self.io["reward"], terminated, truncated, info
+            info["final_observation"] = self._out(self.io["final_obs"])
+            info["episode_totals"] = self._out(self.io["episode_totals"])
+        return self._out(self.io["obs"]), self._out(self.io["reward"]), terminated, truncated, info
 
     def capture_rollout_step(self, policy, sample=None, warmup=3):
         """Capture ONE rollout iteration -- policy forward on the current observation, action sampling, ``om_step``

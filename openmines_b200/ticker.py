@@ -64,6 +64,11 @@ class TickRecorder:
         self.pc = mine.pc
         self.cfg = mine.pc.raw
         self.dispatcher_name = dispatcher_name
+        if result.summary is not None:
+            err = result.summary_np()["err"]
+            if (err == 5).any():          # OM_IERR_TRACE_OVERFLOW: truck states would be rebuilt from a truncated event trace
+                raise RuntimeError("TickRecorder: the event trace of instance %d overflowed its buffer (trace_capacity %d); "
+                                   "run again with a larger trace_capacity" % (int(np.nonzero(err == 5)[0][0]), result.trace_capacity))
         cfg, pc = self.cfg, self.pc
         self.charging_pos = list(cfg["charging_site"]["position"])
         self.site_pos, self.park_pos = {}, {}

@@ -55,6 +55,61 @@ def trace_diffs(ref, got, rel_time_tol=0.0):
     return diffs
 
 
+class HostResult:
+    """Host copy of a RunResult (one device->host transfer per output instead of one per compared instance); quacks like
+    RunResult for ``engine_vs_ref``."""
+
+    def __init__(self, mine, result):
+        self._r = result
+        for f in ("summary", "ticks", "trace", "site_queue_ticks", "site_tons_ticks", "orders", "unit_ticks",
+                  "draw_values", "draw_sites", "draw_count"):
+            t = getattr(result, f)
+            setattr(self, f, t.cpu() if t is not None else None)
+        for f in ("tick_capacity", "trace_capacity", "order_capacity", "draw_capacity"):
+            setattr(self, f, getattr(result, f))
+        self.state = mine.state.cpu().numpy()
+        self._summary = self.summary.numpy().view(type(result).summary_np(result).dtype).reshape(-1)
+        self._ticks = result.ticks_np() if result.ticks is not None else None
+
+    def summary_np(self):
+        return self._summary
+
+    def ticks_np(self):
+        return self._ticks
+
+    def trace_np(self, inst):
+        from openmines_b200.trace import TRACE_DTYPE
+        return self.trace[inst].numpy().view(TRACE_DTYPE).reshape(-1), self._summary[inst]
+
+    def orders_np(self):
+        return self.orders.numpy()
+
+    def draw_tape(self, inst):
+        n = int(self.draw_count[inst])
+        assert n <= self.draw_capacity, "draw tape overflow: %d > %d" % (n, self.draw_capacity)
+        sites, values = self.draw_sites[inst, :n].numpy(), self.draw_values[inst, :n].numpy()
+        keep = sites != 255
+        return sites[keep].copy(), values[keep].copy()
+
+
+def _replay_job(job):
+    """Worker of ``oracle_replays``: one tape replay through the CPU restatement."""
+    from oracle import des_oracle as do
+    cfg, dispatcher, tape, kw = job
+    return do.run_oracle(cfg, dispatcher, "replay", tape=tape, **kw)
+
+
+def oracle_replays(jobs, procs=None):
+    """Run ``(config, dispatcher, tape, kwargs)`` replays of the CPU oracle on the host cores (spawned workers: the parent
+    holds a CUDA context).  Returns the OracleResult objects in job order."""
+    import multiprocessing as mp
+    procs = procs or max(1, min(len(jobs), os.cpu_count() or 1, 32))
+    if procs == 1:
+        return [_replay_job(j) for j in jobs]
+    with mp.get_context("spawn").Pool(procs) as pool:
+        return pool.map(_replay_job, jobs, chunksize=max(1, len(jobs) // (procs * 4)))
+
+
 def engine_vs_ref(ref, mine, result, inst, sptf=False):
     """All differences between a reference/oracle result object and instance `inst` of an engine run."""
     diffs = []
@@ -88,7 +143,7 @@ def engine_vs_ref(ref, mine, result, inst, sptf=False):
         st = result.site_tons_ticks[inst].cpu().numpy()[:nt]
         if not np.array_equal(ref.tick["site_tons"], st):
             diffs.append("tick[site_tons] differs")
-    sa = mine.state_arrays(inst)
+    sa = mine.state_arrays(inst, blob=result.state[inst]) if isinstance(result, HostResult) else mine.state_arrays(inst)
     S = mine.pc.S
     checks = [("truck_total_load", sa["t_total"]), ("truck_service_count", sa["t_svc"]),
               ("truck_cycle_time", sa["t_cycle"]), ("truck_status", sa["t_status"]), ("truck_cur", sa["t_cur"]),

@@ -149,3 +149,113 @@ def test_limits_mine_32_sites_32_units_per_site_vs_oracle():
     res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=4096)
     diffs = engine_vs_ref(live, mine, res, 0)
     assert not diffs, diffs[:5]
+
+
+def test_more_than_32_units_per_site_vs_oracle():
+    """40 shovels at one load site and 40 dumpers at one dump site: get_available_shovel / get_available_dumper
+    (load_site.py:209-220, dump_site.py:105-116) take a second lane trip.  det Naive (every truck to the 40-shovel site, so
+    the first idle unit is found in the second trip once 32 are busy) / SQ / SPTF bit-exact vs the oracle + a tape replay."""
+    from oracle import des_oracle as do
+    from helpers import engine_vs_ref
+    from test_host_side import _limits_mine
+    import openmines_b200 as om
+    cfg = _limits_mine(n_load=6, n_dump=5, units_site0=40)
+    cases = [("NaiveDispatcher", 0), ("SQDispatcher", 0), ("SPTFDispatcher", 0)]
+    oracles = [do.run_oracle(cfg, d, "det", seed=s) for d, s in cases]
+    mine = om.BatchedMine(cfg, len(cases), jam_capacity=256)
+    mine.reset([d for d, _ in cases], seeds=[s for _, s in cases], rng_mode="det")
+    res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=4096)
+    for i, (d, s) in enumerate(cases):
+        diffs = engine_vs_ref(oracles[i], mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s: %s" % (d, diffs[:5])
+    # the second lane trip was taken: some shovel / dumper beyond the first 32 of site 0 served trucks
+    sa = mine.state_arrays(0)
+    assert sa["u_svc"][32:40].sum() > 0
+    live = do.run_oracle(cfg, "NaiveDispatcher", "live", seed=1)
+    mine = om.BatchedMine(cfg, 1, jam_capacity=256)
+    mine.reset("NaiveDispatcher", rng_mode="tape", tapes=[live.tape])
+    res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=4096)
+    diffs = engine_vs_ref(live, mine, res, 0)
+    assert not diffs, diffs[:5]
+
+
+def test_older_handle_survives_a_smaller_one(north_pit):
+    """The kernels' dynamic shared-memory limit is a per-process function attribute: a second, smaller handle must not
+    lower it under a live, larger one (a 4096-env training env followed by a small eval env, run_external(n=1) ...)."""
+    import openmines_b200 as om
+    big = om.BatchedMine(north_pit, 4096)
+    big.reset("SQDispatcher", rng_mode="philox")
+    small = om.BatchedMine(north_pit, 1)
+    small.reset("SQDispatcher", rng_mode="philox")
+    a = small.run(until=30.0).summary_np()
+    assert big.launch_info()["smem_bytes"] > small.launch_info()["smem_bytes"]
+    b = big.run(until=30.0).summary_np()           # used to fail with cudaErrorInvalidValue
+    assert (b["err"] == 0).all() and b["reported_tons"][0] == a["reported_tons"][0]
+
+
+def test_run_refuses_host_side_dispatchers(north_pit):
+    """om_run on instances of a user-defined (host-side) dispatcher would pause them at their first order and return empty
+    results: BatchedMine.run raises and points to run_external; run_dispatch_sim routes such dispatchers there."""
+    import openmines_b200 as om
+    from openmines_b200 import experiments
+
+    class AlwaysFirst(om.BaseDispatcher):
+        def __init__(self):
+            super().__init__()
+            self.name = "AlwaysFirst"
+
+        def give_init_order(self, truck, mine):
+            return 0
+
+        give_haul_order = give_back_order = give_init_order
+
+    mine = om.BatchedMine(north_pit, 2)
+    mine.reset(AlwaysFirst(), rng_mode="det")
+    with pytest.raises(RuntimeError, match="run_external"):
+        mine.run()
+    short = dict(north_pit, sim_time=30)
+    out = experiments.run_dispatch_sim(AlwaysFirst(), short, n_seeds=2, stochastic=False)
+    ref = experiments.run_dispatch_sim("NaiveDispatcher", short, n_seeds=2, stochastic=False, want_ticks=False)
+    assert np.array_equal(out["produced_tons"], ref["summary"]["reported_tons"])     # both always answer 0
+
+
+def test_stats_are_exact_and_order_independent(north_pit):
+    """om_stats_reduce accumulates integers (fixed-point tonnages): bit-identical to the numpy mirror, identical for a
+    shuffled instance order, identical when the batch is cut into 'rank' shards whose partial statistics are added in any
+    order -- i.e. all-reduced N-rank totals equal the single-GPU totals over the same global instance ids.  ShortestTrip
+    (dispatcher id 6) has its own row."""
+    import openmines_b200 as om
+    from openmines_b200 import parallel
+    n = 1400
+    ids = (np.arange(n) % 7).astype(np.int32)
+    seeds = np.arange(n, dtype=np.uint64) + 11
+    mine = om.BatchedMine(north_pit, n)
+    mine.reset(ids, seeds=seeds, rng_mode="philox")
+    res = mine.run(until=120.0)
+    s = res.summary_np()
+    got = mine.stats(res).cpu().numpy()
+    again = mine.stats(res).cpu().numpy()
+    want = parallel.stats_from_summaries(s, ids)
+    assert got.shape == (7, 16) and np.array_equal(got, want) and np.array_equal(got, again)
+    assert (got == np.rint(got)).all() and got[6, 0] == 200
+    rows = parallel.describe(got)
+    for d, name in enumerate(parallel.DISPATCHER_NAMES):
+        t = s["reported_tons"][ids == d]
+        assert abs(rows[name]["mean_tons"] - t.mean()) <= 1e-6 and abs(rows[name]["std_tons"] - t.std()) <= 0.05
+    # shuffled placement
+    perm = np.random.default_rng(3).permutation(n)
+    m2 = om.BatchedMine(north_pit, n)
+    m2.reset(ids[perm], seeds=seeds[perm], rng_mode="philox")
+    assert np.array_equal(m2.stats(m2.run(until=120.0)).cpu().numpy(), got)
+    # 8 "ranks": partial statistics of contiguous shards, summed in two different orders
+    parts = []
+    for r in range(8):
+        lo, hi = parallel.shard_range(n, 8, r)
+        mr = om.BatchedMine(north_pit, hi - lo)
+        mr.reset(ids[lo:hi], seeds=seeds[lo:hi], rng_mode="philox")
+        parts.append(mr.stats(mr.run(until=120.0)).cpu().numpy())
+    fwd = np.zeros_like(got)
+    for p in parts:
+        fwd = fwd + p
+    tree = ((parts[7] + parts[3]) + (parts[5] + parts[1])) + ((parts[6] + parts[2]) + (parts[4] + parts[0]))
+    assert np.array_equal(fwd, got) and np.array_equal(tree, got)

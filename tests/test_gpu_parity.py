@@ -184,7 +184,7 @@ def test_stats_kernel_matches_host_mirror(north_pit):
     res = mine.run(until=90.0)
     got = mine.stats(res).cpu().numpy()
     want = parallel.stats_from_summaries(res.summary_np(), ids)
-    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    assert np.array_equal(got, want)            # integer accumulation: exact
     rows = parallel.describe(got)
     assert set(rows) == set(DISPATCHERS) and all(r["instances"] == 100 for r in rows.values())
 

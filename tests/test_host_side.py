@@ -71,7 +71,12 @@ def test_c_abi_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     from openmines_b200.engine import OmOutputsStruct, OmStateLayoutStruct
     from openmines_b200.trace import SUMMARY_DTYPE, TICK_DTYPE, TRACE_DTYPE
-    assert ctypes.sizeof(OmOutputsStruct) == 72
+    assert ctypes.sizeof(OmOutputsStruct) == 104
+    info = _lib.abi_info()
+    assert info["abi_version"] == cfgmod.OM_ABI_VERSION
+    assert info["sizeof_OmOutputs"] == ctypes.sizeof(OmOutputsStruct)
+    assert info["sizeof_OmStateLayout"] == ctypes.sizeof(OmStateLayoutStruct)
+    assert info["sizeof_OmConfig"] == ctypes.sizeof(cfgmod.OmConfigStruct)
     assert ctypes.sizeof(OmStateLayoutStruct) == 4 * 56
     assert ctypes.sizeof(cfgmod.OmConfigStruct) == 12 * 4 + 14 * 8 + 14 * 8
     assert (TRACE_DTYPE.itemsize, TICK_DTYPE.itemsize, SUMMARY_DTYPE.itemsize) == (32, 32, 64)
@@ -159,8 +164,9 @@ def _limits_mine(n_load=16, n_dump=16, units_site0=32):
 
 
 def test_om_create_rejects_mines_beyond_the_engine_limits():
-    """More than 32 sites or more than 32 shovels / dumpers at one site: OM_E_UNSUPPORTED with a message, checked before
-    any CUDA call (so this runs without a GPU); an ABI version mismatch and an empty mine: OM_E_INVALID."""
+    """More than 32 sites: OM_E_UNSUPPORTED with a message, checked before any CUDA call (so this runs without a GPU); an
+    ABI version mismatch, an empty mine and out-of-range index tables: OM_E_INVALID.  More than 32 shovels / dumpers at one
+    site is supported (unit selection takes one lane trip per 32 units)."""
     lib = _lib.load()
 
     def create(cfg=None, mutate=None):
@@ -174,7 +180,20 @@ def test_om_create_rejects_mines_beyond_the_engine_limits():
     rc, msg = create(_limits_mine(n_load=17, n_dump=16))
     assert rc == -4 and b"L + D <= 32" in msg
     rc, msg = create(_limits_mine(units_site0=33))
-    assert rc == -4 and b"1..32" in msg
+    assert rc == -2 and b"no CUDA device" in msg          # accepted by the argument checks; only the GPU is missing here
+    import numpy as np
+
+    def bad_table(name, value):
+        def mutate(s):
+            arr = np.array([value] * 400, dtype=np.int32)
+            mutate.keep = arr
+            setattr(s, name, arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+        return mutate
+    for name, value in (("truck_type", 99), ("fixed_group", -1), ("nearest_haul", 16), ("nearest_back", 77)):
+        rc, msg = create(mutate=bad_table(name, value))
+        assert rc == -1 and b"out of range" in msg, (name, rc, msg)
+    rc, msg = create(mutate=lambda s: setattr(s, "nearest_init", 16))
+    assert rc == -1 and b"nearest_init" in msg
     rc, msg = create(mutate=lambda s: setattr(s, "abi_version", 1))
     assert rc == -1 and b"ABI" in msg
     rc, msg = create(mutate=lambda s: setattr(s, "n_trucks", 0))

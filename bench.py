@@ -30,7 +30,55 @@ METRIC = "simulated truck-events/sec (north_pit_mine)"   # c5 runs the synthetic
 UNIT = "truck-events/s"
 
 
+# CPU port (oracle/des_oracle.py) vs the UNMODIFIED reference on the same workload, same core: seconds per episode of the
+# reference divided by the port's, measured in the authoring container by tools/measure_reference_factor.py (BASELINE.md
+# section 5).  The reference arm's throughput divided by this factor estimates the unmodified reference on the same cores.
+REFERENCE_FACTOR = None      # filled from BASELINE measurements below
+try:
+    with open(os.path.join(ROOT, "profiles", "reference_factor.json")) as _fh:
+        REFERENCE_FACTOR = json.load(_fh)
+except Exception:
+    REFERENCE_FACTOR = None
+
 _REAL_STDOUT = None
+
+COUNTER_METRICS = ["smsp__inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+                   "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__cycles_active.avg"]
+
+
+def live_counters(device_index, launch, sync):
+    """Hardware counters of the kernels `launch()` enqueues, read in-process through CUPTI (tools/counters/om_counters.cpp:
+    range profiler, one range per kernel, kernel replay).  Called AFTER the timed region; returns {metric: value} of the
+    launch with the most executed instructions (the episode / step kernel) plus "source", or {"error": ...}."""
+    import ctypes
+    path = os.path.join(ROOT, "tools", "counters", "libom_counters.so")
+    try:
+        lib = ctypes.CDLL(path)
+    except OSError as e:
+        return {"error": "libom_counters.so not loadable: %s" % e}
+    lib.omc_last_error.restype = ctypes.c_char_p
+    names = (ctypes.c_char_p * len(COUNTER_METRICS))(*[m.encode() for m in COUNTER_METRICS])
+    max_ranges = 16
+    sync()
+    if lib.omc_begin(int(device_index), names, len(COUNTER_METRICS), max_ranges) != 0:
+        return {"error": lib.omc_last_error().decode()}
+    try:
+        launch()
+        sync()
+    finally:
+        vals = (ctypes.c_double * (max_ranges * len(COUNTER_METRICS)))()
+        nr = ctypes.c_int(0)
+        rc = lib.omc_end(vals, max_ranges, ctypes.byref(nr))
+    if rc != 0:
+        return {"error": lib.omc_last_error().decode()}
+    rows = [[vals[r * len(COUNTER_METRICS) + m] for m in range(len(COUNTER_METRICS))] for r in range(min(nr.value, max_ranges))]
+    if not rows:
+        return {"error": "no kernel range collected"}
+    top = max(rows, key=lambda r: r[0])
+    out = dict(zip(COUNTER_METRICS, top))
+    out["kernels_in_range"] = len(rows)
+    out["source"] = "CUPTI range profiler in this process, after the timed region (tools/counters/om_counters.cpp)"
+    return out
 
 
 def _quiet_stdout():
@@ -53,7 +101,7 @@ def emit_line(line):
 
 
 def load_cfg(name="north_pit_mine"):
-    with open(os.path.join(ROOT, "tests", "golden", "configs", name + ".json"), encoding="utf-8") as fh:
+    with open(os.path.join(ROOT, "openmines_b200", "conf", name + ".json"), encoding="utf-8") as fh:
         return json.load(fh)
 
 
@@ -168,6 +216,14 @@ def cpu_sample(workload_name, episodes_per_core, cores=None):
             "events_per_s": ev / wall, "episodes_per_s": n / wall}
 
 
+def _factor_note():
+    if not REFERENCE_FACTOR:
+        return ""
+    return ("; the port runs %.2fx faster per core than the unmodified reference on this workload (measured in the "
+            "authoring container, %s), so the unmodified reference would score about value / %.2f" % (
+                REFERENCE_FACTOR["port_speedup"], REFERENCE_FACTOR["how"], REFERENCE_FACTOR["port_speedup"]))
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -184,13 +240,14 @@ def run_reference_arm(a):
     _, _, _, desc = workload(a.workload, a.instances, 0)
     sample = "%d episodes per step (%d per core x %d processes) of the same workload, oracle/des_oracle.py " \
              "(pure-Python port of the reference's SimPy path; the reference itself is Python and needs SimPy, " \
-             "which is not installed)" % (per_core * cores, per_core, cores)
+             "which is not installed)%s" % (per_core * cores, per_core, cores, _factor_note())
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1000 * sum(walls) / len(walls), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "sim_time": 240},
             "episodes_per_s": sum(eps) / len(eps),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": dict({"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                                 **({"reference_factor": REFERENCE_FACTOR["port_speedup"]} if REFERENCE_FACTOR else {})),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_line(line)
 
@@ -363,6 +420,45 @@ def run_c4(a):
 
 
 # ------------------------------------------------------------------------------------------------
+# extra: the reference's fleet-size sweep (cli/run.py:283-362) as ONE mixed-config launch vs one launch per fleet size
+# ------------------------------------------------------------------------------------------------
+def run_ablation(a):
+    import numpy as np
+    import torch
+    from openmines_b200 import experiments as ex
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    cfg = load_cfg()
+    names = ["NaiveDispatcher", "RandomDispatcher", "NearestDispatcher", "FixedGroupDispatcher", "SPTFDispatcher", "SQDispatcher"]
+    n_seeds = a.instances or 32
+    lo, hi = 10, 160
+
+    def timed(fn):
+        for _ in range(a.warmup):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            out = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / a.steps, out
+
+    t_one, r_one = timed(lambda: ex.scene_based_fleet_ablation(cfg, lo, hi, dispatchers=names, n_seeds=n_seeds, device=local))
+    t_ser, r_ser = timed(lambda: ex.scene_based_fleet_ablation_serial(cfg, lo, hi, dispatchers=names, n_seeds=n_seeds, device=local))
+    same = all(r_one[k]["productions"] == r_ser[k]["productions"] for k in names)
+    episodes = 10 * len(names) * n_seeds
+    line = {"metric": "fleet-ablation sweep wall time (north_pit_mine, 10 fleet sizes x 6 dispatchers x %d seeds)" % n_seeds,
+            "value": t_one, "unit": "s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * t_one,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "scene_based_fleet_ablation: fleet sizes %s, %d instances, stochastic events on; wall time "
+                                   "includes config packing, om_create_multi, reset, run and the summary copy" % (
+                                       ex.fleet_sizes_for(lo, hi), episodes)},
+            "one_launch_s": t_one, "serial_launches_s": t_ser, "speedup": t_ser / t_one, "identical_results": bool(same),
+            "episodes_per_s": episodes / t_one}
+    emit_line(line)
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def main():
@@ -371,9 +467,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5", "ablation"])
     ap.add_argument("--instances", type=int, default=0, help="instances per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-counters", action="store_true", help="skip the CUPTI counter pass after the timed region")
     ap.add_argument("--no-graph", action="store_true", help="c4: launch the rollout iteration eagerly instead of replaying a CUDA graph")
     a = ap.parse_args()
     _quiet_stdout()
@@ -381,6 +478,8 @@ def main():
         return run_reference_arm(a)
     if a.workload == "c4":
         return run_c4(a)
+    if a.workload == "ablation":
+        return run_ablation(a)
 
     import numpy as np
     import torch
@@ -511,6 +610,10 @@ def main():
     d2h = pipe.d2h_bytes
 
     # ---- roofline of the dominant kernel (om_run_kernel) --------------------------------------
+    # The episode kernel keeps each instance's state in shared memory for the whole episode, so its HBM traffic is ~0 by
+    # construction; what bounds it is warp-instruction issue.  Primary figure: executed warp
+    # instructions per launch (read live from the hardware counters after the timed region) / the kernel's event-timed
+    # duration / (148 SMs x 4 schedulers x SM clock).  The HBM figure is reported beside it.
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -519,31 +622,51 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = n * (2 * mine.state_bytes + T * 32 + 64)  # state in + out, tick KPI records, summary
-    achieved = alg_bytes / (kern_ms / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": "om_run_kernel<%s>" % mode, "kernel_ms": kern_ms,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "episode-resident DES: state lives in shared memory for the whole episode, so HBM traffic is "
-                        "~0 by construction; the limiter is warp-instruction issue / dependent-chain latency "
-                        "(see profiles/ for smsp__inst_executed and issue-active from ncu)"}
-
-    # ncu-derived counters of the same kernel/workload (profiles/kernel_counters.json): DRAM traffic per launch and the
-    # warp-instruction issue rate, which is what actually bounds this kernel
-    try:
-        with open(os.path.join(ROOT, "profiles", "kernel_counters.json")) as fh:
-            kc = json.load(fh).get(a.workload)
-    except Exception:
-        kc = None
-    if kc:
+    achieved_hbm = alg_bytes / (kern_ms / 1000.0) / 1e9
+    counters = {"error": "skipped"}
+    if rank == 0 and not a.no_counters:
+        def _launch():
+            mine.run(result=res)
+        mine._ck(mine.lib.om_reset(mine.h, mine.seeds.data_ptr(), mine.dispatcher_ids.data_ptr(),
+                                   om.engine.RNG_MODES[mode], None, None, None, mine.state.data_ptr(), mine._stream()))
+        counters = live_counters(local, _launch, torch.cuda.synchronize)
+    kc = None
+    if "error" in counters:
+        # fallback: the committed ncu capture of the same kernel / workload, scaled by the instance count
+        try:
+            with open(os.path.join(ROOT, "profiles", "kernel_counters.json")) as fh:
+                kc = json.load(fh).get(a.workload)
+        except Exception:
+            kc = None
+    sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    peak_issue = sms * 4 * sm_mhz * 1e6
+    inst = traffic = None
+    if "error" not in counters:
+        inst = counters["smsp__inst_executed.sum"]
+        traffic = counters["dram__bytes_read.sum"] + counters["dram__bytes_write.sum"]
+        src = counters["source"]
+    elif kc:
         scale = n / float(kc["instances"])
-        roofline["traffic"] = (kc["dram__bytes_read.sum"] + kc["dram__bytes_write.sum"]) * scale
-        sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
         inst = kc["smsp__inst_executed.sum"] * scale
-        peak_issue = 148 * 4 * sm_mhz * 1e6
-        roofline["issue"] = {"warp_inst_per_launch": inst, "achieved_inst_per_s": inst / (kern_ms / 1000.0),
-                             "peak_inst_per_s": peak_issue, "frac": inst / (kern_ms / 1000.0) / peak_issue,
-                             "source": kc["source"] + " (instruction count from the committed ncu capture, kernel time live)"}
+        traffic = (kc["dram__bytes_read.sum"] + kc["dram__bytes_write.sum"]) * scale
+        src = kc["source"] + " (committed ncu capture scaled by the instance count; live counters unavailable: %s)" % counters["error"]
+    hbm_part = {"achieved": achieved_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_hbm / hbm_peak,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
+    if inst is not None:
+        ach = inst / (kern_ms / 1000.0)
+        roofline = {"bound": "issue", "achieved": ach, "peak": peak_issue, "unit": "warp-inst/s", "frac": ach / peak_issue,
+                    "traffic": traffic, "kernel": "om_run_kernel<%s>" % mode, "kernel_ms": kern_ms,
+                    "warp_inst_per_launch": inst, "counter_source": src,
+                    "peak_source": "%d SMs x 4 schedulers x %.0f MHz (median SM clock sampled during the timed region)" % (sms, sm_mhz),
+                    "issue_active_pct": counters.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "hbm": hbm_part,
+                    "note": "episode-resident DES: state lives in shared memory for the whole episode, HBM traffic ~0 by "
+                            "construction (hbm.frac); the limiter is warp-instruction issue / dependent-chain latency"}
+    else:
+        roofline = dict(hbm_part, bound="hbm", traffic=None, kernel="om_run_kernel<%s>" % mode, kernel_ms=kern_ms,
+                        note="instruction counters unavailable (%s): only the HBM figure, which is ~0 by construction" % counters["error"])
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -564,7 +687,10 @@ def main():
             line["cpu_baseline"] = {"value": s["events_per_s"], "unit": UNIT, "cores": s["cores"], "kind": "port",
                                     "episodes_per_s": s["episodes_per_s"],
                                     "sample": "%d episodes of the same workload (%.1f s wall) on %d host processes, "
-                                              "oracle/des_oracle.py" % (s["episodes"], s["wall_s"], s["cores"])}
+                                              "oracle/des_oracle.py%s" % (s["episodes"], s["wall_s"], s["cores"], _factor_note())}
+            if REFERENCE_FACTOR:
+                line["cpu_baseline"]["reference_factor"] = REFERENCE_FACTOR["port_speedup"]
+                line["cpu_baseline"]["unmodified_reference_estimate"] = s["events_per_s"] / REFERENCE_FACTOR["port_speedup"]
         emit_line(line)
     if dist is not None:
         dist.destroy_process_group()

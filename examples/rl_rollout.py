@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=256)
     a = ap.parse_args()
-    cfg = om.load_config(os.path.join(ROOT, "tests", "golden", "configs", "north_pit_mine.json"))
+    cfg = om.load_config(os.path.join(ROOT, "openmines_b200", "conf", "north_pit_mine.json"))
     env = BatchedMineEnv(cfg, a.envs, rng_mode="philox", auto_reset=True)
     dev = env.mine.device
     policy = torch.nn.Sequential(torch.nn.Linear(env.obs_dim, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(),

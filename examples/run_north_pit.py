@@ -25,7 +25,7 @@ from openmines_b200.ticker import TickRecorder                 # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("config", nargs="?", default=os.path.join(ROOT, "tests", "golden", "configs", "north_pit_mine.json"))
+    ap.add_argument("config", nargs="?", default=os.path.join(ROOT, "openmines_b200", "conf", "north_pit_mine.json"))
     ap.add_argument("--seeds", type=int, default=64)
     ap.add_argument("--det", action="store_true", help="stochastic events off")
     ap.add_argument("--out", default="results")

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OM_ABI_VERSION 4
+#define OM_ABI_VERSION 6
 
 /* OmConfig.flags */
 #define OM_CFG_RL_SURFACE 1 /* allocate the fields om_step needs (reward windows, minute-sampled site values): bigger
@@ -115,6 +115,9 @@ typedef struct OmConfig {
   double maint_sigma;        /* truck.py:362 (5) */
   double jam_sd;             /* road.py:185  (0.1) */
   double jam_scale;          /* road.py:212  (10, Weibull shape 2) */
+  double sim_time;           /* the mine JSON's sim_time (cli/run.py:111): instances of a MIXED-config batch stop at
+                                min(until, sim_time) of their own config; <= 0: no limit of its own.  One-config handles
+                                ignore it (om_run's `until` rules). */
 } OmConfig;
 
 /* One record per entry the reference appends to an EventPool during env.run (truck.py:143,188,
@@ -243,6 +246,14 @@ typedef struct OmEngine* OmHandle;
 
 /* Replaces building Mine + sites + road (cli/run.py:48-107).  Copies the config to the device. */
 int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* out);
+/* Mixed-config batch ("seed x dispatcher x CONFIG"): n_configs packed mines and, per instance, the index of the one it
+ * simulates (config_id: HOST array [n_instances]).  This is what the reference's fleet-size and scene sweeps
+ * (cli/run.py:283-472: ten fleet sizes x dispatchers [x scenes], one run_dispatch_sim each) become: ONE batch.  All
+ * instances share one state layout, sized for the largest config in every dimension (om_state_layout / om_state_bytes);
+ * instance n uses the first n_trucks / n_shovels ... entries of each array according to ITS config.  Per-site and per-unit
+ * tick outputs have rows of max(L+D) / max(S+M) entries.  om_step is not available on such a handle. */
+int om_create_multi(const OmConfig* const* cfgs, int32_t n_configs, const int32_t* config_id, int64_t n_instances,
+                    int device, OmHandle* out);
 int om_destroy(OmHandle h);
 const char* om_last_error(OmHandle h);
 
@@ -314,6 +325,16 @@ typedef struct OmStepIO {
 } OmStepIO;
 int om_obs_dim(OmHandle h, int32_t* dim);
 int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* stream);
+
+/* Test hooks: the engine's own draw transforms and its jam-position sampler, for statistical tests of the marginal laws.
+ * om_debug_draws: out[i] = transform(Philox(counter i, key seed)) on the device; kind 0 uniform (0,1], 1 exponential(1),
+ *   2 standard normal, 3 Weibull(shape 2), 4 load jitter, 5 randint [0, arg), 6 jam coin.  out: device [n].
+ * om_debug_jam_positions: n_samples draws of the position of a new jam on `road` for instance `inst` as its state blob
+ *   stands (Road.road_jam_sampling's np.random.choice over the 1000-point grid, road.py:185-206); *fallbacks = how often the
+ *   rejection sampler gave up.  out: device [n_samples], fallbacks: device int. */
+int om_debug_draws(int kind, uint64_t seed, uint32_t arg, int64_t n, double* out, void* stream);
+int om_debug_jam_positions(OmHandle h, void* state, int64_t inst, int32_t road, int32_t n_samples, double* out,
+                           int32_t* fallbacks, void* stream);
 
 /* Kernel launch geometry actually used by om_run (for bench.py's launch accounting). */
 int om_launch_info(OmHandle h, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* warps_per_cta);

@@ -4,7 +4,7 @@ Only the hot path of 370025263/openmines is here: stepping many independent mine
 (seed x dispatcher x config) as hand-written sm_100a CUDA behind the reference's own
 dispatcher / Mine.start / gym-step surface.  See DESIGN.md and INTEGRATION.md.
 """
-from .config import pack_config, load_config, PackedConfig          # noqa: F401
+from .config import pack_config, load_config, builtin_config, PackedConfig          # noqa: F401
 from .dispatcher import (BaseDispatcher, NaiveDispatcher, RandomDispatcher, NearestDispatcher,   # noqa: F401
                          FixedGroupDispatcher, SPTFDispatcher, SQDispatcher, ShortestTripDispatcher, by_name)
 from .engine import BatchedMine, RunResult, DISPATCHER_IDS          # noqa: F401

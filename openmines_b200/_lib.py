@@ -48,6 +48,28 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+COUNTERS_SRC = os.path.join(os.path.dirname(_HERE), "tools", "counters", "om_counters.cpp")
+COUNTERS_LIB = os.path.join(os.path.dirname(_HERE), "tools", "counters", "libom_counters.so")
+
+
+def build_counters(force=False):
+    """Measurement helper of bench.py (CUPTI range profiler behind a C ABI, tools/counters/om_counters.cpp): g++ against the
+    toolkit's libcupti.  Best effort -- returns None when the toolkit has no CUPTI; bench.py then falls back to the committed
+    ncu capture."""
+    if not os.path.exists(COUNTERS_SRC):
+        return None
+    if not force and os.path.exists(COUNTERS_LIB) and os.path.getmtime(COUNTERS_LIB) >= os.path.getmtime(COUNTERS_SRC):
+        return COUNTERS_LIB
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-I" + os.path.join(cuda, "include"),
+           "-I" + os.path.join(cuda, "extras", "CUPTI", "include"), COUNTERS_SRC, "-o", COUNTERS_LIB,
+           "-L" + os.path.join(cuda, "lib64"), "-L" + os.path.join(cuda, "extras", "CUPTI", "lib64"),
+           "-L" + os.path.join(cuda, "lib64", "stubs"), "-lcupti", "-lcuda",
+           "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-Wl,-rpath," + os.path.join(cuda, "extras", "CUPTI", "lib64")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return COUNTERS_LIB if r.returncode == 0 else None
+
+
 def load():
     global _lib
     if _lib is not None:
@@ -67,6 +89,7 @@ def load():
     lib.om_last_error.restype = ctypes.c_char_p
     lib.om_last_error.argtypes = [vp]
     lib.om_create.argtypes = [vp, i64, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.om_create_multi.argtypes = [vp, i32, vp, i64, ctypes.c_int, ctypes.POINTER(vp)]
     lib.om_destroy.argtypes = [vp]
     lib.om_state_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     lib.om_state_layout.argtypes = [vp, vp]
@@ -76,9 +99,12 @@ def load():
     lib.om_stats_reduce.argtypes = [vp, vp, vp, vp, vp]
     lib.om_obs_dim.argtypes = [vp, ctypes.POINTER(i32)]
     lib.om_step.argtypes = [vp, dbl, vp, vp, vp]
-    for f in ("om_create", "om_destroy", "om_state_bytes", "om_state_layout", "om_launch_info", "om_reset",
+    for f in ("om_create", "om_create_multi", "om_destroy", "om_state_bytes", "om_state_layout", "om_launch_info", "om_reset",
               "om_run", "om_stats_reduce", "om_obs_dim", "om_step"):
         getattr(lib, f).restype = ctypes.c_int
+    lib.om_debug_draws.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32, i64, vp, vp]
+    lib.om_debug_jam_positions.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
+    lib.om_debug_draws.restype = lib.om_debug_jam_positions.restype = ctypes.c_int
     lib.om_abi_info.argtypes = [ctypes.POINTER(i32), i32]
     lib.om_abi_info.restype = i32
     _lib = lib
@@ -118,5 +144,5 @@ def _check_abi():
                            % (LIB_PATH, bad))
 
 
-EXPORTED_SYMBOLS = ["om_create", "om_destroy", "om_last_error", "om_abi_info", "om_state_bytes", "om_state_layout", "om_reset",
-                    "om_run", "om_stats_reduce", "om_launch_info", "om_obs_dim", "om_step"]
+EXPORTED_SYMBOLS = ["om_create", "om_create_multi", "om_destroy", "om_last_error", "om_abi_info", "om_state_bytes", "om_state_layout", "om_reset",
+                    "om_run", "om_stats_reduce", "om_launch_info", "om_obs_dim", "om_step", "om_debug_draws", "om_debug_jam_positions"]

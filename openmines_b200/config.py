@@ -21,7 +21,7 @@ import math
 
 import numpy as np
 
-OM_ABI_VERSION = 4
+OM_ABI_VERSION = 6
 OM_CFG_RL_SURFACE = 1    # OmConfig.flags: allocate the fields om_step needs (bigger blobs, fewer resident instances)
 
 ROAD_EVENT_DEFAULTS = {            # road.py:37-43
@@ -71,7 +71,7 @@ class OmConfigStruct(ctypes.Structure):
         ("detour_mu", ctypes.c_double), ("detour_sigma", ctypes.c_double), ("breakdown_mean", ctypes.c_double),
         ("repair_mu", ctypes.c_double), ("repair_sigma", ctypes.c_double), ("unrepairable_mean", ctypes.c_double),
         ("maint_mean", ctypes.c_double), ("maint_mu", ctypes.c_double), ("maint_sigma", ctypes.c_double),
-        ("jam_sd", ctypes.c_double), ("jam_scale", ctypes.c_double),
+        ("jam_sd", ctypes.c_double), ("jam_scale", ctypes.c_double), ("sim_time", ctypes.c_double),
     ]
 
 
@@ -104,7 +104,19 @@ class PackedConfig:
         s.unrepairable_mean = 60 * 24 * 7 * 7                                    # truck.py:67
         s.maint_mean, s.maint_mu, s.maint_sigma = 60 * 24, 45, 5                 # truck.py:358,362
         s.jam_sd, s.jam_scale = 0.1, 10                                          # road.py:185,212
+        s.sim_time = float(self.sim_time)
         return s
+
+
+CONF_DIR = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "conf")
+
+
+def builtin_config(name="north_pit_mine"):
+    """A mine config shipped with the package (``openmines_b200/conf``: the reference's ``conf/north_pit_mine.json`` and
+    ``north_pit_mine_short.json``, re-serialised)."""
+    import os
+    with open(os.path.join(CONF_DIR, name + ".json"), "r", encoding="utf-8") as fh:
+        return json.load(fh)
 
 
 def load_config(path_or_dict):

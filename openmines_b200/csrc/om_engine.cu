@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -57,11 +58,12 @@ __device__ __forceinline__ void om_stage_out(unsigned char* g, const unsigned ch
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void om_reset_kernel(DevCfg c, OmStateLayout ly, unsigned char* state, const uint64_t* seeds,
-                                const int32_t* dispatcher, long long n) {
+__global__ void om_reset_kernel(const DevCfg* cfgs, const int32_t* cfg_id, OmStateLayout ly, unsigned char* state,
+                                const uint64_t* seeds, const int32_t* dispatcher, long long n) {
   long long inst = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (inst >= n) return;
   unsigned char* blob = state + (size_t)inst * ly.total_bytes;
+  const DevCfg& c = cfgs[cfg_id ? cfg_id[inst] : 0];
   om_init_state(blob, blob, ly.total_bytes, c, ly, threadIdx.x & 31, seeds[inst], dispatcher[inst]);
 }
 
@@ -95,12 +97,17 @@ __global__ void om_order_kernel(const int32_t* dispatcher, long long n, int32_t*
   for (long long i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&start[om_cost_rank(dispatcher[i])], 1u)] = (int32_t)i;
 }
 
-template <int RNG, bool TRACE, bool SPLIT>
+// MULTI: mixed-config batch (om_create_multi) -- every instance names its config in p.cfg_id; the warp copies that DevCfg
+// (scalars + table pointers, 320 bytes) from the device table into its shared-memory slot behind the state blob, and the
+// simulation reads its config from there instead of the kernel parameters.  The layout is the same for every instance
+// (sized for the largest config).
+#define OM_CFG_SLOT ((uint32_t)((sizeof(DevCfg) + 15u) & ~15u))
+template <int RNG, bool TRACE, bool SPLIT, bool MULTI>
 __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(const __grid_constant__ RunParams p) {
   extern __shared__ __align__(16) unsigned char om_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t staged = SPLIT ? p.ly.hot_bytes : p.ly.total_bytes;   // SPLIT: truck records / jam pool stay in HBM
-  unsigned char* sm = om_smem + (size_t)warp * staged;
+  unsigned char* sm = om_smem + (size_t)warp * (staged + (MULTI ? OM_CFG_SLOT : 0u));
   __shared__ __align__(8) uint64_t om_mbar[OM_MAX_WARPS_PER_CTA];
   uint32_t phase = 0;
   if (lane == 0) om_mbar_init(&om_mbar[warp]);
@@ -117,9 +124,20 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
     unsigned char* g = p.state + (size_t)inst * p.ly.total_bytes;
     om_stage_in(sm, g, staged, &om_mbar[warp], phase, lane);   // one TMA bulk copy
     phase ^= 1u;
-    Sim<RNG, TRACE, false, SPLIT> s(sm, g, p, lane, (long long)inst);
+    const DevCfg* cfg = &p.c;
+    if (MULTI) {
+      DevCfg* wc = (DevCfg*)(sm + staged);
+      const uint32_t* src = (const uint32_t*)(p.cfgs + p.cfg_id[inst]);
+      __syncwarp();
+      #pragma unroll 1
+      for (uint32_t k = lane; k < sizeof(DevCfg) / 4u; k += 32) ((uint32_t*)wc)[k] = __ldg(src + k);
+      __syncwarp();
+      cfg = wc;
+    }
+    Sim<RNG, TRACE, false, SPLIT> s(sm, g, p, *cfg, lane, (long long)inst);
     s.load_hdr(p);
-    s.run(p.until);
+    // mixed-config batches: every instance stops at its own config's sim_time (or the call's `until`, if earlier)
+    s.run((MULTI && cfg->sim_time > 0.0 && cfg->sim_time < p.until) ? cfg->sim_time : p.until);
     s.store_hdr(p);
     if (p.out.summary != nullptr) {
       double dumped = s.dumped_tons();
@@ -157,12 +175,49 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_step_kernel(c
     unsigned char* g = p.state + (size_t)inst * p.ly.total_bytes;
     om_stage_in(sm, g, staged, &om_mbar[warp], phase, lane);   // one TMA bulk copy
     phase ^= 1u;
-    Sim<RNG, false, true, SPLIT> s(sm, g, p, lane, (long long)inst);
+    Sim<RNG, false, true, SPLIT> s(sm, g, p, p.c, lane, (long long)inst);
     s.load_hdr(p);
     s.rl_step(p);
     s.store_hdr(p);
     om_stage_out(g, sm, staged, lane);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hooks (om_debug_*): the engine's own draw transforms and jam-position sampler, exposed so that the statistical tests
+// can look at the marginal law of a single draw site (tests/test_gpu_rng_marginals.py)
+// ------------------------------------------------------------------------------------------------
+__global__ void om_debug_draws_kernel(int kind, uint64_t seed, uint32_t arg, long long n, double* out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)kind, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  double v;
+  switch (kind) {
+    case 0: v = (double)om_u01(r.x); break;                                              // uniform (0, 1]
+    case 1: v = (double)om_exp1(r.x); break;                                             // exponential, mean 1
+    case 2: v = (double)om_normal_fast(r.x, r.y); break;                                 // standard normal
+    case 3: v = (double)sqrtf(om_exp1(r.z)); break;                                      // Weibull(shape 2), scale 1
+    case 4: v = -0.1 + 0.2 * (double)om_u01(r.x); break;                                 // load jitter
+    case 5: v = (double)om_randint(r.x, arg); break;                                     // randint [0, arg)
+    case 6: v = (double)((float)(r.y >> 8) * 5.9604644775390625e-08f); break;            // jam coin [0, 1)
+    default: v = 0.0;
+  }
+  out[i] = v;
+}
+
+// one warp: n_samples jam positions on road `rid` of instance `inst` as it stands in `state` (epoch = sample index)
+__global__ void om_debug_jam_kernel(RunParams p, long long inst, int rid, int n_samples, double* out, int* fallbacks) {
+  const int lane = threadIdx.x & 31;
+  unsigned char* blob = p.state + (size_t)inst * p.ly.total_bytes;
+  Sim<OM_RNG_PHILOX, false, false, false> s(blob, blob, p, p.c, lane, inst);
+  s.load_hdr(p);
+  const uint32_t n_on = s.debug_trucks_on_road(rid);
+  int fb = 0;
+  for (int k = 0; k < n_samples; ++k) {
+    double pos = (n_on >= 1) ? s.template sample_jam_position<true>(k, rid, n_on, &fb) : -1.0;
+    if (lane == 0) out[k] = pos;
+  }
+  if (lane == 0 && fallbacks) *fallbacks = fb;
 }
 
 #define OM_STATS_PER_DISP 16
@@ -241,7 +296,11 @@ __global__ void __launch_bounds__(256) om_stats_kernel(const OmSummary* summary,
 struct OmEngine {
   int device = 0;
   long long n = 0;
-  DevCfg c;
+  DevCfg c;                    // the config (one-config handles) or the maxima the layout is sized for (mixed-config handles)
+  std::vector<DevCfg> cfgs;    // host copies of the device config table
+  const DevCfg* d_cfgs = nullptr;
+  const int32_t* d_cfg_id = nullptr;   // [n] config of every instance (mixed-config handles only)
+  bool multi = false;
   OmStateLayout ly;
   std::vector<void*> dev_allocs;
   unsigned long long* counter = nullptr;
@@ -358,11 +417,11 @@ int om_abi_info(int32_t* out, int32_t n) {
   return m;
 }
 
-int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* out) {
+// argument checks of one config (no CUDA call: these run without a GPU)
+static int check_config(const OmConfig* cfg) {
   OmEngine* h = nullptr;
-  if (!cfg || !out) return set_err(h, OM_E_INVALID, "om_create: null argument");
+  if (!cfg) return set_err(h, OM_E_INVALID, "om_create: null config");
   if (cfg->abi_version != OM_ABI_VERSION) return set_err(h, OM_E_INVALID, "om_create: ABI version mismatch");
-  if (n_instances <= 0 || n_instances > 0x7FFFFFFFLL) return set_err(h, OM_E_INVALID, "om_create: n_instances must be in 1..2^31-1");
   const int T = cfg->n_trucks, L = cfg->n_load_sites, D = cfg->n_dump_sites, S = cfg->n_shovels, M = cfg->n_dumpers;
   if (T <= 0 || L <= 0 || D <= 0 || S <= 0 || M <= 0 || cfg->n_truck_types <= 0)
     return set_err(h, OM_E_INVALID, "om_create: empty mine (mine.py:346-351 asserts)");
@@ -386,17 +445,13 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
     if (cfg->nearest_back[j] < 0 || cfg->nearest_back[j] >= L) return set_err(h, OM_E_INVALID, "om_create: nearest_back out of range");
   if (cfg->nearest_init < 0 || cfg->nearest_init >= L) return set_err(h, OM_E_INVALID, "om_create: nearest_init out of range");
   if (cfg->sum_mode != 0 && cfg->sum_mode != 1) return set_err(h, OM_E_INVALID, "om_create: sum_mode must be 0 (naive) or 1 (Neumaier)");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
-    return set_err(h, OM_E_CUDA, "om_create: no CUDA device (this engine has no CPU fallback)");
-  if (device < 0 || device >= ndev) return set_err(h, OM_E_INVALID, "om_create: bad device index");
-  h = new OmEngine();
-  h->device = device;
-  h->n = n_instances;
+  return OM_OK;
+}
+
+// Device copy of one packed config: scalars + uploaded tables (owned by the handle).
+static int build_devcfg(OmEngine* h, const OmConfig* cfg, DevCfg& c) {
+  const int T = cfg->n_trucks, L = cfg->n_load_sites, D = cfg->n_dump_sites, S = cfg->n_shovels, M = cfg->n_dumpers;
   int rc = OM_OK;
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) { rc = set_err(nullptr, OM_E_CUDA, cudaGetErrorString(e)); delete h; return rc; }
-  DevCfg& c = h->c;
   memset(&c, 0, sizeof(c));
   c.T = T; c.L = L; c.D = D; c.S = S; c.M = M; c.U = S + M; c.R = L + 2 * L * D; c.NS = L + D;
   c.NT = cfg->n_truck_types; c.J = cfg->jam_capacity; c.sum_mode = cfg->sum_mode; c.nearest_init = cfg->nearest_init;
@@ -405,6 +460,7 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
   c.repair_mu = cfg->repair_mu; c.repair_sigma = cfg->repair_sigma; c.unrepairable_mean = cfg->unrepairable_mean;
   c.maint_mean = cfg->maint_mean; c.maint_mu = cfg->maint_mu; c.maint_sigma = cfg->maint_sigma;
   c.jam_sd = cfg->jam_sd; c.jam_scale = cfg->jam_scale;
+  c.sim_time = cfg->sim_time;
 #define UP(field, src, count) if (rc == OM_OK) rc = upload(h, cfg->src, (size_t)(count), &c.field)
   UP(cap, truck_capacity, T); UP(speed, truck_speed, T); UP(ttype, truck_type, T);
   UP(ubeg, site_unit_begin, L + D + 1); UP(dcycle, dumper_cycle, M); UP(rdist, road_distance, c.R);
@@ -446,6 +502,53 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
       rb[cur] = (cur <= L) ? (cur - 1) * D - 1 : L + L * D + (cur - L - 1) * L - 1;
     rc = upload(h, rb.data(), rb.size(), &c.rbase);
   }
+  return rc;
+}
+
+static int create_impl(const OmConfig* const* cfgs, int32_t n_configs, const int32_t* config_id, int64_t n_instances,
+                       int device, OmHandle* out) {
+  OmEngine* h = nullptr;
+  if (!cfgs || !out || n_configs <= 0) return set_err(h, OM_E_INVALID, "om_create: null argument");
+  if (n_instances <= 0 || n_instances > 0x7FFFFFFFLL) return set_err(h, OM_E_INVALID, "om_create: n_instances must be in 1..2^31-1");
+  if (n_configs > 1 && !config_id) return set_err(h, OM_E_INVALID, "om_create_multi: config_id is required with more than one config");
+  for (int32_t k = 0; k < n_configs; ++k) {
+    int rc0 = check_config(cfgs[k]);
+    if (rc0 != OM_OK) return rc0;
+    if (cfgs[k]->flags != cfgs[0]->flags) return set_err(h, OM_E_INVALID, "om_create_multi: all configs must carry the same flags");
+  }
+  if (n_configs > 1 && (cfgs[0]->flags & OM_CFG_RL_SURFACE))
+    return set_err(h, OM_E_UNSUPPORTED, "om_create_multi: the RL step surface is per config (the observation width depends on the mine)");
+  if (config_id)
+    for (int64_t i = 0; i < n_instances; ++i)
+      if (config_id[i] < 0 || config_id[i] >= n_configs) return set_err(h, OM_E_INVALID, "om_create_multi: config_id out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return set_err(h, OM_E_CUDA, "om_create: no CUDA device (this engine has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_err(h, OM_E_INVALID, "om_create: bad device index");
+  h = new OmEngine();
+  h->device = device;
+  h->n = n_instances;
+  h->multi = n_configs > 1;
+  int rc = OM_OK;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { rc = set_err(nullptr, OM_E_CUDA, cudaGetErrorString(e)); delete h; return rc; }
+  h->cfgs.resize(n_configs);
+  for (int32_t k = 0; k < n_configs && rc == OM_OK; ++k) rc = build_devcfg(h, cfgs[k], h->cfgs[k]);
+  DevCfg& c = h->c;
+  if (rc == OM_OK) {
+    c = h->cfgs[0];
+    if (h->multi) {
+      // the shared layout is sized for the largest config in every dimension; the table pointers of h->c are unused
+      memset(&c, 0, sizeof(c));
+      for (const DevCfg& k : h->cfgs) {
+        c.T = std::max(c.T, k.T); c.S = std::max(c.S, k.S); c.M = std::max(c.M, k.M); c.U = std::max(c.U, k.U);
+        c.R = std::max(c.R, k.R); c.NS = std::max(c.NS, k.NS); c.J = std::max(c.J, k.J); c.L = std::max(c.L, k.L);
+        c.D = std::max(c.D, k.D); c.NT = std::max(c.NT, k.NT);
+      }
+    }
+    rc = upload(h, h->cfgs.data(), h->cfgs.size(), &h->d_cfgs);
+    if (rc == OM_OK && h->multi) rc = upload(h, config_id, (size_t)n_instances, &h->d_cfg_id);
+  }
   if (rc == OM_OK) {
     void* d = nullptr;
     e = cudaMalloc(&d, sizeof(unsigned long long));
@@ -470,7 +573,7 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
     else { h->order = (int32_t*)d; h->dev_allocs.push_back(d); }
   }
   if (rc == OM_OK) {
-    h->rl = (cfg->flags & OM_CFG_RL_SURFACE) != 0;
+    h->rl = (cfgs[0]->flags & OM_CFG_RL_SURFACE) != 0;
     build_layout(c, h->ly, h->rl, false);
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -483,7 +586,7 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
     h->split = (limit / (int)h->ly.total_bytes) < 8;
     if (const char* ev = getenv("OM_SPLIT")) h->split = atoi(ev) != 0;   // tuning knob
     if (h->split) build_layout(c, h->ly, h->rl, true);
-    const int staged = (int)(h->split ? h->ly.hot_bytes : h->ly.total_bytes);
+    const int staged = (int)(h->split ? h->ly.hot_bytes : h->ly.total_bytes) + (h->multi ? (int)OM_CFG_SLOT : 0);
     int w = limit / staged;
     if (w > OM_MAX_WARPS_PER_CTA) w = OM_MAX_WARPS_PER_CTA;
     if (const char* ev = getenv("OM_WARPS_PER_CTA")) {   // tuning knob (occupancy experiments)
@@ -499,12 +602,15 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
       long long ctas = (n_instances + w - 1) / w;
       h->grid = (int)(ctas < sms ? ctas : sms);
       const void* fns[] = {
-          (const void*)om_run_kernel<OM_RNG_DET, false, false>, (const void*)om_run_kernel<OM_RNG_PHILOX, false, false>,
-          (const void*)om_run_kernel<OM_RNG_TAPE, false, false>, (const void*)om_run_kernel<OM_RNG_DET, true, false>,
-          (const void*)om_run_kernel<OM_RNG_PHILOX, true, false>, (const void*)om_run_kernel<OM_RNG_TAPE, true, false>,
-          (const void*)om_run_kernel<OM_RNG_DET, false, true>, (const void*)om_run_kernel<OM_RNG_PHILOX, false, true>,
-          (const void*)om_run_kernel<OM_RNG_TAPE, false, true>, (const void*)om_run_kernel<OM_RNG_DET, true, true>,
-          (const void*)om_run_kernel<OM_RNG_PHILOX, true, true>, (const void*)om_run_kernel<OM_RNG_TAPE, true, true>,
+#define OM_RUN_FNS(MULTI)                                                                                                 \
+          (const void*)om_run_kernel<OM_RNG_DET, false, false, MULTI>, (const void*)om_run_kernel<OM_RNG_PHILOX, false, false, MULTI>, \
+          (const void*)om_run_kernel<OM_RNG_TAPE, false, false, MULTI>, (const void*)om_run_kernel<OM_RNG_DET, true, false, MULTI>,    \
+          (const void*)om_run_kernel<OM_RNG_PHILOX, true, false, MULTI>, (const void*)om_run_kernel<OM_RNG_TAPE, true, false, MULTI>,  \
+          (const void*)om_run_kernel<OM_RNG_DET, false, true, MULTI>, (const void*)om_run_kernel<OM_RNG_PHILOX, false, true, MULTI>,   \
+          (const void*)om_run_kernel<OM_RNG_TAPE, false, true, MULTI>, (const void*)om_run_kernel<OM_RNG_DET, true, true, MULTI>,      \
+          (const void*)om_run_kernel<OM_RNG_PHILOX, true, true, MULTI>, (const void*)om_run_kernel<OM_RNG_TAPE, true, true, MULTI>
+          OM_RUN_FNS(false), OM_RUN_FNS(true),
+#undef OM_RUN_FNS
           (const void*)om_step_kernel<OM_RNG_DET, false>, (const void*)om_step_kernel<OM_RNG_PHILOX, false>,
           (const void*)om_step_kernel<OM_RNG_TAPE, false>, (const void*)om_step_kernel<OM_RNG_DET, true>,
           (const void*)om_step_kernel<OM_RNG_PHILOX, true>, (const void*)om_step_kernel<OM_RNG_TAPE, true>};
@@ -523,6 +629,16 @@ int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* ou
   }
   *out = h;
   return OM_OK;
+}
+
+int om_create(const OmConfig* cfg, int64_t n_instances, int device, OmHandle* out) {
+  if (!cfg || !out) return set_err(nullptr, OM_E_INVALID, "om_create: null argument");
+  return create_impl(&cfg, 1, nullptr, n_instances, device, out);
+}
+
+int om_create_multi(const OmConfig* const* cfgs, int32_t n_configs, const int32_t* config_id, int64_t n_instances, int device,
+                    OmHandle* out) {
+  return create_impl(cfgs, n_configs, config_id, n_instances, device, out);
 }
 
 int om_destroy(OmHandle h) {
@@ -566,8 +682,8 @@ int om_reset(OmHandle h, const uint64_t* seeds, const int32_t* dispatcher, int r
   h->tape_values = tape_values; h->tape_sites = tape_sites; h->tape_offsets = tape_offsets;
   const int wpb = 8;
   long long blocks = (h->n + wpb - 1) / wpb;
-  om_reset_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(h->c, h->ly, (unsigned char*)state, seeds,
-                                                                          dispatcher, h->n);
+  om_reset_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(h->d_cfgs, h->d_cfg_id, h->ly, (unsigned char*)state,
+                                                                          seeds, dispatcher, h->n);
   CK(cudaGetLastError());
   om_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dispatcher, h->n, h->order);
   CK(cudaGetLastError());
@@ -588,6 +704,7 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
   p.tape_values = h->tape_values; p.tape_sites = h->tape_sites; p.tape_offsets = h->tape_offsets;
   p.counter = h->counter; p.n_instances = h->n; p.until = until;
   p.order = h->order;
+  p.cfgs = h->d_cfgs; p.cfg_id = h->d_cfg_id; p.ns_stride = h->c.NS; p.u_stride_out = h->c.U;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
   if (p.out.draw_values != nullptr && (p.out.draw_sites == nullptr || p.out.draw_capacity <= 0))
@@ -595,22 +712,24 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
   if (p.out.draw_values != nullptr && h->rng_mode != OM_RNG_PHILOX)
     return set_err(h, OM_E_INVALID, "om_run: the draw-tape export exists in OM_RNG_PHILOX mode only");
   const bool trace = p.out.trace != nullptr || p.out.orders != nullptr || p.out.draw_values != nullptr;   // event-trace / order-log / draw-tape variant
-#define OM_LAUNCH(MODE)                                                                             \
+#define OM_LAUNCH2(MODE, MULTI)                                                                     \
   do {                                                                                              \
     if (h->split) {                                                                                 \
-      if (trace) om_run_kernel<MODE, true, true><<<h->grid, h->block, h->smem, st>>>(p);            \
-      else om_run_kernel<MODE, false, true><<<h->grid, h->block, h->smem, st>>>(p);                 \
+      if (trace) om_run_kernel<MODE, true, true, MULTI><<<h->grid, h->block, h->smem, st>>>(p);     \
+      else om_run_kernel<MODE, false, true, MULTI><<<h->grid, h->block, h->smem, st>>>(p);          \
     } else {                                                                                        \
-      if (trace) om_run_kernel<MODE, true, false><<<h->grid, h->block, h->smem, st>>>(p);           \
-      else om_run_kernel<MODE, false, false><<<h->grid, h->block, h->smem, st>>>(p);                \
+      if (trace) om_run_kernel<MODE, true, false, MULTI><<<h->grid, h->block, h->smem, st>>>(p);    \
+      else om_run_kernel<MODE, false, false, MULTI><<<h->grid, h->block, h->smem, st>>>(p);         \
     }                                                                                               \
   } while (0)
+#define OM_LAUNCH(MODE) do { if (h->multi) OM_LAUNCH2(MODE, true); else OM_LAUNCH2(MODE, false); } while (0)
   switch (h->rng_mode) {
     case OM_RNG_DET: OM_LAUNCH(OM_RNG_DET); break;
     case OM_RNG_PHILOX: OM_LAUNCH(OM_RNG_PHILOX); break;
     default: OM_LAUNCH(OM_RNG_TAPE); break;
   }
 #undef OM_LAUNCH
+#undef OM_LAUNCH2
   CK(cudaGetLastError());
   return OM_OK;
 }
@@ -627,6 +746,7 @@ int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* str
   if (!h || !state || !io || !io->obs) return set_err(h, OM_E_INVALID, "om_step: null argument");
   if (!h->reset_done) return set_err(h, OM_E_INVALID, "om_step: om_reset has not been called on this handle (the state blobs are uninitialised)");
   if (!h->rl) return set_err(h, OM_E_INVALID, "om_step: the handle was created without OM_CFG_RL_SURFACE (OmConfig.flags)");
+  if (h->multi) return set_err(h, OM_E_UNSUPPORTED, "om_step: not available on a mixed-config handle");
   if (((uintptr_t)state & 15u) != 0) return set_err(h, OM_E_INVALID, "om_step: state must be 16-byte aligned (TMA bulk copies)");
   CK(cudaSetDevice(h->device));
   RunParams p;
@@ -638,6 +758,7 @@ int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* str
   p.state = (unsigned char*)state;
   p.tape_values = h->tape_values; p.tape_sites = h->tape_sites; p.tape_offsets = h->tape_offsets;
   p.counter = h->counter; p.n_instances = h->n; p.until = until;
+  p.cfgs = h->d_cfgs; p.cfg_id = nullptr; p.ns_stride = h->c.NS; p.u_stride_out = h->c.U;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
   switch (h->rng_mode) {
@@ -651,6 +772,26 @@ int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* str
     default: OM_STEP(OM_RNG_TAPE); break;
 #undef OM_STEP
   }
+  CK(cudaGetLastError());
+  return OM_OK;
+}
+
+int om_debug_draws(int kind, uint64_t seed, uint32_t arg, int64_t n, double* out, void* stream) {
+  if (!out || n <= 0 || kind < 0 || kind > 6) return OM_E_INVALID;
+  om_debug_draws_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, seed, arg, (long long)n, out);
+  return cudaGetLastError() == cudaSuccess ? OM_OK : OM_E_CUDA;
+}
+
+int om_debug_jam_positions(OmHandle h, void* state, int64_t inst, int32_t road, int32_t n_samples, double* out, int32_t* fallbacks,
+                           void* stream) {
+  if (!h || !state || !out || inst < 0 || inst >= h->n || n_samples <= 0) return set_err(h, OM_E_INVALID, "om_debug_jam_positions: bad argument");
+  if (h->multi || h->split || road < 0 || road >= h->c.R) return set_err(h, OM_E_UNSUPPORTED, "om_debug_jam_positions: one-config, unsplit handles only");
+  CK(cudaSetDevice(h->device));
+  RunParams p;
+  memset(&p, 0, sizeof(p));
+  p.c = h->c; p.ly = h->ly; p.state = (unsigned char*)state; p.n_instances = h->n;
+  p.ns_stride = h->c.NS; p.u_stride_out = h->c.U;
+  om_debug_jam_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, (long long)inst, road, n_samples, out, fallbacks);
   CK(cudaGetLastError());
   return OM_OK;
 }

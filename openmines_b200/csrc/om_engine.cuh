@@ -144,6 +144,11 @@ struct RunParams {
   double until;
   OmStepIO io;      // om_step only
   int obs_dim;
+  // mixed-config batches (om_create_multi, the MULTI kernels): per-instance config index into a device table; p.c then holds
+  // only the maxima the shared layout was sized for
+  const DevCfg* cfgs;
+  const int32_t* cfg_id;
+  int ns_stride, u_stride_out;   // row widths of the per-site / per-unit tick outputs (max L+D / max S+M over the configs)
 };
 
 __device__ __forceinline__ double om_inf() { return __longlong_as_double(0x7FF0000000000000LL); }
@@ -205,8 +210,10 @@ struct Sim {
   uint32_t dirty; // slots (groups of 32 trucks) whose cached minimum is stale (see run())
   double rl_last, rl_last_prod, acc_wait, acc_shovel, acc_dumper, acc_move, acc_jam;   // RL only
 
-  __device__ __forceinline__ Sim(unsigned char* sm_, unsigned char* blob, const RunParams& p, int lane_, long long inst_)
-      : sm(sm_), cold(SPLIT ? blob : sm_), c(p.c), ly(p.ly), out(p.out), lane(lane_), inst(inst_), ordw_ready(false) {}
+  int ns_stride, u_stride_out;
+  __device__ __forceinline__ Sim(unsigned char* sm_, unsigned char* blob, const RunParams& p, const DevCfg& cfg, int lane_, long long inst_)
+      : sm(sm_), cold(SPLIT ? blob : sm_), c(cfg), ly(p.ly), out(p.out), lane(lane_), inst(inst_), ordw_ready(false),
+        ns_stride(p.ns_stride), u_stride_out(p.u_stride_out) {}
 
   // State accessors.  Per-truck and per-unit scalars live in fixed-size records (array of structures): the scalar
   // DES code touches many fields of ONE truck / unit, so a record base + compile-time field offsets costs one
@@ -946,7 +953,7 @@ struct Sim {
         dst[0] = a; dst[1] = b;
       }
       if (lane < NS) {
-        long long o = (inst * (long long)out.tick_capacity + k) * NS + lane;
+        long long o = (inst * (long long)out.tick_capacity + k) * ns_stride + lane;
         if (out.site_queue_ticks != nullptr) out.site_queue_ticks[o] = (uint16_t)qtot;
         if (out.site_tons_ticks != nullptr) out.site_tons_ticks[o] = site_tons;
       }
@@ -956,7 +963,7 @@ struct Sim {
           OmUnitTick r;
           r.tons = F64(u_tons, u); r.service_count = U32A(u_svc, u); r.queue_length = U16A(u_qlen, u);
           r.repair = (u < c.S) ? U8A(u_repair, u) : (uint8_t)0; r.pad = 0;
-          out.unit_ticks[(inst * (long long)out.tick_capacity + k) * c.U + u] = r;
+          out.unit_ticks[(inst * (long long)out.tick_capacity + k) * u_stride_out + u] = r;
         }
       }
     }
@@ -1105,7 +1112,8 @@ struct Sim {
   // grid window [-h/2, 1+h/2] (else pick again), round to the grid.  Accepted x has density
   // ~ sum_i N(x; c_i, sd) on the window, i.e. the reference's categorical up to the mid-point rule
   // (relative error O((h/sd)^2/24) = 4e-6).  Acceptance >= 1/2 per attempt.
-  __device__ __forceinline__ double sample_jam_position(int k, int rid, uint32_t n_on) {
+  template <bool DBG = false>
+  __device__ __forceinline__ double sample_jam_position(int k, int rid, uint32_t n_on, int* fallbacks = nullptr) {
     const int T = c.T;
     const float sd = (float)c.jam_sd, h = 1.0f / 999.0f;
     float x = 0.5f;
@@ -1141,10 +1149,21 @@ struct Sim {
       float cv = coverage(found, rid);
       float xx = cv + sd * om_normal_fast(r.y, r.z);
       if (xx >= -0.5f * h && xx <= 1.0f + 0.5f * h) { x = xx; break; }
+      if (DBG && it == 63 && fallbacks != nullptr) (*fallbacks)++;      // 64 rejections in a row (p <= 2^-64): x stays 0.5
     }
     int idx = __float2int_rn(x * 999.0f);
     idx = idx < 0 ? 0 : (idx > 999 ? 999 : idx);
     return (double)idx * (1.0 / 999.0);       // np.linspace(0, 1, 1000)[idx]
+  }
+
+  // test hook (om_debug_jam_positions): moving trucks on road `rid`, as jam_sampling() counts them
+  __device__ __forceinline__ uint32_t debug_trucks_on_road(int rid) {
+    uint32_t n = 0;
+    for (int i = 0; i < c.T; ++i) {
+      int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
+      if (U8A(t_status, i) == ST_MOVING && cur != tgt && road_id(cur, tgt) == rid) n++;
+    }
+    return n;
   }
 
   // Truck.get_route_coverage (truck.py:496-520)

@@ -122,26 +122,53 @@ class RunResult:
 class BatchedMine:
     """N independent instances of one mine config on one GPU."""
 
-    def __init__(self, config, n_instances, device=0, jam_capacity=64, sum_mode="neumaier", rl_surface=False):
+    def __init__(self, config, n_instances, device=0, jam_capacity=64, sum_mode="neumaier", rl_surface=False,
+                 config_ids=None):
         """``rl_surface=True`` allocates the fields ``om_step`` needs (reward windows, minute-sampled site values):
         required by ``step()`` / ``BatchedMineEnv`` / ``run_external``; episode runs (``run()``) are faster without it
-        because smaller state blobs leave room for more resident instances per SM."""
+        because smaller state blobs leave room for more resident instances per SM.
+
+        Mixed-config batch: ``config`` may be a LIST of mine configs (dicts / paths / ``PackedConfig``) with ``config_ids``
+        naming, per instance, the one it simulates (``om_create_multi``) -- the reference's fleet-size and scene sweeps
+        (cli/run.py:283-472) as one batch.  ``jam_capacity`` may then be a list too.  ``pc_of(inst)`` gives an instance's
+        packed config; ``pc`` is the first one."""
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
             raise RuntimeError("openmines_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
-        self.pc = config if isinstance(config, PackedConfig) else pack_config(config, jam_capacity, sum_mode)
-        self.pc.flags = OM_CFG_RL_SURFACE if rl_surface else 0
+        self.multi = isinstance(config, (list, tuple))
+        configs = list(config) if self.multi else [config]
+        jams = list(jam_capacity) if isinstance(jam_capacity, (list, tuple)) else [jam_capacity] * len(configs)
+        self.pcs = [c if isinstance(c, PackedConfig) else pack_config(c, j, sum_mode) for c, j in zip(configs, jams)]
+        for pc in self.pcs:
+            pc.flags = OM_CFG_RL_SURFACE if rl_surface else 0
+        self.pc = self.pcs[0]
         self.rl_surface = bool(rl_surface)
         self.n = int(n_instances)
         self.device = torch.device("cuda", device)
-        self._cstruct = self.pc.c_struct()
+        self._cstructs = [pc.c_struct() for pc in self.pcs]
         h = ctypes.c_void_p()
-        rc = self.lib.om_create(ctypes.byref(self._cstruct), self.n, device, ctypes.byref(h))
+        if self.multi:
+            if config_ids is None:
+                raise ValueError("a list of configs needs config_ids (one config index per instance)")
+            self.config_ids = np.ascontiguousarray(config_ids, dtype=np.int32)
+            if self.config_ids.shape != (self.n,):
+                raise ValueError("config_ids must have one entry per instance")
+            arr = (ctypes.c_void_p * len(self.pcs))(*[ctypes.addressof(c) for c in self._cstructs])
+            rc = self.lib.om_create_multi(arr, len(self.pcs), self.config_ids.ctypes.data_as(ctypes.c_void_p), self.n, device,
+                                          ctypes.byref(h))
+        else:
+            self.config_ids = None
+            rc = self.lib.om_create(ctypes.byref(self._cstructs[0]), self.n, device, ctypes.byref(h))
         if rc != 0:
             raise RuntimeError("om_create failed (%d): %s" % (rc, self.lib.om_last_error(None).decode()))
         self.h = h
+        # row widths of the per-site / per-unit outputs and the loop bounds of the helpers: maxima over the configs
+        self.max_T = max(pc.T for pc in self.pcs)
+        self.max_NS = max(pc.L + pc.D for pc in self.pcs)
+        self.max_U = max(pc.S + pc.M for pc in self.pcs)
+        self.max_R = max(pc.R for pc in self.pcs)
         sb = ctypes.c_size_t()
         self._ck(self.lib.om_state_bytes(self.h, ctypes.byref(sb)))
         self.state_bytes = int(sb.value)
@@ -152,7 +179,11 @@ class BatchedMine:
         self.has_external = False
         self.seeds = None
         self._tape = None
-        self.sim_time = self.pc.sim_time
+        self.sim_time = max(pc.sim_time for pc in self.pcs)
+
+    def pc_of(self, inst):
+        """Packed config of instance ``inst``."""
+        return self.pcs[int(self.config_ids[inst])] if self.multi else self.pc
 
     def _ck(self, rc):
         if rc != 0:
@@ -233,7 +264,7 @@ class BatchedMine:
         if r.summary is None:
             r.summary = torch.zeros((self.n, 64), dtype=torch.uint8, device=self.device)
         tick_cap = int(np.ceil(self.sim_time)) if ticks else 0
-        ns = self.pc.L + self.pc.D
+        ns = self.max_NS
         if ticks and r.ticks is None:
             r.ticks = torch.zeros((self.n, tick_cap, 32), dtype=torch.uint8, device=self.device)
             r.tick_capacity = tick_cap
@@ -241,7 +272,7 @@ class BatchedMine:
             r.site_queue_ticks = torch.zeros((self.n, tick_cap, ns), dtype=torch.int16, device=self.device)
             r.site_tons_ticks = torch.zeros((self.n, tick_cap, ns), dtype=torch.float64, device=self.device)
         if unit_ticks and r.unit_ticks is None:
-            r.unit_ticks = torch.zeros((self.n, tick_cap, self.pc.S + self.pc.M, 16), dtype=torch.uint8, device=self.device)
+            r.unit_ticks = torch.zeros((self.n, tick_cap, self.max_U, 16), dtype=torch.uint8, device=self.device)
         if trace_capacity and r.trace is None:
             r.trace = torch.zeros((self.n, trace_capacity, 32), dtype=torch.uint8, device=self.device)
             r.trace_capacity = int(trace_capacity)
@@ -270,7 +301,7 @@ class BatchedMine:
         block), up to three per road per minute (jam coin / position / duration) and six per truck cycle."""
         until = float(self.sim_time if until is None else until)
         minutes = int(np.ceil(until)) + 1
-        return minutes * (2 * self.pc.T + 3 * self.pc.R) + 6 * self.pc.T * (minutes // 4 + 4)
+        return minutes * (2 * self.max_T + 3 * self.max_R) + 6 * self.max_T * (minutes // 4 + 4)
 
     def obs_dim(self):
         d = ctypes.c_int32()
@@ -317,7 +348,7 @@ class BatchedMine:
         ``blob``: the instance's bytes if the caller already copied the state to the host."""
         if blob is None:
             blob = self.state[inst].cpu().numpy()
-        ly, pc = self.layout, self.pc
+        ly, pc = self.layout, self.pc_of(inst)
         T, U, S = pc.T, pc.S + pc.M, pc.S
 
         raw = blob.tobytes()

@@ -139,11 +139,53 @@ def scene_based_fleet_ablation_serial(config_file, min_truck, max_truck, dispatc
     return results
 
 
-def algo_based_fleet_ablation(scenes, baseline, target, min_truck=1, max_truck=160, n_seeds=32, stochastic=True, device=0):
-    """``scenes``: directory with ``*.json`` mine configs (the reference's ``-d``), or a list of paths / config dicts.
-    Returns ``{scene name: {"fleet_sizes": [...], "ratios": [...], "baseline": [...], "target": [...]}}`` -- the
-    ``scenes_data`` that ``Charter.draw_algo_based_fleet_ablation_experiment`` plots (ratio 0 where the baseline produced
-    nothing, cli/run.py:461-463) plus the two mean productions."""
+def _fleet_configs(cfg, sizes):
+    out = []
+    for fs in sizes:
+        c = scaled_fleet_config(cfg, fs)
+        c["charging_site"]["trucks"] = [t for t in c["charging_site"]["trucks"] if t["count"] > 0]
+        out.append(c)
+    return out
+
+
+def scene_based_fleet_ablation(config_file, min_truck, max_truck, dispatchers=None, n_seeds=32, stochastic=True, device=0,
+                               jam_capacity=None, seeds=None):
+    """cli/run.py:283-362 as ONE batch: 10 fleet sizes x dispatchers x seeds are the instances of a single mixed-config
+    ``BatchedMine`` (``om_create_multi``) and one ``om_run`` launch simulates them all.  Returns, per dispatcher,
+    ``{"fleet_sizes", "productions" (mean reported tons over the seeds; with ``stochastic=False`` and one seed exactly the
+    value the reference plots), "std"}``."""
+    cfg = load_config(config_file)
+    names = dispatchers or [n for n in cfg["dispatcher"]["type"] if n in DISPATCHER_IDS]
+    sizes = fleet_sizes_for(min_truck, max_truck)
+    configs = _fleet_configs(cfg, sizes)
+    seeds = np.arange(n_seeds, dtype=np.uint64) if seeds is None else np.asarray(seeds, dtype=np.uint64)
+    n_seeds = len(seeds)
+    # instance order: fleet size (slowest), dispatcher, seed
+    F, K = len(sizes), len(names)
+    config_ids = np.repeat(np.arange(F, dtype=np.int32), K * n_seeds)
+    disp_ids = np.tile(np.repeat([DISPATCHER_IDS[n] for n in names], n_seeds), F).astype(np.int32)
+    all_seeds = np.tile(seeds, F * K)
+    jams = [jam_capacity or default_jam_capacity(c) for c in configs]
+    mine = BatchedMine(configs, F * K * n_seeds, device=device, jam_capacity=jams, config_ids=config_ids)
+    mine.reset(disp_ids, seeds=all_seeds, rng_mode="philox" if stochastic else "det")
+    s = mine.run(ticks=True).summary_np()
+    mine.close()
+    check_instance_errors(s, "scene_based_fleet_ablation")
+    tons = s["reported_tons"].reshape(F, K, n_seeds)
+    results = {}
+    for k, n in enumerate(names):
+        results[n] = {"fleet_sizes": list(sizes), "productions": [float(x) for x in tons[:, k].mean(axis=1)],
+                      "std": [float(x) for x in tons[:, k].std(axis=1)]}
+    return results
+
+
+def algo_based_fleet_ablation(scenes, baseline, target, min_truck=1, max_truck=160, n_seeds=32, stochastic=True, device=0,
+                              jam_capacity=None):
+    """cli/run.py:363-472 as ONE batch.  ``scenes``: directory with ``*.json`` mine configs (the reference's ``-d``), or a list
+    of paths / config dicts.  Every (scene, fleet size) pair is one config of a mixed-config ``BatchedMine``; both dispatchers'
+    seeds of all of them run in one launch.  Returns ``{scene name: {"fleet_sizes": [...], "ratios": [...], "baseline": [...],
+    "target": [...]}}`` -- the ``scenes_data`` that ``Charter.draw_algo_based_fleet_ablation_experiment`` plots (ratio 0 where
+    the baseline produced nothing, cli/run.py:461-463) plus the two mean productions."""
     if isinstance(scenes, (str, os.PathLike)):
         paths = sorted(glob.glob(os.path.join(str(scenes), "*.json")))
         scenes = [(os.path.splitext(os.path.basename(p))[0], load_config(p)) for p in paths]
@@ -155,21 +197,25 @@ def algo_based_fleet_ablation(scenes, baseline, target, min_truck=1, max_truck=1
                 cfg.get("mine", {}).get("name", "scene%d" % k)
             named.append((name, cfg))
         scenes = named
-    ids = np.repeat([DISPATCHER_IDS[by_name(baseline).name], DISPATCHER_IDS[by_name(target).name]], n_seeds).astype(np.int32)
-    seeds = np.tile(np.arange(n_seeds, dtype=np.uint64), 2)
+    sizes = fleet_sizes_for(min_truck, max_truck)
+    F, NSC = len(sizes), len(scenes)
+    configs = []
+    for _, cfg in scenes:
+        configs += _fleet_configs(cfg, sizes)
+    pair = np.repeat([DISPATCHER_IDS[by_name(baseline).name], DISPATCHER_IDS[by_name(target).name]], n_seeds).astype(np.int32)
+    config_ids = np.repeat(np.arange(NSC * F, dtype=np.int32), 2 * n_seeds)
+    disp_ids = np.tile(pair, NSC * F)
+    seeds = np.tile(np.arange(n_seeds, dtype=np.uint64), 2 * NSC * F)
+    jams = [jam_capacity or default_jam_capacity(c) for c in configs]
+    mine = BatchedMine(configs, len(config_ids), device=device, jam_capacity=jams, config_ids=config_ids)
+    mine.reset(disp_ids, seeds=seeds, rng_mode="philox" if stochastic else "det")
+    s = mine.run(ticks=True).summary_np()
+    mine.close()
+    check_instance_errors(s, "algo_based_fleet_ablation")
+    tons = s["reported_tons"].reshape(NSC, F, 2, n_seeds).mean(axis=3)
     out = {}
-    for name, cfg in scenes:
-        data = {"fleet_sizes": [], "ratios": [], "baseline": [], "target": []}
-        for fs in fleet_sizes_for(min_truck, max_truck):
-            c = scaled_fleet_config(cfg, fs)
-            c["charging_site"]["trucks"] = [t for t in c["charging_site"]["trucks"] if t["count"] > 0]
-            mine = BatchedMine(c, 2 * n_seeds, device=device)
-            mine.reset(ids, seeds=seeds, rng_mode="philox" if stochastic else "det")
-            tons = mine.run(ticks=True).summary_np()["reported_tons"].reshape(2, n_seeds).mean(axis=1)
-            mine.close()
-            data["fleet_sizes"].append(fs)
-            data["baseline"].append(float(tons[0]))
-            data["target"].append(float(tons[1]))
-            data["ratios"].append(float(tons[1] / tons[0]) if tons[0] > 1e-9 else 0.0)
-        out[name] = data
+    for k, (name, _) in enumerate(scenes):
+        b, t = tons[k, :, 0], tons[k, :, 1]
+        out[name] = {"fleet_sizes": list(sizes), "baseline": [float(x) for x in b], "target": [float(x) for x in t],
+                     "ratios": [float(t[i] / b[i]) if b[i] > 1e-9 else 0.0 for i in range(F)]}
     return out

@@ -56,13 +56,13 @@ class _Pool:
 
 
 class TickRecorder:
-    def __init__(self, mine, result, dispatcher_name=None, reference_counters=True):
+    def __init__(self, mine, result, dispatcher_name=None, reference_counters=True, config_index=0):
         """reference_counters: report road_jam_count etc. the way the reference counts them (keys of the
         timestamp-keyed random-event dict, needs the event trace) instead of the engine's true counts."""
         self.reference_counters = reference_counters
         self.mine, self.res = mine, result
-        self.pc = mine.pc
-        self.cfg = mine.pc.raw
+        self.pc = mine.pcs[config_index]          # mixed-config batches: the config of the instances to be rendered
+        self.cfg = self.pc.raw
         self.dispatcher_name = dispatcher_name
         if result.summary is not None:
             err = result.summary_np()["err"]

@@ -137,14 +137,15 @@ def engine_vs_ref(ref, mine, result, inst, sptf=False):
             diffs.append("tick[%s] differs first at minute %d: %r vs %r" % (
                 k_ref, bad[0], ref.tick[k_ref][bad[0]], ticks[k_eng][bad[0]]))
     if result.site_queue_ticks is not None:
-        q = result.site_queue_ticks[inst].cpu().numpy()[:nt]
+        ns = mine.pc_of(inst).L + mine.pc_of(inst).D        # rows are max(L+D) wide in a mixed-config batch
+        q = result.site_queue_ticks[inst].cpu().numpy()[:nt, :ns]
         if not np.array_equal(ref.tick["site_queue_total"], q.astype(np.int32)):
             diffs.append("tick[site_queue_total] differs")
-        st = result.site_tons_ticks[inst].cpu().numpy()[:nt]
+        st = result.site_tons_ticks[inst].cpu().numpy()[:nt, :ns]
         if not np.array_equal(ref.tick["site_tons"], st):
             diffs.append("tick[site_tons] differs")
     sa = mine.state_arrays(inst, blob=result.state[inst]) if isinstance(result, HostResult) else mine.state_arrays(inst)
-    S = mine.pc.S
+    S = mine.pc_of(inst).S
     checks = [("truck_total_load", sa["t_total"]), ("truck_service_count", sa["t_svc"]),
               ("truck_cycle_time", sa["t_cycle"]), ("truck_status", sa["t_status"]), ("truck_cur", sa["t_cur"]),
               ("truck_tgt", sa["t_tgt"]), ("shovel_tons", sa["u_tons"][:S]), ("shovel_service_count", sa["u_svc"][:S]),

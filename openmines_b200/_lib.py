@@ -11,7 +11,9 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libopenmines_b200.so")
+# OM_DEBUG_LIB=1: the bounds-checking build (-DOM_BOUNDS_CHECK, see csrc/om_engine.cuh), used by tools/sanitize.sh
+DEBUG = bool(os.environ.get("OM_DEBUG_LIB"))
+LIB_PATH = os.path.join(_HERE, "libopenmines_b200_dbg.so" if DEBUG else "libopenmines_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
@@ -39,7 +41,8 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     cus = [s for s in sources() if s.endswith(".cu")]
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", LIB_PATH] + cus
+    cmd = [nvcc] + NVCC_FLAGS + (["-DOM_BOUNDS_CHECK"] if DEBUG else []) + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-I", INCLUDE, "-o", LIB_PATH] + cus
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
@@ -105,6 +108,8 @@ def load():
     lib.om_debug_draws.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32, i64, vp, vp]
     lib.om_debug_jam_positions.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
     lib.om_debug_draws.restype = lib.om_debug_jam_positions.restype = ctypes.c_int
+    lib.om_debug_bounds_report.argtypes = [ctypes.POINTER(i32)]
+    lib.om_debug_bounds_report.restype = ctypes.c_int
     lib.om_abi_info.argtypes = [ctypes.POINTER(i32), i32]
     lib.om_abi_info.restype = i32
     _lib = lib
@@ -145,4 +150,4 @@ def _check_abi():
 
 
 EXPORTED_SYMBOLS = ["om_create", "om_create_multi", "om_destroy", "om_last_error", "om_abi_info", "om_state_bytes", "om_state_layout", "om_reset",
-                    "om_run", "om_stats_reduce", "om_launch_info", "om_obs_dim", "om_step", "om_debug_draws", "om_debug_jam_positions"]
+                    "om_run", "om_stats_reduce", "om_launch_info", "om_obs_dim", "om_step", "om_debug_draws", "om_debug_jam_positions", "om_debug_bounds_report"]

@@ -796,6 +796,19 @@ int om_debug_jam_positions(OmHandle h, void* state, int64_t inst, int32_t road, 
   return OM_OK;
 }
 
+int om_debug_bounds_report(int32_t* out4) {
+  if (!out4) return OM_E_INVALID;
+#ifdef OM_BOUNDS_CHECK
+  int v[4] = {0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(v, g_om_bounds, sizeof(v)) != cudaSuccess) return OM_E_CUDA;
+  for (int k = 0; k < 4; ++k) out4[k] = v[k];
+  return 1;      // this binary checks
+#else
+  for (int k = 0; k < 4; ++k) out4[k] = 0;
+  return 0;      // this binary does not check
+#endif
+}
+
 int om_stats_reduce(OmHandle h, const OmSummary* summary, const int32_t* dispatcher, double* stats_out, void* stream) {
   if (!h || !summary || !dispatcher || !stats_out) return set_err(h, OM_E_INVALID, "om_stats_reduce: null argument");
   CK(cudaSetDevice(h->device));

@@ -153,6 +153,16 @@ struct RunParams {
 
 __device__ __forceinline__ double om_inf() { return __longlong_as_double(0x7FF0000000000000LL); }
 
+// bounds-check build: {violations, source line of the first, its index, the extent}
+__device__ int g_om_bounds[4];
+__device__ __forceinline__ long long om_chk(long long i, long long n, int line) {
+  if (i < 0 || i >= n) {
+    if (atomicAdd(&g_om_bounds[0], 1) == 0) { g_om_bounds[1] = line; g_om_bounds[2] = (int)i; g_om_bounds[3] = (int)n; }
+    return 0;
+  }
+  return i;
+}
+
 // Out-of-line helpers: the hot loop must stay small enough for the instruction caches (profiles/r1_a),
 // so the 10-round Philox and the fp64 division (a ~35-instruction Newton sequence) exist once.
 __device__ __noinline__ Philox4 om_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
@@ -272,10 +282,61 @@ struct Sim {
 #define OM_A_s_cap(type, i) OM_SOA(type, s_cap, i)
 #define OM_A_s_ability(type, i) OM_SOA(type, s_ability, i)
 #define OM_A_scratch(type, i) OM_SOA(type, scratch, i)
-#define F64(field, i) OM_A_##field(double, i)
-#define U32A(field, i) OM_A_##field(uint32_t, i)
-#define U16A(field, i) OM_A_##field(uint16_t, i)
-#define U8A(field, i) OM_A_##field(uint8_t, i)
+  // Debug build (-DOM_BOUNDS_CHECK, libopenmines_b200_dbg.so): every state access through the accessors checks its index
+  // against the array's extent for THIS instance's config; the first violation is recorded (source line, index, extent;
+  // om_debug_bounds_report) and the access is redirected to element 0.  compute-sanitizer is not available on the GPU pool
+  // this was developed on, so this build + tools/sanitize_target.py is the memcheck of the state arrays.
+#define OM_B_t_time c.T
+#define OM_B_t_key c.T
+#define OM_B_t_phase c.T
+#define OM_B_t_load c.T
+#define OM_B_t_jstart c.T
+#define OM_B_t_prejam c.T
+#define OM_B_t_lastbrk c.T
+#define OM_B_t_repair c.T
+#define OM_B_t_total c.T
+#define OM_B_t_cycle c.T
+#define OM_B_t_dist c.T
+#define OM_B_t_since c.T
+#define OM_B_t_rng c.T
+#define OM_B_t_svc c.T
+#define OM_B_t_epoch c.T
+#define OM_B_t_next c.T
+#define OM_B_t_unit c.T
+#define OM_B_t_status c.T
+#define OM_B_t_cur c.T
+#define OM_B_t_tgt c.T
+#define OM_B_u_rel_key c.U
+#define OM_B_u_last_start c.U
+#define OM_B_u_last_done c.U
+#define OM_B_u_tons c.U
+#define OM_B_u_lastbrk c.S
+#define OM_B_u_svc c.U
+#define OM_B_u_user c.U
+#define OM_B_u_head c.U
+#define OM_B_u_tail c.U
+#define OM_B_u_qlen c.U
+#define OM_B_u_repair c.S
+#define OM_B_r_repair_end c.R
+#define OM_B_j_pos c.J
+#define OM_B_j_start c.J
+#define OM_B_j_end c.J
+#define OM_B_j_road c.J
+#define OM_B_s_qtotal c.NS
+#define OM_B_s_coming c.NS
+#define OM_B_s_tons c.NS
+#define OM_B_s_cap c.NS
+#define OM_B_s_ability c.NS
+#define OM_B_scratch ((ly.slot_cache - ly.scratch) / 8u)
+#ifdef OM_BOUNDS_CHECK
+#define OM_IDX(field, i) om_chk((long long)(i), (long long)(OM_B_##field), __LINE__)
+#else
+#define OM_IDX(field, i) (i)
+#endif
+#define F64(field, i) OM_A_##field(double, OM_IDX(field, i))
+#define U32A(field, i) OM_A_##field(uint32_t, OM_IDX(field, i))
+#define U16A(field, i) OM_A_##field(uint16_t, OM_IDX(field, i))
+#define U8A(field, i) OM_A_##field(uint8_t, OM_IDX(field, i))
 
   // ---------------------------------------------------------------------------------------------
   // header <-> registers

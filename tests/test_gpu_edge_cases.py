@@ -102,15 +102,15 @@ def test_integer_mine_tie_stress_vs_golden(integer_mine):
 
 def test_ragged_mine_live_distribution_vs_reference(ragged_mine):
     """Live RNG on the ragged mine, whose own road_event_params make road repairs and detours frequent (dozens per episode
-    instead of ~1 on north_pit): against 512 runs of the unmodified reference per dispatcher
-    (tests/golden/make_golden_dist.py ragged_mine 512).  Welch z-tests at |z| < 3.5 on the means of reported tons
-    (CI +- 38 t = 1.1 % for SQ), truck events, orders, jams, road repairs, truck breakdowns, unrepairable trucks, the mean
+    instead of ~1 on north_pit): against 2048 runs of the unmodified reference per dispatcher
+    (tests/golden/make_golden_dist.py ragged_mine 2048).  Welch z-tests at |z| < 3.5 on the means of reported tons
+    (CI +- 3.5 * 258 / sqrt(2048) = +- 20 t = 0.6 % for SQ), truck events, orders, jams, road repairs, truck breakdowns, unrepairable trucks, the mean
     production / waiting curves, and KS on the tonnage."""
     import os
     from helpers import GOLDEN
     from test_gpu_parity import live_distribution_check
     ref = np.load(os.path.join(GOLDEN, "live_distribution_ragged_mine.npz"))
-    assert len(ref["SQDispatcher_tons"]) >= 512
+    assert len(ref["SQDispatcher_tons"]) >= 2048
     names = ["SQDispatcher", "SPTFDispatcher", "NearestDispatcher", "FixedGroupDispatcher"]
     fields = (("reported_tons", "tons"), ("n_truck_events", "events"), ("n_wrapper_orders", "orders"), ("n_jams", "jams"),
               ("n_road_repairs", "road_repairs"), ("n_truck_repairs", "breakdowns"), ("n_unrepairable", "unrepairable"))

@@ -102,6 +102,15 @@ def main():
         from openmines_b200 import parallel
         assert np.array_equal(mine.stats(res).cpu().numpy(), parallel.stats_from_summaries(res.summary_np(), ids))
         print("stats ok", flush=True)
+    # the bounds-checking build reports what its accessors saw
+    import ctypes
+    from openmines_b200 import _lib
+    rep = (ctypes.c_int32 * 4)()
+    checks = _lib.load().om_debug_bounds_report(rep)
+    print("bounds-check build: %s; violations %d (first: om_engine.cuh line %d, index %d, extent %d)" % (
+        "yes" if checks == 1 else "NO (plain build)", rep[0], rep[1], rep[2], rep[3]), flush=True)
+    if checks == 1 and rep[0] != 0:
+        sys.exit(9)
 
 
 if __name__ == "__main__":

@@ -332,9 +332,10 @@ int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* str
  * om_debug_jam_positions: n_samples draws of the position of a new jam on `road` for instance `inst` as its state blob
  *   stands (Road.road_jam_sampling's np.random.choice over the 1000-point grid, road.py:185-206); *fallbacks = how often the
  *   rejection sampler gave up.  out: device [n_samples], fallbacks: device int. */
-/* om_debug_bounds_report: returns 1 when the library was built with -DOM_BOUNDS_CHECK (every state access checks its index),
- * 0 otherwise; out4 = {violations so far, source line of the first, its index, the extent}. */
-int om_debug_bounds_report(int32_t* out4);
+/* om_debug_bounds_report: returns 1 when the library was built with -DOM_BOUNDS_CHECK (every state access checks its index,
+ * and the warp-uniform continuations check that the warp arrives converged), 0 otherwise; out8 = {index violations so far,
+ * source line of the first, its index, the extent, convergence violations, source line of the first, its active mask, 0}. */
+int om_debug_bounds_report(int32_t* out8);
 int om_debug_draws(int kind, uint64_t seed, uint32_t arg, int64_t n, double* out, void* stream);
 int om_debug_jam_positions(OmHandle h, void* state, int64_t inst, int32_t road, int32_t n_samples, double* out,
                            int32_t* fallbacks, void* stream);

@@ -13,7 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # OM_DEBUG_LIB=1: the bounds-checking build (-DOM_BOUNDS_CHECK, see csrc/om_engine.cuh), used by tools/sanitize.sh
 DEBUG = bool(os.environ.get("OM_DEBUG_LIB"))
-LIB_PATH = os.path.join(_HERE, "libopenmines_b200_dbg.so" if DEBUG else "libopenmines_b200.so")
+LIB_PATH = os.environ.get("OM_LIB_PATH") or os.path.join(_HERE, "libopenmines_b200_dbg.so" if DEBUG else "libopenmines_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
@@ -41,7 +41,8 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     cus = [s for s in sources() if s.endswith(".cu")]
-    cmd = [nvcc] + NVCC_FLAGS + (["-DOM_BOUNDS_CHECK"] if DEBUG else []) + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [nvcc] + NVCC_FLAGS + (["-DOM_BOUNDS_CHECK=" + (os.environ.get("OM_DEBUG_LIB") or "1")] if DEBUG and os.environ.get("OM_DEBUG_LIB") != "probes" else []) + \
+        (os.environ.get("OM_EXTRA_NVCC_FLAGS", "").split()) + (["-Xptxas", "-v"] if verbose else []) + \
         ["-I", INCLUDE, "-o", LIB_PATH] + cus
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -151,6 +151,9 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
       }
     }
     if (TRACE && RNG == OM_RNG_PHILOX && p.out.draw_count != nullptr && lane == 0) p.out.draw_count[inst] = (uint32_t)s.tape_pos;
+#ifdef OM_BOUNDS_CHECK
+    om_publish_violation(s.dbg_viol);
+#endif
     om_stage_out(g, sm, staged, lane);
   }
 }
@@ -179,6 +182,9 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_step_kernel(c
     s.load_hdr(p);
     s.rl_step(p);
     s.store_hdr(p);
+#ifdef OM_BOUNDS_CHECK
+    om_publish_violation(s.dbg_viol);
+#endif
     om_stage_out(g, sm, staged, lane);
   }
 }
@@ -796,15 +802,19 @@ int om_debug_jam_positions(OmHandle h, void* state, int64_t inst, int32_t road, 
   return OM_OK;
 }
 
-int om_debug_bounds_report(int32_t* out4) {
-  if (!out4) return OM_E_INVALID;
-#ifdef OM_BOUNDS_CHECK
-  int v[4] = {0, 0, 0, 0};
+int om_debug_bounds_report(int32_t* out8) {
+  if (!out8) return OM_E_INVALID;
+#if defined(OM_BOUNDS_CHECK) || defined(OM_CONV_PROBES)
+  int v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cudaMemcpyFromSymbol(v, g_om_bounds, sizeof(v)) != cudaSuccess) return OM_E_CUDA;
-  for (int k = 0; k < 4; ++k) out4[k] = v[k];
-  return 1;      // this binary checks
+  for (int k = 0; k < 8; ++k) out8[k] = v[k];
+#ifdef OM_BOUNDS_CHECK
+  return 1;      // this binary checks indices and convergence
 #else
-  for (int k = 0; k < 4; ++k) out4[k] = 0;
+  return 2;      // this binary checks convergence only
+#endif
+#else
+  for (int k = 0; k < 8; ++k) out8[k] = 0;
   return 0;      // this binary does not check
 #endif
 }

@@ -27,6 +27,11 @@ static_assert(OM_S_LOAD_JITTER == OM_DRAW_LOAD_JITTER && OM_S_BREAK_GAP == OM_DR
               OM_S_JAM_COIN == OM_DRAW_JAM_COIN && OM_S_JAM_DUR == OM_DRAW_JAM_DUR && OM_S_DISPATCH == OM_DRAW_DISPATCH,
               "draw-site ids of om_rng.cuh and include/openmines_b200.h");
 #define OM_FULL 0xffffffffu
+#ifdef OM_NO_RECONV   /* debugging aid: build without the explicit reconvergence points */
+#define OM_RECONV() do { } while (0)
+#else
+#define OM_RECONV() __syncwarp()
+#endif
 #define OM_NONE16 0xFFFFu
 #define OM_NOLOC 0xFFu
 #define OM_KEY_NORMAL 0x80000000u
@@ -153,14 +158,24 @@ struct RunParams {
 
 __device__ __forceinline__ double om_inf() { return __longlong_as_double(0x7FF0000000000000LL); }
 
-// bounds-check build: {violations, source line of the first, its index, the extent}
-__device__ int g_om_bounds[4];
-__device__ __forceinline__ long long om_chk(long long i, long long n, int line) {
-  if (i < 0 || i >= n) {
-    if (atomicAdd(&g_om_bounds[0], 1) == 0) { g_om_bounds[1] = line; g_om_bounds[2] = (int)i; g_om_bounds[3] = (int)n; }
-    return 0;
-  }
-  return i;
+// bounds-check build: {violations, source line of the first, its index, the extent, warp-convergence probes that saw a
+// partial active mask, source line of the first, its mask}
+__device__ int g_om_bounds[8];
+#if defined(OM_BOUNDS_CHECK) || defined(OM_CONV_PROBES)
+#define OM_CONV() do { unsigned am_ = __activemask(); if (am_ != 0xffffffffu && atomicAdd(&g_om_bounds[4], 1) == 0) { g_om_bounds[5] = __LINE__; g_om_bounds[6] = (int)am_; } } while (0)
+#else
+#define OM_CONV() do { } while (0)
+#endif
+// Branch-free on purpose: a check that branches changes where the compiler reconverges the warp, and the engine's redundant
+// all-lane stores are only safe on a converged warp (see emit()).  The violation is latched in a per-lane register (source
+// line of the first one) and published when the instance ends (om_publish_violation).
+__device__ __forceinline__ long long om_chk(long long i, long long n, int line, uint32_t& latch) {
+  const bool bad = (i < 0) | (i >= n);
+  latch = (bad && latch == 0u) ? (uint32_t)line : latch;
+  return bad ? 0 : i;
+}
+__device__ __forceinline__ void om_publish_violation(uint32_t latch) {
+  if (latch != 0u && atomicAdd(&g_om_bounds[0], 1) == 0) g_om_bounds[1] = (int)latch;
 }
 
 // Out-of-line helpers: the hot loop must stay small enough for the instruction caches (profiles/r1_a),
@@ -215,6 +230,7 @@ struct Sim {
   unsigned long long tape_pos, tape_end;
   const double* tape_v;
   const uint8_t* tape_s;
+  uint32_t dbg_viol = 0;   // bounds-check build: source line of this lane's first out-of-range state access
   Philox4 ordw;   // words of the current order's Philox call (PHILOX mode)
   bool ordw_ready; // ordw already holds them (computed alongside the load draw earlier in this chain)
   uint32_t dirty; // slots (groups of 32 trucks) whose cached minimum is stale (see run())
@@ -329,7 +345,7 @@ struct Sim {
 #define OM_B_s_ability c.NS
 #define OM_B_scratch ((ly.slot_cache - ly.scratch) / 8u)
 #ifdef OM_BOUNDS_CHECK
-#define OM_IDX(field, i) om_chk((long long)(i), (long long)(OM_B_##field), __LINE__)
+#define OM_IDX(field, i) om_chk((long long)(i), (long long)(OM_B_##field), __LINE__, dbg_viol)
 #else
 #define OM_IDX(field, i) (i)
 #endif
@@ -389,6 +405,11 @@ struct Sim {
           r.arg0 = (uint16_t)arg0; r.arg1 = (uint16_t)arg1;
           out.trace[inst * (long long)out.trace_capacity + trace_count] = r;
         }
+        // Explicit reconvergence after a lane-0-only region: the warp-uniform code that follows reads state that the same
+        // code, run by another lane, changes (e.g. "is the unit still free?" before a grant).  A lane that fell behind here
+        // would find the grant already made by the others and skip its own copy of it -- harmless for the state, but lane 0
+        // owns the trace.  (Found with the bounds-checking build, whose extra branches made the compiler leave lane 0 behind.)
+        OM_RECONV();
       } else if (err == OM_IERR_NONE) {
         err = OM_IERR_TRACE_OVERFLOW;
       }
@@ -396,8 +417,10 @@ struct Sim {
     }
   }
   __device__ __forceinline__ void log_order(int kind, int site) {
-    if (TRACE && out.orders != nullptr && order_count < (uint32_t)out.order_capacity && lane == 0)
-      out.orders[inst * (long long)out.order_capacity + order_count] = (int16_t)((kind << 12) | site);
+    if (TRACE && out.orders != nullptr && order_count < (uint32_t)out.order_capacity) {
+      if (lane == 0) out.orders[inst * (long long)out.order_capacity + order_count] = (int16_t)((kind << 12) | site);
+      OM_RECONV();      // reconverge after the lane-0-only store (see emit())
+    }
     order_count++;
   }
 
@@ -429,7 +452,10 @@ struct Sim {
   __device__ __forceinline__ void tape_put(int site, double v) {
     if (TAPE_OUT && out.draw_values != nullptr) {
       if (tape_pos >= (unsigned long long)out.draw_capacity) { if (err == OM_IERR_NONE) err = OM_IERR_TRACE_OVERFLOW; }
-      else if (lane == 0) tape_put_at(tape_pos, site, v);
+      else {
+        if (lane == 0) tape_put_at(tape_pos, site, v);
+        OM_RECONV();    // reconverge after the lane-0-only store (see emit())
+      }
       tape_pos++;
     }
   }
@@ -1027,6 +1053,7 @@ struct Sim {
           out.unit_ticks[(inst * (long long)out.tick_capacity + k) * u_stride_out + u] = r;
         }
       }
+      OM_RECONV();      // reconverge after the lane-specific output stores
     }
     n_ticks++;
     if (RNG != OM_RNG_DET) {
@@ -1359,7 +1386,8 @@ struct Sim {
       if (!(tmin < until) || (err != OM_IERR_NONE && err != OM_IERR_TRACE_OVERFLOW)) break;
       now = tmin;
       n_hops++;
-      if (__builtin_expect(is_tick, 0)) { tick_block(); continue; }   // 15 % of the pops: keep its 12 KB out of the main path
+      OM_CONV();
+      if (__builtin_expect(is_tick, 0)) { tick_block(); OM_CONV(); continue; }   // 15 % of the pops: keep its 12 KB out of the main path
 
       const bool inl = now > 0.0;            // URGENT successors run inline
       const bool chain = unique && inl;      // same-time NORMAL successors run inline
@@ -1412,12 +1440,14 @@ struct Sim {
 
       // ================= chain 1: ARRIVE -> RET -> (grant) -> GRANTED -> BEGIN =================
     L_ARRIVE:                                                          // truck.py:211-218
+      OM_CONV();
       rl_close(acc_move, i);
       U8A(t_cur, i) = U8A(t_tgt, i);
       F64(t_prejam, i) = 0.0;
       if (!chain) { sched_truck(i, now, OM_KEY_NORMAL, PH_MOVE_RET); continue; }
       seq++;                                                           // Process(move) event
     L_MOVE_RET: {                                                      // truck.py:324-339 / 409-419
+      OM_CONV();
       int cur = U8A(t_cur, i);
       u = pick_unit(cur - 1);
       q_push(u, i);
@@ -1445,6 +1475,7 @@ struct Sim {
       seq++;                                                           // Request.succeed()
     }
     L_GRANTED:                                                         // truck.py:342-350 / 422-429
+      OM_CONV();
       u = U16A(t_unit, i);
       dump = u >= S;
       if (!dump) rl_close(acc_wait, i);
@@ -1467,6 +1498,7 @@ struct Sim {
 
       // ====== chain 2: DONE -> RET -> release + order -> MOVE_BEGIN -> depart -> Release pops -> (GRANTED) ======
     L_SVC_DONE: {                                                      // truck.py:230-235 / 243-251
+      OM_CONV();
       u = U16A(t_unit, i);
       dump = u >= S;
       double load;
@@ -1526,10 +1558,13 @@ struct Sim {
       kind = dump ? OM_ORDER_BACK : OM_ORDER_HAUL;
     L_ORDER: {                                                         // dispatcher.py:35-89 + truck.py:303-317,389-402,441-453
       if (__builtin_expect(disp == OM_DISP_EXTERNAL, 0)) { pause_for_order(i, kind, rel_u, rel_key, pend_truck, pend_kind); break; }
+      OM_CONV();
       int site = decide(kind, i);
+      OM_CONV();
       int nmax = (kind == OM_ORDER_HAUL) ? D : L;
       if (__builtin_expect(site < 0 || site >= nmax, 0)) { bad_order(i, kind, site, rel_u, rel_key); continue; }
       apply_order(i, kind, site);
+      OM_CONV();
       seq++;                                                           // env.process(move): Initialize URGENT
       if (!inl) {
         set_entry(i, now, seq - 1, PH_MOVE_BEGIN);
@@ -1549,8 +1584,10 @@ struct Sim {
       if (!dead && rep != 0.0) { begin_repair(i, rep); goto L_AFTER_DEPART; }
     }
     L_DEPART:                                                          // truck.py:151-210
+      OM_CONV();
       move_depart(i, dead);
     L_AFTER_DEPART:
+      OM_CONV();
       // the Release issued earlier in this chain is now the unique minimum: pop it
       if (rel_u < 0) continue;
       u = rel_u;
@@ -1837,6 +1874,7 @@ __device__ __forceinline__ void om_init_state(unsigned char* sm, unsigned char* 
                                               const OmStateLayout& ly, int lane, uint64_t seed, int dispatcher) {
   const double inf = om_inf();
   (void)inf;
+  uint32_t dbg_viol = 0;
   const bool SPLIT = true;   // accessors: follow the layout (ly.t_loc != 0 <=> the handle runs the SPLIT kernels)
   // zero everything first
   #pragma unroll 1
@@ -1874,5 +1912,8 @@ __device__ __forceinline__ void om_init_state(unsigned char* sm, unsigned char* 
     h->pending_truck = -1;
     h->pending_kind = -1;
   }
+#ifdef OM_BOUNDS_CHECK
+  om_publish_violation(dbg_viol);
+#endif
   __syncwarp();
 }

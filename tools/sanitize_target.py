@@ -13,7 +13,27 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def bounds_report():
+    import ctypes
+    from openmines_b200 import _lib
+    rep = (ctypes.c_int32 * 8)()
+    checks = _lib.load().om_debug_bounds_report(rep)
+    print("bounds-check build: %s; index violations %d (first: om_engine.cuh line %d, index %d, extent %d); "
+          "convergence violations %d (first: line %d, active mask %08x)" % (
+              {1: "yes", 2: "convergence probes only"}.get(checks, "NO (plain build)"), rep[0], rep[1], rep[2], rep[3], rep[4], rep[5], rep[6] & 0xFFFFFFFF), flush=True)
+    return checks, rep[0] + rep[4]
+
+
 def main():
+    try:
+        legs()
+    finally:
+        checks, bad = bounds_report()
+    if checks in (1, 2) and bad != 0:
+        sys.exit(9)
+
+
+def legs():
     import torch
     import openmines_b200 as om
     from conftest import load_cfg
@@ -28,7 +48,8 @@ def main():
         res = mine.run(until=until, trace_capacity=2048, site_ticks=True, unit_ticks=True, order_capacity=1024)
         for i, d in enumerate(DISPATCHERS):
             o = do.run_oracle(np_cfg, d, "det", seed=i, sim_time=until)
-            assert not engine_vs_ref(o, mine, res, i, sptf=(d == "SPTFDispatcher")), d
+            diffs = engine_vs_ref(o, mine, res, i, sptf=(d == "SPTFDispatcher"))
+            assert not diffs, (d, diffs[:4])
         print("det ok", flush=True)
     if "tape" in legs:
         gs = [Golden("live_north_pit_mine_%s_s11" % d) for d in ("SQDispatcher", "SPTFDispatcher")]
@@ -102,15 +123,6 @@ def main():
         from openmines_b200 import parallel
         assert np.array_equal(mine.stats(res).cpu().numpy(), parallel.stats_from_summaries(res.summary_np(), ids))
         print("stats ok", flush=True)
-    # the bounds-checking build reports what its accessors saw
-    import ctypes
-    from openmines_b200 import _lib
-    rep = (ctypes.c_int32 * 4)()
-    checks = _lib.load().om_debug_bounds_report(rep)
-    print("bounds-check build: %s; violations %d (first: om_engine.cuh line %d, index %d, extent %d)" % (
-        "yes" if checks == 1 else "NO (plain build)", rep[0], rep[1], rep[2], rep[3]), flush=True)
-    if checks == 1 and rep[0] != 0:
-        sys.exit(9)
 
 
 if __name__ == "__main__":

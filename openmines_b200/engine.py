@@ -91,6 +91,8 @@ class RunResult:
         self.unit_ticks = None
         self.draw_values = self.draw_sites = self.draw_count = None
         self.tick_capacity = self.trace_capacity = self.order_capacity = self.draw_capacity = 0
+        self.regrown = 0                 # instances re-simulated with a larger jam pool (run(regrow=True))
+        self.regrown_instances = []
 
     def summary_np(self):
         return self.summary.cpu().numpy().view(SUMMARY_DTYPE).reshape(-1)
@@ -229,6 +231,7 @@ class BatchedMine:
         seeds = np.asarray(seeds, dtype=np.uint64)
         assert seeds.shape == (self.n,)
         self.dispatcher_ids = torch.from_numpy(ids).to(self.device)
+        self._reset_args = (ids.copy(), seeds.copy(), rng_mode, tapes)
         self.has_external = bool((ids == DISPATCHER_IDS["external"]).any())
         self.seeds = torch.from_numpy(seeds.view(np.int64)).to(self.device)
         mode = RNG_MODES[rng_mode]
@@ -250,10 +253,16 @@ class BatchedMine:
         return self
 
     def run(self, until=None, ticks=True, trace_capacity=0, site_ticks=False, order_capacity=0, result=None,
-            unit_ticks=False, draw_capacity=0):
+            unit_ticks=False, draw_capacity=0, regrow=False):
         """Advance every instance to simulated time ``until`` (default: the config's sim_time).
         ``draw_capacity`` > 0 (rng_mode="philox" only): export every instance's draw tape (``RunResult.draw_tape``);
-        ``draw_tape_slots()`` gives a safe size."""
+        ``draw_tape_slots()`` gives a safe size.
+        ``regrow=True`` (whole-episode runs after ``reset()``): instances that stopped because more jams were active at once
+        than ``jam_capacity`` holds (OM_IERR_JAM_OVERFLOW) are re-simulated from t = 0 in a temporary handle with a four
+        times larger pool -- same config, dispatcher, seed and RNG mode, hence the same trajectory, now complete -- and their
+        outputs replace the truncated ones (``result.regrown`` / ``regrown_instances``).  Their state blobs in THIS handle
+        stay as they stopped (blob sizes differ between pool sizes), so do not resume such a batch.  Costs one
+        synchronising read of the summaries."""
         torch = self.torch
         if getattr(self, "has_external", False):
             raise RuntimeError("BatchedMine.run: the batch holds instances of a host-side dispatcher (device id 255); om_run "
@@ -294,7 +303,37 @@ class BatchedMine:
         o.orders, o.order_capacity = ptr(r.orders), r.order_capacity
         o.unit_ticks = ptr(r.unit_ticks)
         self._ck(self.lib.om_run(self.h, until, ctypes.c_void_p(self.state.data_ptr()), ctypes.byref(o), self._stream()))
+        if regrow:
+            self._regrow(r, until, site_ticks, unit_ticks)
         return r
+
+    def _regrow(self, r, until, site_ticks, unit_ticks):
+        torch = self.torch
+        OM_IERR_JAM_OVERFLOW = 3
+        todo = np.nonzero(r.summary_np()["err"] == OM_IERR_JAM_OVERFLOW)[0]
+        r.regrown, r.regrown_instances = len(todo), [int(i) for i in todo]
+        ids, seeds, rng_mode, tapes = self._reset_args
+        cap = max(pc.jam_capacity for pc in self.pcs)
+        while len(todo):
+            if cap >= 4096:
+                raise RuntimeError("jam pool overflow with the largest supported pool (4096) in %d instances" % len(todo))
+            cap = min(4096, cap * 4)
+            raws = [pc.raw for pc in self.pcs]
+            sub = BatchedMine(raws if self.multi else raws[0], len(todo), device=self.device.index, jam_capacity=cap,
+                              sum_mode=self.pc.sum_mode, rl_surface=False,
+                              config_ids=self.config_ids[todo] if self.multi else None)
+            sub.reset(ids[todo], seeds=seeds[todo], rng_mode=rng_mode, tapes=[tapes[i] for i in todo] if tapes is not None else None)
+            q = sub.run(until=until, ticks=r.ticks is not None, trace_capacity=r.trace_capacity, site_ticks=site_ticks,
+                        order_capacity=r.order_capacity, unit_ticks=unit_ticks, draw_capacity=r.draw_capacity)
+            idx = torch.from_numpy(todo).to(self.device)
+            for f in ("summary", "ticks", "trace", "site_queue_ticks", "site_tons_ticks", "orders", "unit_ticks", "draw_values",
+                      "draw_sites", "draw_count"):
+                dst, src = getattr(r, f), getattr(q, f)
+                if dst is not None and src is not None:
+                    dst[idx] = src
+            still = q.summary_np()["err"] == OM_IERR_JAM_OVERFLOW
+            sub.close()
+            todo = todo[still]
 
     def draw_tape_slots(self, until=None):
         """Upper estimate of the draw-tape slots one instance needs up to ``until``: two per truck per minute (breakdown

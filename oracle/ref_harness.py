@@ -95,9 +95,10 @@ def load_reference(ref_root=REF_ROOT_DEFAULT):
     from openmines.src.dispatch_algorithms.fixed_group_dispatcher import FixedGroupDispatcher
     from openmines.src.dispatch_algorithms.sptf_dispatcher import SPTFDispatcher
     from openmines.src.dispatch_algorithms.sq_dispatcher import SQDispatcher
+    from openmines.src.dispatch_algorithms.shortest_trip_dispatcher import ShortestTripDispatcher
     ns.run_mod, ns.mine_mod, ns.event_mod = run_mod, mine_mod, event_mod
     ns.dispatchers = {c.__name__: c for c in (NaiveDispatcher, RandomDispatcher, NearestDispatcher,
-                                              FixedGroupDispatcher, SPTFDispatcher, SQDispatcher)}
+                                              FixedGroupDispatcher, SPTFDispatcher, SQDispatcher, ShortestTripDispatcher)}
     import openmines.src.load_site as ls_mod
     import openmines.src.dump_site as ds_mod
     import openmines.src.charging_site as cs_mod

@@ -430,3 +430,62 @@ def test_c_program_through_the_c_abi_vs_golden(tmp_path):
         assert int(row[3]) == int(g.n_truck_events)
         assert int(row[5]) == int(g.n_ticks) and int(row[6]) == 0
         assert float(row[7]) == float(g.tick["produced_tons"][60])
+
+
+def test_shortest_trip_dispatcher_vs_reference_goldens(north_pit, ragged_mine):
+    """OM_DISP_SHORTESTTRIP in om_run against goldens of the unmodified reference running ShortestTripDispatcher as a
+    dispatcher (tests/golden/make_golden_teacher.py): det and tape replay, north_pit and the ragged mine."""
+    d = "ShortestTripDispatcher"
+    for cname, cfg, jam in (("north_pit_mine", north_pit, 64), ("ragged_mine", ragged_mine, 128)):
+        gd, gl = Golden("det_%s_%s_s0" % (cname, d)), Golden("live_%s_%s_s17" % (cname, d))
+        mine = _mine(cfg, 1, jam_capacity=jam)
+        mine.reset(d, rng_mode="det")
+        res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=4096)
+        assert not engine_vs_ref(gd, mine, res, 0), cname
+        mine.reset(d, rng_mode="tape", tapes=[gl.tape])
+        res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=4096)
+        assert not engine_vs_ref(gl, mine, res, 0), cname
+
+
+def test_naive_sum_flavour_vs_oracle(north_pit):
+    """OmConfig.sum_mode = 0: the reference under CPython <= 3.11 (its CI pins 3.9.6, .github/workflows/pypi.yml:19), whose
+    sum() adds left to right instead of the Neumaier-compensated sum of CPython >= 3.12.  Decisions of SPTF
+    (sptf_dispatcher.py:35) and every reported tonnage (dump_site.py:69, mine.py:61) go through sum(): live oracle runs with
+    sum_mode="naive" -> tape -> engine with sum_mode="naive", bit-exact; and the two flavours do differ on the same tape."""
+    from oracle import des_oracle as do
+    names = ["SPTFDispatcher", "SQDispatcher", "FixedGroupDispatcher", "RandomDispatcher"]
+    oracles = [do.run_oracle(north_pit, d, "live", seed=40 + k, sum_mode="naive") for k, d in enumerate(names)]
+    mine = _mine(north_pit, len(names), sum_mode="naive")
+    mine.reset(names, rng_mode="tape", tapes=[o.tape for o in oracles])
+    res = mine.run(trace_capacity=8192, site_ticks=True, order_capacity=2048)
+    for i, d in enumerate(names):
+        diffs = engine_vs_ref(oracles[i], mine, res, i, sptf=(d == "SPTFDispatcher"))
+        assert not diffs, "%s: %s" % (d, diffs[:5])
+    naive_curves = res.ticks_np()["produced_tons"].copy()
+    comp = _mine(north_pit, len(names))                       # default: Neumaier
+    comp.reset(names, rng_mode="tape", tapes=[o.tape for o in oracles])
+    res2 = comp.run(trace_capacity=8192)
+    comp_curves = res2.ticks_np()["produced_tons"]
+    assert (naive_curves != comp_curves).any(), "the summation flavour should show in the last bits of the production curves"
+    assert np.allclose(naive_curves, comp_curves, rtol=1e-12)
+
+
+def test_jam_pool_overflow_is_regrown_not_lost(north_pit):
+    """A jam pool that is too small stops the instance with OM_IERR_JAM_OVERFLOW; run(regrow=True) re-simulates exactly those
+    instances with a larger pool and patches their outputs in, so the batch equals one run with a big pool from the start."""
+    n = 256
+    names = ["SQDispatcher", "SPTFDispatcher"] * (n // 2)
+    seeds = np.arange(n, dtype=np.uint64) + 900
+    big = _mine(north_pit, n, jam_capacity=128)
+    big.reset(names, seeds=seeds, rng_mode="philox")
+    want = big.run()
+    small = _mine(north_pit, n, jam_capacity=12)
+    small.reset(names, seeds=seeds, rng_mode="philox")
+    raw = small.run().summary_np()
+    n_over = int((raw["err"] == 3).sum())
+    assert n_over > 0                                        # 12 entries do overflow on north_pit
+    small.reset(names, seeds=seeds, rng_mode="philox")
+    got = small.run(regrow=True)
+    assert got.regrown == n_over
+    assert got.summary_np().tobytes() == want.summary_np().tobytes()
+    assert got.ticks_np().tobytes() == want.ticks_np().tobytes()

@@ -222,3 +222,15 @@ def test_oracle_one_truck_mine(one_truck_mine):
 def test_oracle_integer_mine_tie_stress(d, integer_mine):
     """All durations are whole minutes, so truck hops, Releases and the per-minute monitors tie constantly."""
     assert not _same(Golden("det_integer_mine_%s_s0" % d), do.run_oracle(integer_mine, d, "det", seed=0))
+
+
+@pytest.mark.parametrize("cname", ["north_pit_mine", "ragged_mine"])
+def test_oracle_shortest_trip_matches_reference_golden(cname, north_pit, ragged_mine):
+    """ShortestTripDispatcher run AS A DISPATCHER by the unmodified reference (tests/golden/make_golden_teacher.py): det,
+    live with the same seeds (tape included) and tape replay."""
+    cfg = north_pit if cname == "north_pit_mine" else ragged_mine
+    d = "ShortestTripDispatcher"
+    assert not _same(Golden("det_%s_%s_s0" % (cname, d)), do.run_oracle(cfg, d, "det"))
+    g = Golden("live_%s_%s_s17" % (cname, d))
+    assert not _same(g, do.run_oracle(cfg, d, "live", seed=17), check_tape=True)
+    assert not _same(g, do.run_oracle(cfg, d, "replay", tape=g.tape), check_tape=True)

@@ -372,17 +372,27 @@ def run_c4(a):
         sm = e2e_tot[1:].clone(); dist.all_reduce(sm)
         e2e_tot = torch.cat([mx, sm])
     e2e_ms, e2e_events, e2e_dec = [float(x) for x in e2e_tot.cpu()]
-    # kernel-only timing of om_step for the HBM roofline (same steady state, constant action)
+    # kernel-only timing of om_step for the roofline: the same rollout (the policy keeps choosing the actions, so the envs stay
+    # in the regime `value` was measured in), launched eagerly with one event pair around every om_step
     act = torch.zeros(n, dtype=torch.int32, device=dev)
+
+    def policy_action():
+        with torch.no_grad():
+            act.copy_(torch.distributions.Categorical(logits=policy(env.io["obs"]), validate_args=False).sample())
+
     for _ in range(20):
+        policy_action()
         env._step(act)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
+    pairs = []
     for _ in range(100):
+        policy_action()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
         env._step(act)
-    k1.record()
+        k1.record()
+        pairs.append((k0, k1))
     torch.cuda.synchronize()
-    step_ms = k0.elapsed_time(k1) / 100
+    step_ms = sum(x.elapsed_time(y) for x, y in pairs) / len(pairs)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -392,6 +402,20 @@ def run_c4(a):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     alg = n * (2 * env.mine.state_bytes + env.obs_dim * 4 + 4 + 8 + 1 + 3 * 4 + 32)
     achieved = alg / (step_ms / 1000.0) / 1e9
+    counters = {"error": "skipped"}
+    if rank == 0 and not a.no_counters:
+        counters = live_counters(local, policy_action, lambda: env._step(act), torch.cuda.synchronize)
+    issue = None
+    if "error" not in counters:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        inst = counters["smsp__inst_executed.sum"]
+        issue = {"warp_inst_per_launch": inst, "warp_inst_per_env_step": inst / n,
+                 "achieved_inst_per_s": inst / (step_ms / 1000.0), "peak_inst_per_s": sms * 4 * sm_mhz * 1e6,
+                 "frac": inst / (step_ms / 1000.0) / (sms * 4 * sm_mhz * 1e6),
+                 "issue_active_pct": counters.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                 "dram_bytes": counters["dram__bytes_read.sum"] + counters["dram__bytes_write.sum"],
+                 "source": counters["source"]}
     line = {"metric": METRIC, "value": n_events / sec,
             "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -415,10 +439,11 @@ def run_c4(a):
                             "PCIe)" % e2e_steps},
             "gpu_launches": a.steps * steps_per,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "kernel": "om_step_kernel<philox>", "kernel_ms": step_ms,
+                         "traffic": (issue or {}).get("dram_bytes"), "issue": issue if issue else counters,
+                         "kernel": "om_step_kernel<philox>", "kernel_ms": step_ms,
                          "algorithmic_bytes_per_launch": alg,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                         "note": "kernel_ms measured in steady state with a constant action (100 launches)"}}
+                         "note": "kernel_ms: mean over 100 om_step launches of the same policy-driven rollout, one CUDA-event pair around each"}}
     if rank == 0:
         emit_line(line)
     if dist is not None:

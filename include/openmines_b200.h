@@ -293,6 +293,8 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
 int om_stats_reduce(OmHandle h, const OmSummary* summary, const int32_t* dispatcher,
                     double* stats_out, void* stream);
 
+#define OM_STEP_WRITE_STATIC 4 /* (re)write the observation columns that never change (the road distances); om_step sets it
+                                  by itself whenever it is handed an observation buffer it has not written before */
 #define OM_STEP_AUTO_RESET 1
 #define OM_STEP_SPARSE_REWARD 2 /* reward_mode="sparse" (rl_dispatch.py:186-192): 0 at every decision; the final step carries the
                                    dense reward of Mine.start_rl (mine.py:456-459) with last_production never updated */

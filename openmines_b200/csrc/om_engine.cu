@@ -55,6 +55,19 @@ __device__ __forceinline__ void om_stage_out(unsigned char* g, const unsigned ch
   __syncwarp();
 }
 
+// The work queue is one atomic counter; the last warp of a launch to leave it puts it (and the exit count) back to zero, so a
+// launch needs no memset in front of it (one stream operation less per env step; safe under CUDA-graph replay, where the
+// kernel parameters are frozen).  When the last warp retires every other warp has already seen the queue empty.
+__device__ __forceinline__ void om_retire_warp(const RunParams& p, int lane) {
+  if (lane == 0) {
+    const unsigned long long total = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    if (atomicAdd(p.counter + 1, 1ull) == total - 1ull) {
+      p.counter[0] = 0ull;
+      p.counter[1] = 0ull;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
@@ -156,6 +169,7 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
 #endif
     om_stage_out(g, sm, staged, lane);
   }
+  om_retire_warp(p, lane);
 }
 
 // Batched gym-style step: one warp per env; the state blob round-trips HBM every step (this kernel IS
@@ -187,6 +201,7 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_step_kernel(c
 #endif
     om_stage_out(g, sm, staged, lane);
   }
+  om_retire_warp(p, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -307,6 +322,7 @@ struct OmEngine {
   const DevCfg* d_cfgs = nullptr;
   const int32_t* d_cfg_id = nullptr;   // [n] config of every instance (mixed-config handles only)
   bool multi = false;
+  const void* last_obs = nullptr;      // observation buffer of the previous om_step (static columns already written there)
   OmStateLayout ly;
   std::vector<void*> dev_allocs;
   unsigned long long* counter = nullptr;
@@ -502,6 +518,25 @@ static int build_devcfg(OmEngine* h, const OmConfig* cfg, DevCfg& c) {
     if (rc == OM_OK) rc = upload(h, trip.data(), trip.size(), &c.trip60);
   }
   if (rc == OM_OK) {
+    // observation helpers of the RL surface (see DevCfg)
+    std::vector<float> tt(c.R), df(c.R);
+    for (int r = 0; r < c.R; ++r) {
+      volatile double m = cfg->road_distance[r] * 60.0;
+      tt[r] = (float)(m / 25.0);
+      df[r] = (float)cfg->road_distance[r];
+    }
+    std::vector<double> iu(c.NS), ip(L), idc(M);
+    for (int s = 0; s < c.NS; ++s) iu[s] = 1.0 / (double)(cfg->site_unit_begin[s + 1] - cfg->site_unit_begin[s]);
+    for (int s = 0; s < L; ++s) ip[s] = 1.0 / cfg->site_productivity[s];
+    for (int u = 0; u < M; ++u) idc[u] = 1.0 / cfg->dumper_cycle[u];
+    c.inv_tn = 1.0 / ((double)T + 1e-8);
+    rc = upload(h, tt.data(), tt.size(), &c.obs_tt);
+    if (rc == OM_OK) rc = upload(h, df.data(), df.size(), &c.obs_dist);
+    if (rc == OM_OK) rc = upload(h, iu.data(), iu.size(), &c.inv_units);
+    if (rc == OM_OK) rc = upload(h, ip.data(), ip.size(), &c.inv_prod);
+    if (rc == OM_OK) rc = upload(h, idc.data(), idc.size(), &c.inv_dcycle);
+  }
+  if (rc == OM_OK) {
     std::vector<int32_t> rb(c.NS + 1);
     rb[0] = -1;
     for (int cur = 1; cur <= c.NS; ++cur)
@@ -557,7 +592,8 @@ static int create_impl(const OmConfig* const* cfgs, int32_t n_configs, const int
   }
   if (rc == OM_OK) {
     void* d = nullptr;
-    e = cudaMalloc(&d, sizeof(unsigned long long));
+    e = cudaMalloc(&d, 2 * sizeof(unsigned long long));          // {work-queue counter, retired warps}: see om_retire_warp
+    if (e == cudaSuccess) e = cudaMemset(d, 0, 2 * sizeof(unsigned long long));
     if (e != cudaSuccess) rc = set_err(h, OM_E_CUDA, cudaGetErrorString(e));
     else { h->counter = (unsigned long long*)d; h->dev_allocs.push_back(d); }
   }
@@ -686,6 +722,7 @@ int om_reset(OmHandle h, const uint64_t* seeds, const int32_t* dispatcher, int r
   h->rng_mode = rng_mode;
   h->reset_done = true;
   h->tape_values = tape_values; h->tape_sites = tape_sites; h->tape_offsets = tape_offsets;
+  CK(cudaMemsetAsync(h->counter, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));   // also after an aborted launch
   const int wpb = 8;
   long long blocks = (h->n + wpb - 1) / wpb;
   om_reset_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(h->d_cfgs, h->d_cfg_id, h->ly, (unsigned char*)state,
@@ -712,7 +749,6 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
   p.order = h->order;
   p.cfgs = h->d_cfgs; p.cfg_id = h->d_cfg_id; p.ns_stride = h->c.NS; p.u_stride_out = h->c.U;
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
   if (p.out.draw_values != nullptr && (p.out.draw_sites == nullptr || p.out.draw_capacity <= 0))
     return set_err(h, OM_E_INVALID, "om_run: draw_values needs draw_sites and draw_capacity > 0");
   if (p.out.draw_values != nullptr && h->rng_mode != OM_RNG_PHILOX)
@@ -759,14 +795,18 @@ int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* str
   memset(&p, 0, sizeof(p));
   p.c = h->c; p.ly = h->ly;
   p.c.sim_time = until;
+  p.c.inv_sim_time = 1.0 / until;
   p.io = *io;
+  if ((const void*)io->obs != h->last_obs) {      // a buffer this handle has not written yet: its static columns too
+    p.io.flags |= OM_STEP_WRITE_STATIC;
+    h->last_obs = (const void*)io->obs;
+  }
   om_obs_dim(h, &p.obs_dim);
   p.state = (unsigned char*)state;
   p.tape_values = h->tape_values; p.tape_sites = h->tape_sites; p.tape_offsets = h->tape_offsets;
   p.counter = h->counter; p.n_instances = h->n; p.until = until;
   p.cfgs = h->d_cfgs; p.cfg_id = nullptr; p.ns_stride = h->c.NS; p.u_stride_out = h->c.U;
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
   switch (h->rng_mode) {
 #define OM_STEP(MODE)                                                                        \
   do {                                                                                       \

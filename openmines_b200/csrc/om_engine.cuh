@@ -97,6 +97,15 @@ struct DevCfg {
   const int32_t* fixed_group;
   const double* shovel_rate;
   const double* site_prod;
+  // RL observation helpers (built in om_create; reciprocals replace ~10 fp64 divisions per env step -- observations are
+  // float32 and pinned to the reference at 2 ulp fp32, the reward and the teacher keep their exact divisions)
+  const float* obs_tt;        // [R] (road_distance * 60) / 25 as float: travel minutes at the hard-coded speed (feature_processing.py:43)
+  const float* obs_dist;      // [R] road_distance as float (static block of the observation)
+  const double* inv_units;    // [NS] 1 / units of the site
+  const double* inv_prod;     // [L] 1 / load_site_productivity
+  const double* inv_dcycle;   // [M] 1 / dumper cycle time
+  double inv_tn;              // 1 / (T + 1e-8)
+  double inv_sim_time;        // om_step: 1 / until
   double sim_time;
   double road_lambda, road_mu, road_sigma, detour_mu, detour_sigma;
   double breakdown_mean, repair_mu, repair_sigma, unrepairable_mean, maint_mean, maint_mu, maint_sigma;
@@ -711,7 +720,11 @@ struct Sim {
   // ---------------------------------------------------------------------------------------------
   // Every helper below (unit_est_all, site_est, road_load, argmin_lanes) has ONE call site: they are force-inlined,
   // and duplicated copies of them used to make this function 14 KB of SASS in the middle of the hot order chain.
-  __device__ __forceinline__ int decide(int kind, int i, bool est_ready = false) {
+  // `est_ready`: both sides' wait estimates are in scratch already; `shared_on` / `shared_cap` (lane q = candidate q): the
+  // moving trucks / their capacity sum on the roads from the truck's CURRENT location, as the RL observation just counted
+  // them -- the ShortestTrip teacher looks at the same roads for haul and init orders (have_shared).
+  __device__ __forceinline__ int decide(int kind, int i, bool est_ready = false, bool have_shared = false, int shared_on = 0,
+                                        double shared_cap = 0.0) {
     int r = 0;
     const int L = c.L, D = c.D;
     const bool haul = kind == OM_ORDER_HAUL;
@@ -801,9 +814,9 @@ struct Sim {
         // on the charging-site roads (:71).
         const double v = __ldg(&c.speed[i]);
         const int cur = U8A(t_cur, i);
-        int pc_, cnt;
-        double capsum;
-        road_load(haul ? cur : 0, 1 + sbase_site, n, pc_, cnt, capsum);
+        int pc_ = 0, cnt = shared_on;
+        double capsum = shared_cap;
+        if (!(have_shared && (haul || cur == 0))) road_load(haul ? cur : 0, 1 + sbase_site, n, pc_, cnt, capsum);
         if (lane < n) {
           int site = sbase_site + lane, tgt = 1 + site;
           int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
@@ -967,7 +980,7 @@ struct Sim {
     const int k = (int)now;
     const bool neu = c.sum_mode != 0;
     // (1) queue totals per site (load_site.py:81-83) and site tons (load_site.py:175, dump_site.py:69)
-    double site_tons = 0.0;
+    double site_tons = 0.0, rl_cap = 0.0;
     uint32_t qtot = 0, site_svc = 0;
     if (lane < NS) {
       int ub = __ldg(&c.ubeg[lane]), ue = __ldg(&c.ubeg[lane + 1]);
@@ -981,22 +994,30 @@ struct Sim {
       site_tons = ps.result(neu);
       U16A(s_qtotal, lane) = (uint16_t)qtot;
       if (RL) {
-        // minute-sampled values the observation reads (load_site.py:175-185, dump_site.py:69-78)
-        F64(s_tons, lane) = site_tons;
+        // minute-sampled values the observation reads (load_site.py:175-185, dump_site.py:69-78).  They change once per
+        // minute but are observed at every decision, so the observation's log(x + 1) of them is taken here, once:
+        // s_tons <- log(site tons + 1), s_cap <- log(capacity + 1), s_ability <- service ability ratio.
         if (lane < L) {
           PySum pa; pa.init();
 #pragma unroll 1
           for (int u = ub; u < ue; ++u) pa.add(__ldg(&c.shovel_rate[u]) * (U8A(u_repair, u) ? 0.0 : 1.0), neu);
-          double prod = __ldg(&c.site_prod[lane]);
-          F64(s_cap, lane) = prod;
-          F64(s_ability, lane) = om_ddiv(pa.result(neu), prod);
+          rl_cap = __ldg(&c.site_prod[lane]);
+          F64(s_ability, lane) = pa.result(neu) * __ldg(&c.inv_prod[lane]);
         } else {
           PySum pd; pd.init();
 #pragma unroll 1
-          for (int u = ub; u < ue; ++u) pd.add(om_ddiv0(F64(u_tons, u), __ldg(&c.dcycle[u - c.S])), neu);
-          F64(s_cap, lane) = pd.result(neu);
+          for (int u = ub; u < ue; ++u) pd.add(F64(u_tons, u) * __ldg(&c.inv_dcycle[u - c.S]), neu);
+          rl_cap = pd.result(neu);
           F64(s_ability, lane) = 1.0;
         }
+      }
+    }
+    if (RL) {
+      // one log call for both blocks: lanes [0, NS) capacity, the same lanes' tons in a second trip of a rolled loop
+#pragma unroll 1
+      for (int w = 0; w < 2; ++w) {
+        const double v = om_dlog(((w == 0) ? rl_cap : site_tons) + 1.0);
+        if (lane < NS) { if (w == 0) F64(s_cap, lane) = v; else F64(s_tons, lane) = v; }
       }
     }
     tick_k = k;
@@ -1628,37 +1649,33 @@ struct Sim {
       acc_wait = acc_shovel = acc_dumper = acc_move = acc_jam = 0.0;
       return 0.0;
     }
-    double w = 0.0, sh = 0.0, du = 0.0, mv = 0.0, jm = 0.0;
+    // The four duration penalties are one weighted sum: -0.1 wait - 0.05 (shovel + dumper) - 0.05 jam - 0.01 move
+    // (rl_dispatch.py:282-291).  Every lane accumulates its trucks' / jams' share already weighted, so ONE warp sum is
+    // needed instead of five (the reward is pinned to the reference at 1e-9 relative; the order of these additions moves
+    // it by ~1e-16).
+    double pen = 0.0;
 #pragma unroll 1
     for (int i = lane; i < T; i += 32) {           // intervals still open at this decision
       int ph = (int)U32A(t_phase, i), cur = U8A(t_cur, i);
       double st = F64(t_since, i);
       double lo = (st > rl_last) ? st : rl_last;
       double part = (lo < now) ? (now - lo) : 0.0;
-      if ((ph == PH_WAITING || ph == PH_LOAD_GRANTED) && cur >= 1 && cur <= c.L) w += part;
-      else if (ph == PH_LOAD_BEGIN || ph == PH_LOAD_DONE || ph == PH_LOAD_RET) sh += part;
-      else if (ph == PH_DUMP_BEGIN || ph == PH_DUMP_DONE || ph == PH_DUMP_RET) du += part;
-      else if (ph == PH_MOVE_ARRIVE) mv += part;
+      double wt = 0.0;
+      if ((ph == PH_WAITING || ph == PH_LOAD_GRANTED) && cur >= 1 && cur <= c.L) wt = 0.1;
+      else if (ph == PH_LOAD_BEGIN || ph == PH_LOAD_DONE || ph == PH_LOAD_RET || ph == PH_DUMP_BEGIN || ph == PH_DUMP_DONE ||
+               ph == PH_DUMP_RET) wt = 0.05;
+      else if (ph == PH_MOVE_ARRIVE) wt = 0.01;
+      pen += wt * part;
     }
 #pragma unroll 1
     for (uint32_t j = lane; j < jam_count; j += 32) {
       double st = F64(j_start, j), en = F64(j_end, j);
       double lo = (st > rl_last) ? st : rl_last, hi = (en < now) ? en : now;
-      if (lo < hi) jm += hi - lo;
+      if (lo < hi) pen += 0.05 * (hi - lo);
     }
-    // one butterfly for the five partial sums (same xor order per value as five separate reductions)
 #pragma unroll 1
-    for (int o = 16; o > 0; o >>= 1) {
-      w += __shfl_xor_sync(OM_FULL, w, o);
-      sh += __shfl_xor_sync(OM_FULL, sh, o);
-      du += __shfl_xor_sync(OM_FULL, du, o);
-      mv += __shfl_xor_sync(OM_FULL, mv, o);
-      jm += __shfl_xor_sync(OM_FULL, jm, o);
-    }
-    w = acc_wait + w;
-    double service = (acc_shovel + sh) + (acc_dumper + du);
-    mv = acc_move + mv;
-    jm = acc_jam + jm;
+    for (int o = 16; o > 0; o >>= 1) pen += __shfl_xor_sync(OM_FULL, pen, o);
+    pen += 0.1 * acc_wait + 0.05 * (acc_shovel + acc_dumper) + 0.05 * acc_jam + 0.01 * acc_move;
     double final_reward = 0.0;
     if (final_step && now != 0.0) {
       double ft = rl_last_prod - 10000.0;
@@ -1666,7 +1683,7 @@ struct Sim {
     }
     double delta = reported_tons - rl_last_prod;   // mine.produce_tons is the minute-sampled value
     rl_last_prod = reported_tons;
-    double reward = -0.1 * w + -0.05 * service + -0.05 * jm + -0.01 * mv + 5.0 * om_dlog(delta + 1.0) + final_reward;
+    double reward = -pen + 5.0 * om_dlog(delta + 1.0) + final_reward;
     double dt = now - rl_last;
     if (dt > 0.0) reward += 0.1 * om_ddiv0(delta, dt + 1e-6);
     acc_wait = acc_shovel = acc_dumper = acc_move = acc_jam = 0.0;
@@ -1675,14 +1692,17 @@ struct Sim {
 
   // Observation of the pending decision (truck i, order kind).  Layout generalises the reference's
   // L = D = 5 vector: C = max(L, D) candidate slots (zero padded), NS = L + D, R roads.
-  __device__ __forceinline__ void rl_observation(int i, int kind, float* ob) {
-    const int T = c.T, L = c.L, D = c.D, NS = c.NS, R = c.R;
+  // Returns (through the reference parameters) the trucks on the candidate roads from the current location as
+  // road_load() found them (lane q = candidate q), for the teacher to reuse when it looks at the same roads.
+  __device__ __forceinline__ void rl_observation(int i, int kind, float* ob, bool write_static, int& pair_cnt, int& on_cnt,
+                                                 double& capsum) {
+    const int L = c.L, D = c.D, NS = c.NS, R = c.R;
     const int C = L > D ? L : D;
     const int o1 = 6, o2 = o1 + 1 + NS, o3 = o2 + 2, o4 = o3 + C, o5 = o4 + C, o6 = o5 + R, o7 = o6 + R,
               o8 = o7 + C, o9 = o8 + NS, o10 = o9 + NS, o11 = o10 + NS, o12 = o11 + NS;
     const int cur = U8A(t_cur, i);
-    const double tn = (double)T + 1e-8;
-    // all roads: distance and active-jam count (lanes over the jam pool, shared-memory counters per road)
+    // all roads: active-jam count (lanes over the jam pool, shared-memory counters per road); the road distances never
+    // change, so they are written only when the caller hands in a new observation buffer (OM_STEP_WRITE_STATIC)
     {
       uint32_t* rj = (uint32_t*)(sm + ly.scratch);   // scratch is reused by unit_est_all() right after
 #pragma unroll 1
@@ -1694,7 +1714,7 @@ struct Sim {
       __syncwarp();
 #pragma unroll 1
       for (int r = lane; r < R; r += 32) {
-        ob[o5 + r] = (float)__ldg(&c.rdist[r]);
+        if (write_static) ob[o5 + r] = __ldg(&c.obs_dist[r]);
         ob[o6 + r] = (float)rj[r];
       }
       __syncwarp();
@@ -1702,52 +1722,68 @@ struct Sim {
     // dispatcher.update_mine (dispatcher.py:24-33): both sides' wait estimates (one inlined copy, two trips)
 #pragma unroll 1
     for (int side = 0; side < 2; ++side) unit_est_all(side == 0);
+    // estimated_queue_wait_time of every site, lane = site (NS <= 32)
+    const double est_site = (lane < NS) ? site_est(lane) : 0.0;
     if (lane == 0) {
       ob[0] = kind == OM_ORDER_INIT ? 1.f : 0.f; ob[1] = kind == OM_ORDER_HAUL ? 1.f : 0.f;
       ob[2] = kind == OM_ORDER_BACK ? 1.f : 0.f;
       ob[3] = (float)(now - rl_last);
-      double time_now = om_ddiv0(now, c.sim_time);
+      double time_now = now * c.inv_sim_time;
       ob[4] = (float)time_now; ob[5] = (float)(1.0 - time_now);
-      ob[o2] = (float)om_dlog(F64(t_load, i) + 1.0);
-      ob[o2 + 1] = (float)om_dlog(F64(t_cycle, i) + 1.0);
     }
 #pragma unroll 1
     for (int q = lane; q < 1 + NS; q += 32) ob[o1 + q] = (q == cur) ? 1.f : 0.f;
     // candidate roads from the current location
     const int ncand = (kind == OM_ORDER_HAUL) ? D : L;
-    {
-      int pair_cnt, on_cnt;
-      double capsum;
-      road_load(cur, (kind == OM_ORDER_HAUL) ? 1 + L : 1, ncand, pair_cnt, on_cnt, capsum);
+    const int tgt0 = (kind == OM_ORDER_HAUL) ? 1 + L : 1;
+    road_load(cur, tgt0, ncand, pair_cnt, on_cnt, capsum);
+    // Every log(x + 1) of the observation in ONE pass over "log slots" (a single copy of the fp64 log, one trip for
+    // north_pit's 17 slots instead of six calls): slot 0 truck load, 1 truck cycle time, 2 .. 2+C candidate wait,
+    // 2+C .. 2+C+NS site wait.  Lanes take their slot's argument from the lane that owns it by shuffle.
+    __syncwarp();
+    const int nlog = 2 + C + NS;
 #pragma unroll 1
-      for (int q = lane; q < C; q += 32) {          // C <= 32: one trip, lane q = candidate q
-        float tt = 0.f, tc = 0.f, sw = 0.f;
-        if (q < ncand) {
-          int tgt = (kind == OM_ORDER_HAUL) ? 1 + L + q : 1 + q;
-          int site = tgt - 1;
-          double dist = __ldg(&c.rdist[road_id(cur, tgt)]);
-          tt = (float)om_ddiv(dist * 60.0, 25.0);                        // speed is hard-coded (feature_processing.py:43)
-          tc = (float)om_ddiv0((double)pair_cnt, tn);
+    for (int base = 0; base < nlog; base += 32) {
+      const int q = base + lane;
+      const int cq = q - 2, sq = q - 2 - C;                      // candidate / site index of this slot
+      // operands owned by other lanes (all lanes take part in the shuffles)
+      const int src_c = (cq >= 0 && cq < C) ? cq : 0, src_s = (sq >= 0 && sq < NS) ? sq : 0;
+      const int site_of_c = tgt0 - 1 + src_c;                     // site of candidate src_c
+      const double est_c = __shfl_sync(OM_FULL, est_site, site_of_c < NS ? site_of_c : 0);
+      const double est_s = __shfl_sync(OM_FULL, est_site, src_s);
+      const int pc_c = __shfl_sync(OM_FULL, pair_cnt, src_c), on_c = __shfl_sync(OM_FULL, on_cnt, src_c);
+      const double cap_c = __shfl_sync(OM_FULL, capsum, src_c);
+      double arg = 0.0;
+      int dst = -1;
+      if (q == 0) { arg = F64(t_load, i); dst = o2; }
+      else if (q == 1) { arg = F64(t_cycle, i); dst = o2 + 1; }
+      else if (cq < C) {
+        dst = o7 + cq;
+        float tt = 0.f, tc = 0.f;
+        if (cq < ncand) {
+          const int tgt = tgt0 + cq, site = tgt - 1;
+          tt = __ldg(&c.obs_tt[road_id(cur, tgt)]);                      // (distance * 60) / 25
+          tc = (float)((double)pc_c * c.inv_tn);
           double extra;
-          if (kind == OM_ORDER_HAUL) {
-            int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
-            extra = om_ddiv0((double)on_cnt, (double)(ue - ub)) * __ldg(&c.dcycle[ub - c.S]);
-          } else {
-            extra = om_ddiv0(capsum, __ldg(&c.site_prod[q]));
-          }
-          sw = (float)om_dlog((site_est(site) + extra) + 1.0);
+          if (kind == OM_ORDER_HAUL) extra = ((double)on_c * __ldg(&c.inv_units[site])) * __ldg(&c.dcycle[__ldg(&c.ubeg[site]) - c.S]);
+          else extra = cap_c * __ldg(&c.inv_prod[cq]);
+          arg = est_c + extra;
+        } else {
+          dst = -(o7 + cq) - 2;                                          // padded slot: 0, no log
         }
-        ob[o3 + q] = tt; ob[o4 + q] = tc; ob[o7 + q] = sw;
-      }
+        ob[o3 + cq] = tt; ob[o4 + cq] = tc;
+      } else if (sq < NS) { arg = est_s; dst = o8 + sq; }
+      const double lg = om_dlog(arg + 1.0);
+      if (dst >= 0) ob[dst] = (float)lg;
+      else if (dst < -1) ob[-dst - 2] = 0.f;
     }
-    // per-site blocks
+    // per-site blocks: minute-sampled values (their logs were taken by the monitor block)
 #pragma unroll 1
-    for (int s = lane; s < NS; s += 32) {
-      ob[o8 + s] = (float)om_dlog(site_est(s) + 1.0);
-      ob[o9 + s] = (float)om_ddiv0((double)U16A(s_qtotal, s), tn);
-      ob[o10 + s] = (float)om_dlog(F64(s_cap, s) + 1.0);
-      ob[o11 + s] = (float)F64(s_ability, s);
-      ob[o12 + s] = (float)om_dlog(F64(s_tons, s) + 1.0);
+    for (int s2 = lane; s2 < NS; s2 += 32) {
+      ob[o9 + s2] = (float)((double)U16A(s_qtotal, s2) * c.inv_tn);
+      ob[o10 + s2] = (float)F64(s_cap, s2);
+      ob[o11 + s2] = (float)F64(s_ability, s2);
+      ob[o12 + s2] = (float)F64(s_tons, s2);
     }
     __syncwarp();
   }
@@ -1789,14 +1825,16 @@ struct Sim {
     float* ob = io.obs + (size_t)inst * p.obs_dim;
     if (pt >= 0 && !failed) {
       double delta_time = now - rl_last;
-      rl_observation(pt, pk, ob);
+      int pair_cnt, on_cnt;
+      double capsum;
+      rl_observation(pt, pk, ob, (io.flags & OM_STEP_WRITE_STATIC) != 0, pair_cnt, on_cnt, capsum);
       double reward = rl_reward(false, (io.flags & OM_STEP_SPARSE_REWARD) != 0);
       int sug = -1;
       if (io.teacher >= 0 && io.teacher != OM_DISP_RANDOM) {
         int saved_disp = disp;
         uint32_t saved_err = err;
         disp = io.teacher;
-        sug = decide(pk, pt, true);              // rl_observation() left both sides' wait estimates in scratch
+        sug = decide(pk, pt, true, true, on_cnt, capsum);   // rl_observation() left both sides' wait estimates in scratch
         if (sug < 0) sug = -1;                       // the teacher raised (e.g. SQ before its minute's sample)
         disp = saved_disp; err = saved_err;
       }
@@ -1874,7 +1912,9 @@ __device__ __forceinline__ void om_init_state(unsigned char* sm, unsigned char* 
                                               const OmStateLayout& ly, int lane, uint64_t seed, int dispatcher) {
   const double inf = om_inf();
   (void)inf;
+#ifdef OM_BOUNDS_CHECK
   uint32_t dbg_viol = 0;
+#endif
   const bool SPLIT = true;   // accessors: follow the layout (ly.t_loc != 0 <=> the handle runs the SPLIT kernels)
   // zero everything first
   #pragma unroll 1

@@ -15,8 +15,12 @@ from openmines_b200.trace import SUMMARY_DTYPE
 def _fake_summaries(lo, hi):
     ids = np.arange(lo, hi)
     s = np.zeros(len(ids), dtype=SUMMARY_DTYPE)
-    s["reported_tons"] = 1000.0 + 3.5 * ids
-    s["dumped_tons"] = 1010.0 + 3.5 * ids
+    # tonnages with full 52-bit mantissas (sums of jittered loads look like this): floating-point partial sums of them
+    # depend on the order of addition, the fixed-point statistics must not
+    rng = np.random.default_rng(12345)
+    tons = 8000.0 + 600.0 * rng.standard_normal(1 << 12)
+    s["reported_tons"] = tons[ids % len(tons)] + 1e-7 * ids
+    s["dumped_tons"] = s["reported_tons"] + 37.0 * rng.random(1 << 12)[ids % len(tons)]
     s["n_truck_events"] = 600 + ids
     s["n_decisions"] = 150 + ids % 7
     s["n_jams"] = ids % 5
@@ -57,9 +61,12 @@ def test_shard_and_allreduce_world2():
     s, d = _fake_summaries(0, n_total)
     want = parallel.stats_from_summaries(s, d)
     for _, _, _, st in got:
-        assert np.allclose(st, want, rtol=1e-12, atol=0)
+        assert np.array_equal(st, want)            # all-reduced 2-rank totals == single-process totals, bit for bit
+    assert (want == np.rint(want)).all()           # integer-valued: exact in any order of addition
     rows = parallel.describe(want)
     assert rows["NaiveDispatcher"]["instances"] == len(range(0, n_total, 6))
+    t = s["reported_tons"][d == 5]
+    assert abs(rows["SQDispatcher"]["mean_tons"] - t.mean()) < 1e-6 and abs(rows["SQDispatcher"]["std_tons"] - t.std()) < 0.05
 
 
 def test_shard_range_properties():

@@ -402,8 +402,10 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl, bool split
   if (split) {   // shared-memory helpers that keep the per-minute / per-departure scans of a big mine out of HBM
     ly.t_lastbrk_hot = take(off, 8, T);  // last breakdown time per truck (instead of the record field)
     ly.t_loc = take(off, 4, T);          // {status, current, target, -} per truck (instead of the record fields)
-    ly.t_road = take(off, 2, T);         // current road of every truck (0xFFFF: not on a road), refreshed every minute
     ly.r_jamcnt = take(off, 2, R);       // stored jams per road
+    // trucks under way per road: count + doubly linked list, maintained at departure / arrival (jam sampling)
+    ly.r_on = take(off, 2, R); ly.r_head = take(off, 2, R);
+    ly.t_rnext = take(off, 2, T); ly.t_rprev = take(off, 2, T);
   }
   ly.hot_bytes = (off + 15u) & ~15u;
   off = ly.hot_bytes;

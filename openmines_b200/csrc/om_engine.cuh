@@ -891,6 +891,35 @@ struct Sim {
     F64(t_dist, i) = dist;
   }
 
+  // Big mines (SPLIT layouts): the trucks under way on every road are kept as a doubly linked list per road in shared memory
+  // (r_head / t_rnext / t_rprev, with the count in r_on), maintained at departure and arrival -- so the per-minute jam
+  // sampling neither recounts 500 trucks nor scans them once per sampled position (both were 16-trip passes).
+  __device__ __forceinline__ void road_link(int i, int rid) {
+    if (SPLIT && ly.r_head != 0) {
+      uint16_t* head = (uint16_t*)(sm + ly.r_head);
+      uint16_t* nxt = (uint16_t*)(sm + ly.t_rnext);
+      uint16_t* prv = (uint16_t*)(sm + ly.t_rprev);
+      uint16_t* cnt = (uint16_t*)(sm + ly.r_on);
+      const uint16_t h = head[rid];
+      nxt[i] = h; prv[i] = OM_NONE16;
+      if (h != OM_NONE16) prv[h] = (uint16_t)i;
+      head[rid] = (uint16_t)i;
+      cnt[rid] = (uint16_t)(cnt[rid] + 1);
+    }
+  }
+  __device__ __forceinline__ void road_unlink(int i, int rid) {
+    if (SPLIT && ly.r_head != 0) {
+      uint16_t* head = (uint16_t*)(sm + ly.r_head);
+      uint16_t* nxt = (uint16_t*)(sm + ly.t_rnext);
+      uint16_t* prv = (uint16_t*)(sm + ly.t_rprev);
+      uint16_t* cnt = (uint16_t*)(sm + ly.r_on);
+      const uint16_t p = prv[i], n = nxt[i];
+      if (p != OM_NONE16) nxt[p] = n; else head[rid] = n;
+      if (n != OM_NONE16) prv[n] = p;
+      cnt[rid] = (uint16_t)(cnt[rid] - 1);
+    }
+  }
+
   // move(): jam scan + departure (truck.py:151-210)
   __device__ __forceinline__ void move_depart(int i, bool dead) {
     int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
@@ -931,6 +960,7 @@ struct Sim {
     emit(kind, (uint32_t)i, (uint32_t)idx, 0, now + duration + pre, dist);
     if (RL) F64(t_since, i) = now;
     U8A(t_status, i) = ST_MOVING;
+    road_link(i, rid);
     sched_truck(i, now + (duration + pre), OM_KEY_NORMAL, PH_MOVE_ARRIVE);
   }
 
@@ -970,6 +1000,52 @@ struct Sim {
     U16A(j_road, jam_count) = (uint16_t)rid;
     if (SPLIT && rjc != nullptr) rjc[rid] = (uint16_t)(rjc[rid] + 1);
     jam_count++;
+  }
+
+  // Big mines (SPLIT): drop the expired jams once per minute, lanes over the pool, creation order kept (a move adds the
+  // delays of the jams on its road in that order).  The pool of the 500-truck mine otherwise fills up with expired entries
+  // (it is only compacted when full) and every departure on a road with a stored jam scans all 512 of them.
+  __device__ __forceinline__ void jam_compact_parallel() {
+    uint16_t* rjc = (ly.r_jamcnt != 0) ? (uint16_t*)(sm + ly.r_jamcnt) : nullptr;
+    uint32_t w = 0;
+    double expired = 0.0;                              // RL: jam minutes of the dropped entries inside the reward window
+    #pragma unroll 1
+    for (uint32_t base = 0; base < jam_count; base += 32) {
+      const uint32_t j = base + lane;
+      const bool valid = j < jam_count;
+      double en = 0.0, pos = 0.0, st = 0.0;
+      uint32_t rd = 0;
+      if (valid) { en = F64(j_end, j); pos = F64(j_pos, j); rd = U16A(j_road, j); if (RL) st = F64(j_start, j); }
+      const bool keep = valid && en >= now;
+      if (RL && valid && !keep) {
+        const double lo = (st > rl_last) ? st : rl_last;
+        if (lo < en) expired += en - lo;
+      }
+      const unsigned m = __ballot_sync(OM_FULL, keep);
+      unsigned md = __ballot_sync(OM_FULL, valid && !keep);
+      const uint32_t dst = w + (uint32_t)__popc(m & ((1u << lane) - 1u));
+      __syncwarp();                                    // the chunk is in registers before any lane overwrites part of it
+      if (keep) {
+        F64(j_end, dst) = en; F64(j_pos, dst) = pos; U16A(j_road, dst) = (uint16_t)rd; if (RL) F64(j_start, dst) = st;
+      }
+      w += (uint32_t)__popc(m);
+      if (rjc != nullptr) {
+        #pragma unroll 1
+        while (md) {                                   // stored jams per road: the dropped ones leave (warp-uniform)
+          const int b = __ffs(md) - 1;
+          md &= md - 1;
+          const uint32_t r = __shfl_sync(OM_FULL, rd, b);
+          rjc[r] = (uint16_t)(rjc[r] - 1);
+        }
+      }
+    }
+    if (RL) {
+      #pragma unroll 1
+      for (int o = 16; o > 0; o >>= 1) expired += __shfl_xor_sync(OM_FULL, expired, o);
+      acc_jam += expired;
+    }
+    jam_count = w;
+    __syncwarp();
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -1133,6 +1209,7 @@ struct Sim {
         __syncwarp();
       }
       // (4) jam sampling per road in monitor order (mine.py:138-154, road.py:137-233)
+      if (SPLIT && jam_count > 32u) jam_compact_parallel();
       if (now >= 2.0) jam_sampling(k);
     }
     // re-arm: every monitor generator does `yield env.timeout(1)`; the block's eids are contiguous
@@ -1144,20 +1221,19 @@ struct Sim {
   __device__ __forceinline__ void jam_sampling(int k) {
     const int T = c.T, R = c.R;
     uint32_t* rcnt = (uint32_t*)(sm + ly.scratch);   // scratch is sized >= max(U, R/2 + 1, 32) doubles
-    #pragma unroll 1
-    for (int r = lane; r < R; r += 32) rcnt[r] = 0;
-    __syncwarp();
-    // Big mines (SPLIT): the truck records live in HBM, so this pass also leaves every truck's current road in a
-    // shared-memory array for sample_jam_position(), which would otherwise re-read all records once per attempt.
-    uint16_t* troad = (SPLIT && ly.t_road != 0) ? (uint16_t*)(sm + ly.t_road) : nullptr;
-    #pragma unroll 1
-    for (int i = lane; i < T; i += 32) {
-      int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
-      int rid = (U8A(t_status, i) == ST_MOVING && cur != tgt) ? road_id(cur, tgt) : -1;
-      if (rid >= 0) atomicAdd(&rcnt[rid], 1u);
-      if (SPLIT && troad != nullptr) troad[i] = (uint16_t)rid;
+    const uint16_t* ron = (SPLIT && ly.r_on != 0) ? (const uint16_t*)(sm + ly.r_on) : nullptr;   // big mines: kept incrementally
+    if (!(SPLIT && ron != nullptr)) {
+      #pragma unroll 1
+      for (int r = lane; r < R; r += 32) rcnt[r] = 0;
+      __syncwarp();
+      #pragma unroll 1
+      for (int i = lane; i < T; i += 32) {
+        int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
+        int rid = (U8A(t_status, i) == ST_MOVING && cur != tgt) ? road_id(cur, tgt) : -1;
+        if (rid >= 0) atomicAdd(&rcnt[rid], 1u);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     // every candidate road flips its own keyed coin (road.py:179): lane l of the 64-road group g serves roads
     // 64g + l (words x: coin, z: duration) and 64g + 32 + l (words y, w) from ONE Philox call
     Philox4 rr;
@@ -1165,14 +1241,14 @@ struct Sim {
     #pragma unroll 1
     for (int base = 0; base < R; base += 32) {
       int r = base + lane;
-      uint32_t n_on = (r < R) ? rcnt[r] : 0u;
+      uint32_t n_on = (r < R) ? ((SPLIT && ron != nullptr) ? (uint32_t)ron[r] : rcnt[r]) : 0u;
       bool candidate = n_on >= 2u;                          // road.py:148-176: >= 2 moving trucks
       bool hit = candidate;
       double coin = 0.0;
       const bool second = (base & 32) != 0;
       if (RNG == OM_RNG_PHILOX) {
         if (!second) {
-          uint32_t n2 = (r + 32 < R) ? rcnt[r + 32] : 0u;
+          uint32_t n2 = (r + 32 < R) ? ((SPLIT && ron != nullptr) ? (uint32_t)ron[r + 32] : rcnt[r + 32]) : 0u;
           if (__any_sync(OM_FULL, candidate || n2 >= 2u)) rr = px((uint32_t)k, (uint32_t)r, OM_S_JAM_COIN);
         }
         uint32_t cw = second ? rr.y : rr.x;
@@ -1229,29 +1305,34 @@ struct Sim {
 #pragma unroll 1
     for (uint32_t it = 0; it < 64; ++it) {
       Philox4 r = px((uint32_t)k, (uint32_t)rid, OM_S_JAM_POS, it);
-      int pick = (int)om_randint(r.x, n_on);               // pick-th truck on this road, truck order
+      int pick = (int)om_randint(r.x, n_on);               // pick-th truck on this road (truck order; list order for big mines)
       int found = -1;
+      if (SPLIT && ly.r_head != 0) {
+        // big mines: walk the road's list (a uniform pick is uniform whatever the order of the list)
+        const uint16_t* nxt = (const uint16_t*)(sm + ly.t_rnext);
+        uint32_t tk = ((const uint16_t*)(sm + ly.r_head))[rid];
 #pragma unroll 1
-      for (int base = 0; base < T && found < 0; base += 32) {
-        int i = base + lane;
-        bool on = false;
-        if (i < T) {
-          if (SPLIT && ly.t_road != 0) {
-            on = ((const uint16_t*)(sm + ly.t_road))[i] == (uint16_t)rid;      // written by jam_sampling() this minute
-          } else {
+        for (int q = 0; q < pick && tk != OM_NONE16; ++q) tk = nxt[tk];
+        found = (tk != OM_NONE16) ? (int)tk : -1;
+      } else {
+#pragma unroll 1
+        for (int base = 0; base < T && found < 0; base += 32) {
+          int i = base + lane;
+          bool on = false;
+          if (i < T) {
             int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
             on = U8A(t_status, i) == ST_MOVING && cur != tgt && road_id(cur, tgt) == rid;
           }
-        }
-        unsigned m = __ballot_sync(OM_FULL, on);
-        int cnt = __popc(m);
-        if (pick < cnt) {
-          // position of the pick-th set bit
+          unsigned m = __ballot_sync(OM_FULL, on);
+          int cnt = __popc(m);
+          if (pick < cnt) {
+            // position of the pick-th set bit
 #pragma unroll 1
-          for (int q = 0; q < pick; ++q) m &= m - 1;
-          found = base + __ffs(m) - 1;
-        } else {
-          pick -= cnt;
+            for (int q = 0; q < pick; ++q) m &= m - 1;
+            found = base + __ffs(m) - 1;
+          } else {
+            pick -= cnt;
+          }
         }
       }
       if (found < 0) break;                                 // cannot happen: n_on trucks are on the road
@@ -1463,6 +1544,7 @@ struct Sim {
     L_ARRIVE:                                                          // truck.py:211-218
       OM_CONV();
       rl_close(acc_move, i);
+      if (SPLIT) road_unlink(i, road_id(U8A(t_cur, i), U8A(t_tgt, i)));
       U8A(t_cur, i) = U8A(t_tgt, i);
       F64(t_prejam, i) = 0.0;
       if (!chain) { sched_truck(i, now, OM_KEY_NORMAL, PH_MOVE_RET); continue; }
@@ -1932,6 +2014,10 @@ __device__ __forceinline__ void om_init_state(unsigned char* sm, unsigned char* 
     U8A(t_tgt, i) = OM_NOLOC;
     U16A(t_next, i) = OM_NONE16;
     U16A(t_unit, i) = OM_NONE16;
+  }
+  if (ly.r_head != 0) {                          // split layouts: empty per-road lists of the trucks under way
+    #pragma unroll 1
+    for (int r = lane; r < c.R; r += 32) ((uint16_t*)(sm + ly.r_head))[r] = OM_NONE16;
   }
   #pragma unroll 1
   for (int u = lane; u < c.U; u += 32) {

@@ -47,7 +47,7 @@ _LAYOUT_FIELDS = ["total_bytes", "hdr", "t_time", "t_load", "t_jstart", "t_preja
                   "t_status", "t_cur", "t_tgt", "u_last_start", "u_last_done", "u_tons", "u_lastbrk",
                   "u_rel_key", "u_svc", "u_user", "u_head", "u_tail", "u_qlen", "u_repair", "r_repair_end",
                   "j_pos", "j_start", "j_end", "j_road", "s_qtotal", "s_coming", "s_tons", "s_cap", "s_ability", "scratch",
-                  "t_rec", "u_rec", "t_stride", "u_stride", "e_stride", "hot_bytes", "hdr_bytes", "slot_cache", "t_road", "r_jamcnt", "t_loc", "t_lastbrk_hot"]
+                  "t_rec", "u_rec", "t_stride", "u_stride", "e_stride", "hot_bytes", "hdr_bytes", "slot_cache", "t_road", "r_jamcnt", "t_loc", "t_lastbrk_hot", "r_on", "r_head", "t_rnext", "t_rprev"]
 _ENTRY_FIELDS = {"t_time", "t_key", "t_phase"}                # the truck's 16-byte pending entry
 _SOA_FIELDS = {"u_rel_key", "u_lastbrk", "t_since"}            # every other t_* / u_* field lives in a record
 

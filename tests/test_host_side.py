@@ -77,7 +77,7 @@ def test_struct_sizes_match_header():
     assert info["sizeof_OmOutputs"] == ctypes.sizeof(OmOutputsStruct)
     assert info["sizeof_OmStateLayout"] == ctypes.sizeof(OmStateLayoutStruct)
     assert info["sizeof_OmConfig"] == ctypes.sizeof(cfgmod.OmConfigStruct)
-    assert ctypes.sizeof(OmStateLayoutStruct) == 4 * 56
+    assert ctypes.sizeof(OmStateLayoutStruct) == 4 * 60
     assert ctypes.sizeof(cfgmod.OmConfigStruct) == 12 * 4 + 14 * 8 + 15 * 8
     assert (TRACE_DTYPE.itemsize, TICK_DTYPE.itemsize, SUMMARY_DTYPE.itemsize) == (32, 32, 64)
 

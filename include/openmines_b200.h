@@ -342,7 +342,8 @@ int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* str
 int om_debug_bounds_report(int32_t* out8);
 int om_debug_draws(int kind, uint64_t seed, uint32_t arg, int64_t n, double* out, void* stream);
 int om_debug_jam_positions(OmHandle h, void* state, int64_t inst, int32_t road, int32_t n_samples, double* out,
-                           int32_t* fallbacks, void* stream);
+                           int32_t* fallbacks, double* coverage_out /* device [T] or NULL: Truck.get_route_coverage
+                           (truck.py:496-520) of every truck under way on the road, -1 for the others */, void* stream);
 
 /* Kernel launch geometry actually used by om_run (for bench.py's launch accounting). */
 int om_launch_info(OmHandle h, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* warps_per_cta);

@@ -107,7 +107,7 @@ def load():
               "om_run", "om_stats_reduce", "om_obs_dim", "om_step"):
         getattr(lib, f).restype = ctypes.c_int
     lib.om_debug_draws.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32, i64, vp, vp]
-    lib.om_debug_jam_positions.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
+    lib.om_debug_jam_positions.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.om_debug_draws.restype = lib.om_debug_jam_positions.restype = ctypes.c_int
     lib.om_debug_bounds_report.argtypes = [ctypes.POINTER(i32)]
     lib.om_debug_bounds_report.restype = ctypes.c_int

@@ -227,12 +227,15 @@ __global__ void om_debug_draws_kernel(int kind, uint64_t seed, uint32_t arg, lon
 }
 
 // one warp: n_samples jam positions on road `rid` of instance `inst` as it stands in `state` (epoch = sample index)
-__global__ void om_debug_jam_kernel(RunParams p, long long inst, int rid, int n_samples, double* out, int* fallbacks) {
+__global__ void om_debug_jam_kernel(RunParams p, long long inst, int rid, int n_samples, double* out, int* fallbacks,
+                                    double* coverage_out) {
   const int lane = threadIdx.x & 31;
   unsigned char* blob = p.state + (size_t)inst * p.ly.total_bytes;
   Sim<OM_RNG_PHILOX, false, false, false> s(blob, blob, p, p.c, lane, inst);
   s.load_hdr(p);
   const uint32_t n_on = s.debug_trucks_on_road(rid);
+  if (coverage_out != nullptr)                 // Truck.get_route_coverage of every truck under way on the road, -1 for the others
+    for (int i = lane; i < p.c.T; i += 32) coverage_out[i] = s.debug_coverage(i, rid);
   int fb = 0;
   for (int k = 0; k < n_samples; ++k) {
     double pos = (n_on >= 1) ? s.template sample_jam_position<true>(k, rid, n_on, &fb) : -1.0;
@@ -831,7 +834,7 @@ int om_debug_draws(int kind, uint64_t seed, uint32_t arg, int64_t n, double* out
 }
 
 int om_debug_jam_positions(OmHandle h, void* state, int64_t inst, int32_t road, int32_t n_samples, double* out, int32_t* fallbacks,
-                           void* stream) {
+                           double* coverage_out, void* stream) {
   if (!h || !state || !out || inst < 0 || inst >= h->n || n_samples <= 0) return set_err(h, OM_E_INVALID, "om_debug_jam_positions: bad argument");
   if (h->multi || h->split || road < 0 || road >= h->c.R) return set_err(h, OM_E_UNSUPPORTED, "om_debug_jam_positions: one-config, unsplit handles only");
   CK(cudaSetDevice(h->device));
@@ -839,7 +842,7 @@ int om_debug_jam_positions(OmHandle h, void* state, int64_t inst, int32_t road, 
   memset(&p, 0, sizeof(p));
   p.c = h->c; p.ly = h->ly; p.state = (unsigned char*)state; p.n_instances = h->n;
   p.ns_stride = h->c.NS; p.u_stride_out = h->c.U;
-  om_debug_jam_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, (long long)inst, road, n_samples, out, fallbacks);
+  om_debug_jam_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, (long long)inst, road, n_samples, out, fallbacks, coverage_out);
   CK(cudaGetLastError());
   return OM_OK;
 }

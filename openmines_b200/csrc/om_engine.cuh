@@ -1356,6 +1356,12 @@ struct Sim {
     return n;
   }
 
+  __device__ __forceinline__ double debug_coverage(int i, int rid) {
+    int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
+    const bool on = U8A(t_status, i) == ST_MOVING && cur != tgt && road_id(cur, tgt) == rid;
+    return on ? (double)coverage(i, rid) : -1.0;
+  }
+
   // Truck.get_route_coverage (truck.py:496-520)
   __device__ __forceinline__ float coverage(int i, int rid) {
     double total = __ldg(&c.trip60[__ldg(&c.sclass[i]) * c.R + rid]) + F64(t_prejam, i) + F64(t_repair, i);

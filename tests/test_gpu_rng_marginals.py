@@ -95,21 +95,27 @@ def test_jam_position_sampler_vs_reference_categorical(north_pit, n_trucks):
     hdr = mine.headers()
     T = mine.pc.T
     trip = (mine.pc.road_distance[0] / mine.pc.truck_speed[0]) * 60
+    # Truck.get_route_coverage (truck.py:496-520): (now - journey_start) / ((dist / speed) * 60 + pre_jam_time + repair_time),
+    # capped at 1 -- with a jam delay on some trucks and a pending repair time on others
+    prejam = np.where(np.arange(T) % 3 == 1, 2.5, 0.0)
+    repair = np.where(np.arange(T) % 4 == 2, 7.25, 0.0)
     for i in range(T):
         on = i < n_trucks
         _poke(mine, st, "t_status", i, 2 if on else 3, np.uint8)            # ST_MOVING / ST_WAIT_SHOVEL
         _poke(mine, st, "t_cur", i, 0 if on else 1, np.uint8)
         _poke(mine, st, "t_tgt", i, 1, np.uint8)
-        _poke(mine, st, "t_jstart", i, now - cov[i] * trip if on else 0.0, np.float64)
-        _poke(mine, st, "t_prejam", i, 0.0, np.float64)
-        _poke(mine, st, "t_repair", i, 0.0, np.float64)
+        _poke(mine, st, "t_jstart", i, now - cov[i] * (trip + prejam[i] + repair[i]) if on else 0.0, np.float64)
+        _poke(mine, st, "t_prejam", i, prejam[i], np.float64)
+        _poke(mine, st, "t_repair", i, repair[i], np.float64)
     st[0, mine.layout.hdr:mine.layout.hdr + 8] = np.frombuffer(np.array([now]).tobytes(), dtype=np.uint8)   # InstHdr.now
     mine.state.copy_(torch.from_numpy(st))
     n = 200_000
     out = torch.empty(n, dtype=torch.float64, device=mine.device)
     fb = torch.zeros(1, dtype=torch.int32, device=mine.device)
+    cov_dev_t = torch.zeros(T, dtype=torch.float64, device=mine.device)
     rc = _lib.load().om_debug_jam_positions(mine.h, ctypes.c_void_p(mine.state.data_ptr()), 0, 0, n,
-                                            ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(fb.data_ptr()), None)
+                                            ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(fb.data_ptr()),
+                                            ctypes.c_void_p(cov_dev_t.data_ptr()), None)
     assert rc == 0, _lib.load().om_last_error(mine.h)
     torch.cuda.synchronize()
     pos = out.cpu().numpy()
@@ -117,8 +123,14 @@ def test_jam_position_sampler_vs_reference_categorical(north_pit, n_trucks):
     x = np.linspace(0, 1, 1000)
     idx = np.rint(pos * 999).astype(np.int64)
     assert np.array_equal(x[idx], pos)                       # grid values, bit for bit
-    # the device sees coverage in fp32 of (now - jstart) / trip; the reference's p for the same coverages
-    cov_dev = np.minimum((now - (now - cov * trip)) / trip, 1.0)
+    # the device's coverage() against the reference formula in fp64 (the device rounds the result to fp32)
+    jstart = now - cov * (trip + prejam[:n_trucks] + repair[:n_trucks])
+    cov_ref = np.minimum((now - jstart) / ((mine.pc.road_distance[0] / mine.pc.truck_speed[:n_trucks]) * 60 + prejam[:n_trucks]
+                                           + repair[:n_trucks]), 1.0)
+    got_cov = cov_dev_t.cpu().numpy()
+    assert (got_cov[n_trucks:] == -1.0).all()
+    assert np.abs(got_cov[:n_trucks] - cov_ref).max() <= 1.2e-7, np.abs(got_cov[:n_trucks] - cov_ref).max()
+    cov_dev = got_cov[:n_trucks]
     p = np.zeros_like(x)
     for c in cov_dev:
         p += stats.norm.pdf(x, c, 0.1)

@@ -234,3 +234,29 @@ def test_oracle_shortest_trip_matches_reference_golden(cname, north_pit, ragged_
     g = Golden("live_%s_%s_s17" % (cname, d))
     assert not _same(g, do.run_oracle(cfg, d, "live", seed=17), check_tape=True)
     assert not _same(g, do.run_oracle(cfg, d, "replay", tape=g.tape), check_tape=True)
+
+
+def test_device_philox_trajectories_replayed_by_the_reference(north_pit, ragged_mine):
+    """tests/golden/device_tapes.npz holds 12 trajectories the PHILOX-mode CUDA kernels produced on a B200 together with the
+    draw tapes they exported (tools/export_device_tapes.py).  Replaying each tape through the CPU restatement -- and, where
+    /root/reference exists, through the UNMODIFIED reference itself (oracle/ref_harness.py) -- must give the device's event
+    trace (times included), production and waiting-truck curves, tonnage, event / order counts and order lists bit for bit,
+    consuming the tape to its last entry (tests/golden/make_golden_device_tapes.py)."""
+    import sys
+    from helpers import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    from make_golden_device_tapes import cases, compare
+    z = np.load(os.path.join(GOLDEN, "device_tapes.npz"))
+    from oracle import ref_harness as rh
+    use_ref = rh.reference_available()
+    n = 0
+    for key, cname, disp in cases(z):
+        cfg = north_pit if cname == "north_pit_mine" else ragged_mine
+        tape = (z[key + "_tape_sites"], z[key + "_tape_values"])
+        o = do.run_oracle(cfg, disp, "replay", tape=tape)
+        assert o.error is None and not compare(key, z, o, disp == "SPTFDispatcher"), key
+        if use_ref and n % 3 == 0:              # the reference itself on every third one (it is ~5x slower)
+            r = rh.run_reference(cfg, disp, "replay", tape=tape)
+            assert r.error is None and not compare(key, z, r, disp == "SPTFDispatcher"), key
+        n += 1
+    assert n == 12

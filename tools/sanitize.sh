@@ -10,6 +10,10 @@ python tools/sanitize_target.py > gpurun_out/${TAG}_sanitize_plain.log 2>&1 || {
 echo "plain: $(tail -1 gpurun_out/${TAG}_sanitize_plain.log)"
 OM_DEBUG_LIB=1 python -c "from openmines_b200 import _lib; _lib.build()" && OM_DEBUG_LIB=1 python tools/sanitize_target.py > gpurun_out/${TAG}_sanitize_bounds.log 2>&1
 echo "bounds rc=$? : $(tail -1 gpurun_out/${TAG}_sanitize_bounds.log)"
+# 2b. warp-convergence probes alone (production code + __activemask() checks): at scale
+OM_DEBUG_LIB=probes OM_EXTRA_NVCC_FLAGS="-DOM_CONV_PROBES" OM_LIB_PATH=$PWD/openmines_b200/libprobes.so python -c "from openmines_b200 import _lib; _lib.build()" && \
+  OM_LIB_PATH=$PWD/openmines_b200/libprobes.so python tools/conv_probe_run.py > gpurun_out/${TAG}_sanitize_probes.log 2>&1
+echo "probes rc=$? : $(grep -c 'convergence violations 0 ' gpurun_out/${TAG}_sanitize_probes.log) of 3 workloads with 0 convergence violations"
 [ -n "$SKIP_COMPUTE_SANITIZER" ] && exit 0
 for tool in memcheck racecheck initcheck synccheck; do
   extra=""

@@ -44,13 +44,16 @@ __device__ __forceinline__ void om_stage_in(unsigned char* sm, const unsigned ch
 }
 
 // called by every lane after the last shared-memory write of the instance; returns when the buffer may be reused
-__device__ __forceinline__ void om_stage_out(unsigned char* g, const unsigned char* sm, uint32_t bytes, int lane) {
+// `complete`: wait until the bytes are written (not only read out of shared memory) -- another warp is about to be told that
+// the blob is in HBM (episode segments)
+__device__ __forceinline__ void om_stage_out(unsigned char* g, const unsigned char* sm, uint32_t bytes, int lane, bool complete = false) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
   __syncwarp();
   if (lane == 0) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(om_smem_u32(sm)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (complete) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   __syncwarp();
 }
@@ -125,14 +128,35 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
   uint32_t phase = 0;
   if (lane == 0) om_mbar_init(&om_mbar[warp]);
   __syncwarp();
+  // Work items: (segment, instance), all first segments before all second ones ...  Cutting the episode into segments keeps
+  // the tail of the persistent grid short (16384 instances on 2960 resident warps are 5.5 waves; when the queue runs dry
+  // the last warps still have a whole episode in front of them).  A later segment of an instance waits for the flag its
+  // predecessor sets after its blob is back in HBM; the predecessor was handed out earlier and waits for nothing younger.
+  const int S = SPLIT ? 1 : (p.n_segments > 1 ? p.n_segments : 1);
   while (true) {
     unsigned long long inst = 0;
+    int seg = 0;
     if (lane == 0) {
-      inst = atomicAdd(p.counter, 1ull);
-      if (inst < (unsigned long long)p.n_instances && p.order != nullptr) inst = (unsigned long long)p.order[inst];
+      const unsigned long long q = atomicAdd(p.counter, 1ull);
+      inst = ~0ull;
+      if (q < (unsigned long long)p.n_instances * (unsigned long long)S) {
+        unsigned long long qi = q;
+        #pragma unroll 1
+        while (qi >= (unsigned long long)p.n_instances) { qi -= (unsigned long long)p.n_instances; ++seg; }   // S <= 16 trips
+        inst = (p.order != nullptr) ? (unsigned long long)p.order[qi] : qi;
+        if (seg > 0) {
+          const uint32_t want = p.seg_epoch * (uint32_t)S + (uint32_t)seg;
+          uint32_t have;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(p.seg_done + inst) : "memory");
+            if (have != want) __nanosleep(256);
+          } while (have != want);
+        }
+      }
     }
     inst = __shfl_sync(OM_FULL, inst, 0);
-    if (inst >= (unsigned long long)p.n_instances) break;
+    seg = __shfl_sync(OM_FULL, seg, 0);
+    if (inst == ~0ull) break;
     // stage the instance's blob HBM -> shared memory
     unsigned char* g = p.state + (size_t)inst * p.ly.total_bytes;
     om_stage_in(sm, g, staged, &om_mbar[warp], phase, lane);   // one TMA bulk copy
@@ -150,9 +174,11 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
     Sim<RNG, TRACE, false, SPLIT> s(sm, g, p, *cfg, lane, (long long)inst);
     s.load_hdr(p);
     // mixed-config batches: every instance stops at its own config's sim_time (or the call's `until`, if earlier)
-    s.run((MULTI && cfg->sim_time > 0.0 && cfg->sim_time < p.until) ? cfg->sim_time : p.until);
+    const double until_i = (MULTI && cfg->sim_time > 0.0 && cfg->sim_time < p.until) ? cfg->sim_time : p.until;
+    const bool last_seg = seg == S - 1;
+    s.run(last_seg ? until_i : until_i * (1.0 - p.seg_tail * (double)(S - 1 - seg)));
     s.store_hdr(p);
-    if (p.out.summary != nullptr) {
+    if (last_seg && p.out.summary != nullptr) {
       double dumped = s.dumped_tons();
       if (lane == 0) {
         OmSummary r;
@@ -167,7 +193,12 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
 #ifdef OM_BOUNDS_CHECK
     om_publish_violation(s.dbg_viol);
 #endif
-    om_stage_out(g, sm, staged, lane);
+    om_stage_out(g, sm, staged, lane, !last_seg);
+    if (!last_seg && lane == 0) {            // the blob is in HBM: release the instance's next segment
+      __threadfence();
+      const uint32_t v = p.seg_epoch * (uint32_t)S + (uint32_t)seg + 1u;
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.seg_done + inst), "r"(v) : "memory");
+    }
   }
   om_retire_warp(p, lane);
 }
@@ -326,6 +357,10 @@ struct OmEngine {
   const int32_t* d_cfg_id = nullptr;   // [n] config of every instance (mixed-config handles only)
   bool multi = false;
   const void* last_obs = nullptr;      // observation buffer of the previous om_step (static columns already written there)
+  uint32_t* seg_done = nullptr;        // [n] episode-segment progress flags (see om_run_kernel)
+  uint32_t seg_epoch = 0;              // om_run launches so far
+  int segments = 1;
+  double seg_tail = 0.1;
   OmStateLayout ly;
   std::vector<void*> dev_allocs;
   unsigned long long* counter = nullptr;
@@ -620,6 +655,13 @@ static int create_impl(const OmConfig* const* cfgs, int32_t n_configs, const int
     else { h->order = (int32_t*)d; h->dev_allocs.push_back(d); }
   }
   if (rc == OM_OK) {
+    void* d = nullptr;
+    e = cudaMalloc(&d, sizeof(uint32_t) * (size_t)n_instances);
+    if (e == cudaSuccess) e = cudaMemset(d, 0, sizeof(uint32_t) * (size_t)n_instances);
+    if (e != cudaSuccess) rc = set_err(h, OM_E_NOMEM, cudaGetErrorString(e));
+    else { h->seg_done = (uint32_t*)d; h->dev_allocs.push_back(d); }
+  }
+  if (rc == OM_OK) {
     h->rl = (cfgs[0]->flags & OM_CFG_RL_SURFACE) != 0;
     build_layout(c, h->ly, h->rl, false);
     int sms = 0;
@@ -648,6 +690,13 @@ static int create_impl(const OmConfig* const* cfgs, int32_t n_configs, const int
       h->warps = w; h->block = w * 32; h->smem = w * staged;
       long long ctas = (n_instances + w - 1) / w;
       h->grid = (int)(ctas < sms ? ctas : sms);
+      // more instances than resident warps: the last tenth of every episode is a work item of its own, handed out after all
+      // the first parts -- when the queue runs dry the resident warps have a tenth of an episode left, not a whole one
+      // (measured on the C3 shard: 2 x {0.9, 0.1} 26.35 ms, 2 x {0.8, 0.2} 26.55, 3 x 26.50, 4 x 26.6-26.8, 1 x 28.2)
+      h->segments = (!h->split && n_instances > (long long)h->grid * w) ? 2 : 1;
+      if (const char* ev = getenv("OM_SEGMENTS")) { int sv = atoi(ev); if (sv >= 1 && sv <= 16 && !h->split) h->segments = sv; }
+      h->seg_tail = 0.1;
+      if (const char* ev = getenv("OM_SEG_TAIL")) { double tv = atof(ev); if (tv > 0.0 && tv * (h->segments - 1) < 1.0) h->seg_tail = tv; }
       const void* fns[] = {
 #define OM_RUN_FNS(MULTI)                                                                                                 \
           (const void*)om_run_kernel<OM_RNG_DET, false, false, MULTI>, (const void*)om_run_kernel<OM_RNG_PHILOX, false, false, MULTI>, \
@@ -753,6 +802,7 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
   p.counter = h->counter; p.n_instances = h->n; p.until = until;
   p.order = h->order;
   p.cfgs = h->d_cfgs; p.cfg_id = h->d_cfg_id; p.ns_stride = h->c.NS; p.u_stride_out = h->c.U;
+  p.seg_done = h->seg_done; p.n_segments = h->segments; p.seg_epoch = ++h->seg_epoch; p.seg_tail = h->seg_tail;
   cudaStream_t st = (cudaStream_t)stream;
   if (p.out.draw_values != nullptr && (p.out.draw_sites == nullptr || p.out.draw_capacity <= 0))
     return set_err(h, OM_E_INVALID, "om_run: draw_values needs draw_sites and draw_capacity > 0");

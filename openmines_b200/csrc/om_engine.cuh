@@ -163,6 +163,12 @@ struct RunParams {
   const DevCfg* cfgs;
   const int32_t* cfg_id;
   int ns_stride, u_stride_out;   // row widths of the per-site / per-unit tick outputs (max L+D / max S+M over the configs)
+  // episode segments (om_run, unsplit layouts): an episode is cut into n_segments work items so that the last, partially
+  // filled wave of the persistent grid is short; seg_done[inst] == seg_epoch * n_segments + s  <=>  segments < s are stored
+  uint32_t* seg_done;
+  uint32_t seg_epoch;
+  int n_segments;
+  double seg_tail;     // every segment after the first covers this fraction of the episode (the last one sets the tail)
 };
 
 __device__ __forceinline__ double om_inf() { return __longlong_as_double(0x7FF0000000000000LL); }

@@ -693,9 +693,12 @@ static int create_impl(const OmConfig* const* cfgs, int32_t n_configs, const int
       // more instances than resident warps: the last tenth of every episode is a work item of its own, handed out after all
       // the first parts -- when the queue runs dry the resident warps have a tenth of an episode left, not a whole one
       // (measured on the C3 shard: 2 x {0.9, 0.1} 26.35 ms, 2 x {0.8, 0.2} 26.55, 3 x 26.50, 4 x 26.6-26.8, 1 x 28.2)
-      h->segments = (!h->split && n_instances > (long long)h->grid * w) ? 2 : 1;
+      // With only a few waves the long first parts leave stragglers nobody can fill in for (C2: 6144 instances = 2.07 waves;
+      // four equal segments 5.44 ms, {0.9, 0.1} 5.75 ms, one 6.06 ms), so short batches are cut into four equal parts.
+      const double waves = (double)n_instances / ((double)h->grid * (double)w);
+      h->segments = (h->split || waves <= 1.0) ? 1 : (waves >= 4.0 ? 2 : 4);
       if (const char* ev = getenv("OM_SEGMENTS")) { int sv = atoi(ev); if (sv >= 1 && sv <= 16 && !h->split) h->segments = sv; }
-      h->seg_tail = 0.1;
+      h->seg_tail = (h->segments == 2) ? 0.1 : 1.0 / (double)h->segments;
       if (const char* ev = getenv("OM_SEG_TAIL")) { double tv = atof(ev); if (tv > 0.0 && tv * (h->segments - 1) < 1.0) h->seg_tail = tv; }
       const void* fns[] = {
 #define OM_RUN_FNS(MULTI)                                                                                                 \

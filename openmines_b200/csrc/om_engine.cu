@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
         while (qi >= (unsigned long long)p.n_instances) { qi -= (unsigned long long)p.n_instances; ++seg; }   // S <= 16 trips
         inst = (p.order != nullptr) ? (unsigned long long)p.order[qi] : qi;
         if (seg > 0) {
-          const uint32_t want = p.seg_epoch * (uint32_t)S + (uint32_t)seg;
+          const uint32_t want = (uint32_t)seg;
           uint32_t have;
           do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(p.seg_done + inst) : "memory");
@@ -194,9 +194,11 @@ __global__ void __launch_bounds__(OM_MAX_WARPS_PER_CTA * 32, 1) om_run_kernel(co
     om_publish_violation(s.dbg_viol);
 #endif
     om_stage_out(g, sm, staged, lane, !last_seg);
-    if (!last_seg && lane == 0) {            // the blob is in HBM: release the instance's next segment
+    if (S > 1 && lane == 0) {
+      // the blob is in HBM: release the instance's next segment; the last segment puts the flag back to 0, so a launch
+      // leaves the flags as it found them (no epoch, no memset: safe under CUDA-graph replay)
       __threadfence();
-      const uint32_t v = p.seg_epoch * (uint32_t)S + (uint32_t)seg + 1u;
+      const uint32_t v = last_seg ? 0u : (uint32_t)seg + 1u;
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.seg_done + inst), "r"(v) : "memory");
     }
   }
@@ -780,6 +782,7 @@ int om_reset(OmHandle h, const uint64_t* seeds, const int32_t* dispatcher, int r
   h->reset_done = true;
   h->tape_values = tape_values; h->tape_sites = tape_sites; h->tape_offsets = tape_offsets;
   CK(cudaMemsetAsync(h->counter, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));   // also after an aborted launch
+  CK(cudaMemsetAsync(h->seg_done, 0, sizeof(uint32_t) * (size_t)h->n, (cudaStream_t)stream));
   const int wpb = 8;
   long long blocks = (h->n + wpb - 1) / wpb;
   om_reset_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(h->d_cfgs, h->d_cfg_id, h->ly, (unsigned char*)state,
@@ -805,7 +808,7 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
   p.counter = h->counter; p.n_instances = h->n; p.until = until;
   p.order = h->order;
   p.cfgs = h->d_cfgs; p.cfg_id = h->d_cfg_id; p.ns_stride = h->c.NS; p.u_stride_out = h->c.U;
-  p.seg_done = h->seg_done; p.n_segments = h->segments; p.seg_epoch = ++h->seg_epoch; p.seg_tail = h->seg_tail;
+  p.seg_done = h->seg_done; p.n_segments = h->segments; p.seg_epoch = 0; p.seg_tail = h->seg_tail;
   cudaStream_t st = (cudaStream_t)stream;
   if (p.out.draw_values != nullptr && (p.out.draw_sites == nullptr || p.out.draw_capacity <= 0))
     return set_err(h, OM_E_INVALID, "om_run: draw_values needs draw_sites and draw_capacity > 0");

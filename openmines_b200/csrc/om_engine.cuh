@@ -164,7 +164,7 @@ struct RunParams {
   const int32_t* cfg_id;
   int ns_stride, u_stride_out;   // row widths of the per-site / per-unit tick outputs (max L+D / max S+M over the configs)
   // episode segments (om_run, unsplit layouts): an episode is cut into n_segments work items so that the last, partially
-  // filled wave of the persistent grid is short; seg_done[inst] == seg_epoch * n_segments + s  <=>  segments < s are stored
+  // filled wave of the persistent grid is short; seg_done[inst] == s  <=>  segments < s of the current launch are stored
   uint32_t* seg_done;
   uint32_t seg_epoch;
   int n_segments;

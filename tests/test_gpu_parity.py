@@ -490,3 +490,40 @@ def test_jam_pool_overflow_is_regrown_not_lost(north_pit):
     assert got.summary_np().tobytes() == want.summary_np().tobytes()
     assert got.ticks_np().tobytes() == want.ticks_np().tobytes()
 
+
+
+def test_episode_batch_in_a_cuda_graph(north_pit):
+    """om_reset + om_run + om_stats_reduce captured in a CUDA graph and replayed: the work-queue counter and the per-instance
+    segment flags are left as the launch found them (no memset, no epoch in the kernel parameters), so every replay gives
+    the eager result -- on a batch big enough to be cut into episode segments."""
+    import torch
+    n = 4096                                         # 1.4 waves of 2960 resident warps -> segmented episodes
+    ids = np.where(np.arange(n) % 2 == 0, 5, 4).astype(np.int32)
+    mine = _mine(north_pit, n)
+    mine.reset(ids, seeds=np.arange(n) // 2, rng_mode="philox")
+    res = mine.run(until=60.0)
+    want_s, want_t = res.summary_np().copy(), res.ticks_np().copy()
+    want_stats = mine.stats(res).cpu().numpy()
+    import ctypes
+    from openmines_b200.engine import RNG_MODES
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    stats_box = []
+
+    def body():
+        mine._ck(mine.lib.om_reset(mine.h, mine.seeds.data_ptr(), mine.dispatcher_ids.data_ptr(), RNG_MODES["philox"],
+                                   None, None, None, mine.state.data_ptr(), mine._stream()))
+        mine.run(until=60.0, result=res)
+        stats_box[:] = [mine.stats(res)]
+    with torch.cuda.stream(side):
+        body()                                       # warm-up on the capture stream
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        body()
+    for _ in range(3):
+        res.summary.zero_(); res.ticks.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert res.summary_np().tobytes() == want_s.tobytes() and res.ticks_np().tobytes() == want_t.tobytes()
+        assert np.array_equal(stats_box[0].cpu().numpy(), want_stats)

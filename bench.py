@@ -261,7 +261,7 @@ def run_reference_arm(a):
 # ------------------------------------------------------------------------------------------------
 # BASELINE configs[3]: batched RL env step, random-init policy feeding the orders
 # ------------------------------------------------------------------------------------------------
-def run_c4(a):
+def run_c4(a, emit=True):
     """Steady-state batched RL rollout: policy forward + om_step per env step, every env restarting by itself when its
     episode ends (per-env auto reset).  One bench step = 500 env steps of all envs (about one episode's decisions)."""
     import numpy as np
@@ -384,7 +384,8 @@ def run_c4(a):
         policy_action()
         env._step(act)
     pairs = []
-    for _ in range(100):
+    n_timed = 600            # a whole episode's worth of decisions (~560): the step cost varies with the episode phase
+    for _ in range(n_timed):
         policy_action()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
@@ -443,7 +444,10 @@ def run_c4(a):
                          "kernel": "om_step_kernel<philox>", "kernel_ms": step_ms,
                          "algorithmic_bytes_per_launch": alg,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                         "note": "kernel_ms: mean over 100 om_step launches of the same policy-driven rollout, one CUDA-event pair around each"}}
+                         "note": "kernel_ms: mean over 600 consecutive om_step launches (a whole episode: the cost of a step varies with the episode phase, 0.29-0.42 ms) of the same policy-driven rollout, one CUDA-event pair around each"}}
+    if not emit:
+        env.close()
+        return line
     if rank == 0:
         emit_line(line)
     if dist is not None:
@@ -490,6 +494,61 @@ def run_ablation(a):
 
 
 # ------------------------------------------------------------------------------------------------
+# the other BASELINE configs, measured in the same run (short): the driver only runs the default line, so the numbers of
+# configs[1] / configs[4] ride along under "extras" instead of existing only in builder-run files
+# ------------------------------------------------------------------------------------------------
+def measure_extra(name, rank, local, dist, steps=3, warmup=3):
+    import numpy as np
+    import torch
+    import openmines_b200 as om
+    if name == "c5":
+        from openmines_b200.synthetic import scaled_mine
+        cfg = scaled_mine()
+    else:
+        cfg = load_cfg()
+    disp, seeds, mode, desc = workload(name, 0, rank)
+    mine = om.BatchedMine(cfg, len(disp), device=local, jam_capacity=512 if name == "c5" else 64)
+    mine.reset(disp, seeds=seeds, rng_mode=mode)
+    res = mine.run()
+
+    def step():
+        mine._ck(mine.lib.om_reset(mine.h, mine.seeds.data_ptr(), mine.dispatcher_ids.data_ptr(),
+                                   om.engine.RNG_MODES[mode], None, None, None, mine.state.data_ptr(), mine._stream()))
+        mine.run(result=res)
+        st = mine.stats(res)
+        if dist is not None:
+            dist.all_reduce(st)
+        return st
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=mine.device)
+    evs = []
+    for _ in range(steps):
+        flush.fill_(1)                                   # L2 flushed before every timed step (outside the events)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = step()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = sum(x.elapsed_time(y) for x, y in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device=mine.device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / steps
+    stats = st.cpu().numpy()
+    out = {"workload": desc, "value": float(stats[:, 3].sum()) / (ms_per_step / 1000.0), "unit": UNIT, "ms_per_step": ms_per_step,
+           "episodes_per_s": float(stats[:, 0].sum()) / (ms_per_step / 1000.0), "instance_errors": float(stats[:, 9].sum()),
+           "steps": steps, "warmup": warmup, "launch": mine.launch_info(), "l2_policy": "L2 flushed (512 MB write) before every timed step"}
+    mine.close()
+    del flush
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def main():
@@ -502,6 +561,7 @@ def main():
     ap.add_argument("--instances", type=int, default=0, help="instances per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-counters", action="store_true", help="skip the CUPTI counter pass after the timed region")
+    ap.add_argument("--no-extras", action="store_true", help="default workload only: skip the short configs[1] / configs[4] measurements")
     ap.add_argument("--no-graph", action="store_true", help="c4: launch the rollout iteration eagerly instead of replaying a CUDA graph")
     a = ap.parse_args()
     _quiet_stdout()
@@ -714,6 +774,19 @@ def main():
                     "ms_per_step": 1000 * e2e_s / a.steps},
             "gpu_launches": a.steps * 4,      # om_reset_kernel + om_order_kernel + om_run_kernel + om_stats_kernel per step
             "roofline": roofline}
+    if a.workload == "c3" and not a.no_extras:
+        # BASELINE configs[1] (det, 6 dispatchers x 1024 seeds) and configs[4] (500-truck mine, 1024 instances per GPU), short
+        line["extras"] = {"c2": measure_extra("c2", rank, local, dist), "c5": measure_extra("c5", rank, local, dist)}
+        if world == 1:
+            # BASELINE configs[3]: the batched RL env step with the policy in the loop (one bench step = 500 env steps)
+            import copy
+            a4 = copy.copy(a)
+            a4.steps, a4.warmup, a4.instances, a4.no_counters = 1, 2, 0, True
+            c4 = run_c4(a4, emit=False)
+            line["extras"]["c4"] = {"workload": c4["config"]["workload"], "value": c4["value"], "unit": UNIT,
+                                    "decisions_per_s": c4["decisions_per_s"], "env_steps_per_s": c4["env_steps_per_s"],
+                                    "ms_per_step": c4["ms_per_step"], "om_step_kernel_ms": c4["roofline"]["kernel_ms"],
+                                    "hbm_frac": c4["roofline"]["frac"], "e2e_host_policy": c4["e2e"]}
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
             s = cpu_sample(a.workload, 32)

@@ -13,9 +13,9 @@ timeout -k 10 600 python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-ba
 timeout -k 10 600 python bench.py --workload ablation --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ablation.json 2> gpurun_out/${TAG}_bench_ablation.err; echo "bench ablation rc=$?"
 timeout -k 10 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err; echo "bench reference arm rc=$?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-counters > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-counters --no-extras > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:om_run_kernel -s 1 -c 1 -o gpurun_out/${TAG}_prof -f \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-counters > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-counters --no-extras > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:om_step_kernel -s 200 -c 1 -o gpurun_out/${TAG}_step_prof -f \
     python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline --no-counters > gpurun_out/${TAG}_ncu_step.log 2>&1; echo "ncu step rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:om_run_kernel -s 1 -c 1 -o gpurun_out/${TAG}_c5_prof -f \

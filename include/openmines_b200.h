@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OM_ABI_VERSION 8
+#define OM_ABI_VERSION 9
 
 /* OmConfig.flags */
 #define OM_CFG_RL_SURFACE 1 /* allocate the fields om_step needs (reward windows, minute-sampled site values): bigger
@@ -237,9 +237,11 @@ typedef struct OmStateLayout {
   uint32_t hot_bytes;          /* prefix of the blob the kernels stage in shared memory (== total_bytes unless split) */
   uint32_t hdr_bytes;          /* bytes of the per-instance header present in the blob */
   uint32_t slot_cache;         /* kernel-internal cache (16 B per 32 trucks); contents are meaningless between calls */
-  uint32_t t_road, r_jamcnt;   /* split layouts only (0 otherwise): t_road unused since ABI 7 (always 0); r_jamcnt u16 [R] stored jams per road */
-  uint32_t t_loc, t_lastbrk_hot; /* split layouts only (0 otherwise): {status, cur, tgt, -} u8[4] per truck and last breakdown time
-                                  f64 per truck in the hot part; t_status / t_cur / t_tgt / t_lastbrk then point here (strides 4 / 8) */
+  uint32_t t_aux, r_jamcnt;    /* split layouts only (0 otherwise): t_aux {unit, next, epoch, service count} u16[4] per truck in the hot
+                                  part -- t_unit / t_next / t_epoch / t_svc then point here (stride 8); r_jamcnt u16 [R] stored jams per road */
+  uint32_t t_loc, t_lastbrk_hot; /* split layouts only (0 otherwise): {status, cur, tgt, flags} u8[4] per truck (flags bit 0: a repair
+                                  time is pending) and the MINUTE of the last breakdown as uint16 per truck, both in the hot part;
+                                  t_status / t_cur / t_tgt / t_lastbrk then point here (strides 4 / 2; t_lastbrk is NOT an f64 then) */
   uint32_t r_on, r_head, t_rnext, t_rprev; /* split layouts only (0 otherwise), all u16: moving trucks per road [R], head of the
                                   road's list of them [R] (0xFFFF: empty), next / previous truck on the same road [T] */
 } OmStateLayout;

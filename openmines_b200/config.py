@@ -21,7 +21,7 @@ import math
 
 import numpy as np
 
-OM_ABI_VERSION = 8
+OM_ABI_VERSION = 9
 OM_CFG_RL_SURFACE = 1    # OmConfig.flags: allocate the fields om_step needs (bigger blobs, fewer resident instances)
 
 ROAD_EVENT_DEFAULTS = {            # road.py:37-43

@@ -12,7 +12,9 @@
 
 #include "om_engine.cuh"
 
+#ifndef OM_MAX_WARPS_PER_CTA
 #define OM_MAX_WARPS_PER_CTA 20
+#endif
 #define OM_SMEM_LIMIT (227 * 1024 - 256)   /* minus the static shared memory (mbarriers) */
 
 // ------------------------------------------------------------------------------------------------
@@ -440,8 +442,9 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl, bool split
   ly.u_rel_key = take(off, 4, U);
   ly.s_qtotal = take(off, 2, NS); ly.s_coming = take(off, 2, NS);
   if (split) {   // shared-memory helpers that keep the per-minute / per-departure scans of a big mine out of HBM
-    ly.t_lastbrk_hot = take(off, 8, T);  // last breakdown time per truck (instead of the record field)
-    ly.t_loc = take(off, 4, T);          // {status, current, target, -} per truck (instead of the record fields)
+    ly.t_aux = take(off, 8, T);          // {unit, next in queue, order epoch, service count} u16[4] per truck (instead of the record fields)
+    ly.t_loc = take(off, 4, T);          // {status, current, target, flags} per truck (instead of the record fields)
+    ly.t_lastbrk_hot = take(off, 2, T);  // minute of the last breakdown per truck, uint16 (instead of the record's f64)
     ly.r_jamcnt = take(off, 2, R);       // stored jams per road
     // trucks under way per road: count + doubly linked list, maintained at departure / arrival (jam sampling)
     ly.r_on = take(off, 2, R); ly.r_head = take(off, 2, R);
@@ -458,6 +461,7 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl, bool split
   ly.t_cur = ly.t_rec + 78; ly.t_tgt = ly.t_rec + 79;
   if (split) {   // published offsets follow the data (strides: t_loc_stride / 8)
     ly.t_status = ly.t_loc + 0; ly.t_cur = ly.t_loc + 1; ly.t_tgt = ly.t_loc + 2; ly.t_lastbrk = ly.t_lastbrk_hot;
+    ly.t_unit = ly.t_aux + 0; ly.t_next = ly.t_aux + 2; ly.t_epoch = ly.t_aux + 4; ly.t_svc = ly.t_aux + 6;
   }
   if (rl) ly.t_since = take(off, 8, T);
   ly.j_pos = take(off, 8, J); ly.j_end = take(off, 8, J);
@@ -797,6 +801,7 @@ int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* s
   if (!h || !state) return set_err(h, OM_E_INVALID, "om_run: null argument");
   if (!h->reset_done) return set_err(h, OM_E_INVALID, "om_run: om_reset has not been called on this handle (the state blobs are uninitialised)");
   if (((uintptr_t)state & 15u) != 0) return set_err(h, OM_E_INVALID, "om_run: state must be 16-byte aligned (TMA bulk copies)");
+  if (h->split && !(until <= 65535.0)) return set_err(h, OM_E_UNSUPPORTED, "om_run: split layouts (big mines) hold breakdown minutes as uint16: until <= 65535");
   CK(cudaSetDevice(h->device));
   RunParams p;
   memset(&p, 0, sizeof(p));
@@ -851,6 +856,7 @@ int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* str
   if (!h->rl) return set_err(h, OM_E_INVALID, "om_step: the handle was created without OM_CFG_RL_SURFACE (OmConfig.flags)");
   if (h->multi) return set_err(h, OM_E_UNSUPPORTED, "om_step: not available on a mixed-config handle");
   if (((uintptr_t)state & 15u) != 0) return set_err(h, OM_E_INVALID, "om_step: state must be 16-byte aligned (TMA bulk copies)");
+  if (h->split && !(until <= 65535.0)) return set_err(h, OM_E_UNSUPPORTED, "om_step: split layouts (big mines) hold breakdown minutes as uint16: until <= 65535");
   CK(cudaSetDevice(h->device));
   RunParams p;
   memset(&p, 0, sizeof(p));

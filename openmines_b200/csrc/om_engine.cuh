@@ -252,6 +252,7 @@ struct Sim {
   double rl_last, rl_last_prod, acc_wait, acc_shovel, acc_dumper, acc_move, acc_jam;   // RL only
 
   int ns_stride, u_stride_out;
+  static constexpr bool LY_DYNAMIC = false;   // see OM_SPLIT_HOT
   __device__ __forceinline__ Sim(unsigned char* sm_, unsigned char* blob, const RunParams& p, const DevCfg& cfg, int lane_, long long inst_)
       : sm(sm_), cold(SPLIT ? blob : sm_), c(cfg), ly(p.ly), out(p.out), lane(lane_), inst(inst_), ordw_ready(false),
         ns_stride(p.ns_stride), u_stride_out(p.u_stride_out) {}
@@ -276,21 +277,28 @@ struct Sim {
 #define OM_A_t_load(type, i) OM_TREC(type, 0, i)
 #define OM_A_t_jstart(type, i) OM_TREC(type, 8, i)
 #define OM_A_t_prejam(type, i) OM_TREC(type, 16, i)
+  // Split layouts (big mines) keep what the scalar chains LOAD of a truck in small hot arrays, so that a pop costs no
+  // L2 round trip for them: t_loc {status, current, target, flags} (4 B), t_aux {unit, next-in-queue, order epoch, service
+  // count} (8 B) and the minute of the last breakdown as a uint16 (2 B; it is always an integer minute, see lastbrk_*()).
+  // OM_SPLIT_HOT(f): this kernel / this layout has them (the SPLIT kernels only ever see split layouts; om_init_state()
+  // serves both and looks at the layout).
 #define OM_THOT(type, field, esz, off, i) (*(type*)(sm + ly.field + (uint32_t)(i) * (esz) + (off)))
-#define OM_A_t_lastbrk(type, i) (*((SPLIT && ly.t_lastbrk_hot) ? &OM_THOT(type, t_lastbrk_hot, 8u, 0, i) : &OM_TREC(type, 24, i)))
+#define OM_SPLIT_HOT(f) (SPLIT && (!LY_DYNAMIC || ly.f != 0))
+#define OM_A_t_lastbrk(type, i) OM_TREC(type, 24, i)   /* unsplit layouts only: use lastbrk_get() / lastbrk_set_now() */
 #define OM_A_t_repair(type, i) OM_TREC(type, 32, i)
 #define OM_A_t_total(type, i) OM_TREC(type, 40, i)
 #define OM_A_t_cycle(type, i) OM_TREC(type, 48, i)
 #define OM_A_t_dist(type, i) OM_TREC(type, 56, i)
 #define OM_A_t_since(type, i) OM_SOAC(type, t_since, i)   /* RL surface only */
 #define OM_A_t_rng(type, i) OM_TREC(type, 64, i)
-#define OM_A_t_svc(type, i) OM_TREC(type, 68, i)
-#define OM_A_t_epoch(type, i) OM_TREC(type, 70, i)
-#define OM_A_t_next(type, i) OM_TREC(type, 72, i)
-#define OM_A_t_unit(type, i) OM_TREC(type, 74, i)
-#define OM_A_t_status(type, i) (*((SPLIT && ly.t_loc) ? &OM_THOT(type, t_loc, 4u, 0, i) : &OM_TREC(type, 77, i)))
-#define OM_A_t_cur(type, i) (*((SPLIT && ly.t_loc) ? &OM_THOT(type, t_loc, 4u, 1, i) : &OM_TREC(type, 78, i)))
-#define OM_A_t_tgt(type, i) (*((SPLIT && ly.t_loc) ? &OM_THOT(type, t_loc, 4u, 2, i) : &OM_TREC(type, 79, i)))
+#define OM_A_t_svc(type, i) (*(OM_SPLIT_HOT(t_aux) ? &OM_THOT(type, t_aux, 8u, 6, i) : &OM_TREC(type, 68, i)))
+#define OM_A_t_epoch(type, i) (*(OM_SPLIT_HOT(t_aux) ? &OM_THOT(type, t_aux, 8u, 4, i) : &OM_TREC(type, 70, i)))
+#define OM_A_t_next(type, i) (*(OM_SPLIT_HOT(t_aux) ? &OM_THOT(type, t_aux, 8u, 2, i) : &OM_TREC(type, 72, i)))
+#define OM_A_t_unit(type, i) (*(OM_SPLIT_HOT(t_aux) ? &OM_THOT(type, t_aux, 8u, 0, i) : &OM_TREC(type, 74, i)))
+#define OM_A_t_status(type, i) (*(OM_SPLIT_HOT(t_loc) ? &OM_THOT(type, t_loc, 4u, 0, i) : &OM_TREC(type, 77, i)))
+#define OM_A_t_cur(type, i) (*(OM_SPLIT_HOT(t_loc) ? &OM_THOT(type, t_loc, 4u, 1, i) : &OM_TREC(type, 78, i)))
+#define OM_A_t_tgt(type, i) (*(OM_SPLIT_HOT(t_loc) ? &OM_THOT(type, t_loc, 4u, 2, i) : &OM_TREC(type, 79, i)))
+#define OM_A_t_flags(type, i) OM_THOT(type, t_loc, 4u, 3, i)   /* split layouts only: bit 0 = a repair time is pending (t_repair != 0) */
 #define OM_A_u_rel_key(type, i) OM_SOA(type, u_rel_key, i)
 #define OM_A_u_last_start(type, i) OM_UREC(type, 0, i)
 #define OM_A_u_last_done(type, i) OM_UREC(type, 8, i)
@@ -337,6 +345,7 @@ struct Sim {
 #define OM_B_t_status c.T
 #define OM_B_t_cur c.T
 #define OM_B_t_tgt c.T
+#define OM_B_t_flags c.T
 #define OM_B_u_rel_key c.U
 #define OM_B_u_last_start c.U
 #define OM_B_u_last_done c.U
@@ -531,6 +540,31 @@ struct Sim {
   }
   __device__ __forceinline__ void fail(uint32_t code) {
     if (err == OM_IERR_NONE || err == OM_IERR_TRACE_OVERFLOW) err = code;
+  }
+  // Truck.last_breakdown_time (truck.py:522-536): only ever set to the clock of a monitor block, i.e. to an integer minute
+  // (or its initial 0), so split layouts hold it as a uint16 in the hot part (om_run refuses until > 65535 there).
+  __device__ __forceinline__ double lastbrk_get(int i) {
+    if (SPLIT) return (double)((const uint16_t*)(sm + ly.t_lastbrk_hot))[OM_IDX(t_lastbrk, i)];
+    return F64(t_lastbrk, i);
+  }
+  __device__ __forceinline__ void lastbrk_set_now(int i) {
+    if (SPLIT) ((uint16_t*)(sm + ly.t_lastbrk_hot))[OM_IDX(t_lastbrk, i)] = (uint16_t)(int)now;
+    else F64(t_lastbrk, i) = now;
+  }
+  // Truck.repair_time: written by the minute's breakdown sampling, consumed and cleared by the truck's next move.  Split
+  // layouts flag a pending one in the hot part so that the move (and the jam sampler's coverage()) only goes to the
+  // truck's record in HBM when there is something to read.
+  __device__ __forceinline__ void repair_set(int i, double d) {
+    F64(t_repair, i) = d;
+    if (SPLIT) U8A(t_flags, i) = 1;
+  }
+  __device__ __forceinline__ double repair_get(int i) {
+    if (SPLIT && U8A(t_flags, i) == 0) return 0.0;
+    return F64(t_repair, i);
+  }
+  __device__ __forceinline__ void repair_clear(int i) {
+    F64(t_repair, i) = 0.0;
+    if (SPLIT) U8A(t_flags, i) = 0;
   }
 
   // FIFO of waiting trucks per unit (simpy Resource.put_queue), linked through t_next
@@ -1165,10 +1199,10 @@ struct Sim {
         #pragma unroll 1
         for (int i = 0; i < T; ++i) {
           double gap = tape_next(OM_S_BREAK_GAP);
-          if (now >= F64(t_lastbrk, i) + gap) {
+          if (now >= lastbrk_get(i) + gap) {
             double d = tape_next(OM_S_BREAK_DUR);
-            F64(t_repair, i) = (0.0 > d) ? 0.0 : d;
-            F64(t_lastbrk, i) = now;
+            repair_set(i, (0.0 > d) ? 0.0 : d);
+            lastbrk_set_now(i);
           }
         }
       } else {
@@ -1197,7 +1231,7 @@ struct Sim {
                 tape_put_at(tbase + 2ull * (unsigned long long)i, OM_S_BREAK_GAP, gap);
                 tape_put_at(tbase + 2ull * (unsigned long long)i + 1ull, OM_DRAW_SKIP, 0.0);
               }
-              if (now >= F64(t_lastbrk, i) + gap) {
+              if (now >= lastbrk_get(i) + gap) {
                 if (used) {
                   Philox4 r2 = px((uint32_t)k, (uint32_t)i, OM_S_BREAK_DUR);
                   na = r2.x; nb2 = r2.y;
@@ -1205,8 +1239,8 @@ struct Sim {
                 used = true;
                 double d = c.repair_mu + c.repair_sigma * (double)om_normal_fast(na, nb2);
                 if (TAPE_OUT && tp) tape_put_at(tbase + 2ull * (unsigned long long)i + 1ull, OM_S_BREAK_DUR, d);
-                F64(t_repair, i) = (0.0 > d) ? 0.0 : d;
-                F64(t_lastbrk, i) = now;
+                repair_set(i, (0.0 > d) ? 0.0 : d);
+                lastbrk_set_now(i);
               }
             }
           }
@@ -1370,7 +1404,7 @@ struct Sim {
 
   // Truck.get_route_coverage (truck.py:496-520)
   __device__ __forceinline__ float coverage(int i, int rid) {
-    double total = __ldg(&c.trip60[__ldg(&c.sclass[i]) * c.R + rid]) + F64(t_prejam, i) + F64(t_repair, i);
+    double total = __ldg(&c.trip60[__ldg(&c.sclass[i]) * c.R + rid]) + F64(t_prejam, i) + repair_get(i);
     double cov = om_ddiv0(now - F64(t_jstart, i), total);
     if (cov > 1.0) cov = 1.0;
     return (float)cov;
@@ -1409,10 +1443,28 @@ struct Sim {
     if (rel_u >= 0) file_release(rel_u, rel_key);
   }
 
-  __device__ __forceinline__ void run(double until) {
+  // `resume_i` (om_step only): the truck whose order the caller has just applied at `now` > 0.  Its Initialize(move) is
+  // URGENT at the current clock and no other URGENT entry can be pending, so it is the very next pop: the first trip
+  // enters MOVE_BEGIN directly (one hop counted, its eid already consumed by the caller) instead of storing the entry and
+  // finding it again by a warp reduction.  Other entries may share the timestamp (the Release filed at the pause), so no
+  // same-time chain is assumed.
+  __device__ __forceinline__ void run(double until, int resume_i = -1) {
     const int T = c.T, U = c.U, L = c.L, D = c.D, S = c.S;
     int pend_truck = -1, pend_kind = -1;
     for (;;) {
+      bool inl, chain;
+      int i, rel_u, kind, u;
+      uint32_t rel_key, ph0;
+      bool dead, dump;
+      if (RL && resume_i >= 0) {
+        i = resume_i; resume_i = -1;
+        n_hops++;
+        inl = true; chain = false; rel_u = -1; rel_key = 0; kind = 0; u = 0; ph0 = 0; dead = false; dump = false;
+        ordw_ready = false;
+        OM_CONV();
+        goto L_MOVE_BEGIN;
+      }
+      {
       // ---- next pending entry.  Times are >= 0, so their bit patterns order as unsigned integers.
       uint32_t bhi = 0x7FF00000u, blo = 0u, bk = OM_KEY_SENTINEL;
       int bid = -1;
@@ -1503,15 +1555,15 @@ struct Sim {
       OM_CONV();
       if (__builtin_expect(is_tick, 0)) { tick_block(); OM_CONV(); continue; }   // 15 % of the pops: keep its 12 KB out of the main path
 
-      const bool inl = now > 0.0;            // URGENT successors run inline
-      const bool chain = unique && inl;      // same-time NORMAL successors run inline
-      int i = id;
-      int rel_u = -1;                        // Release created in this chain, not yet popped (kept in registers)
+      inl = now > 0.0;                       // URGENT successors run inline
+      chain = unique && inl;                 // same-time NORMAL successors run inline
+      i = id;
+      rel_u = -1;                            // Release created in this chain, not yet popped (kept in registers)
       ordw_ready = false;
-      uint32_t rel_key = 0;
-      int kind = 0, u = 0;
-      uint32_t ph0 = 0;
-      bool dead = false, dump = false;
+      rel_key = 0;
+      kind = 0; u = 0;
+      ph0 = 0;
+      dead = false; dump = false;
       if (id >= T) {
         // Release event popped: Resource._trigger_put hands the unit to the queue head
         u = id - T;
@@ -1529,9 +1581,10 @@ struct Sim {
         case PH_MOVE_ARRIVE: goto L_ARRIVE;
         case PH_LOAD_DONE: case PH_DUMP_DONE: goto L_SVC_DONE;
         case PH_MOVE_RET: goto L_MOVE_RET;
-        case PH_LOAD_GRANTED: case PH_DUMP_GRANTED: goto L_GRANTED;
-        case PH_LOAD_BEGIN: case PH_DUMP_BEGIN: goto L_BEGIN;
-        case PH_LOAD_RET: case PH_DUMP_RET: goto L_SVC_RET;
+        // `u` (the truck's unit) is in a register on every fused path into the labels below; only these entries load it
+        case PH_LOAD_GRANTED: case PH_DUMP_GRANTED: u = U16A(t_unit, i); goto L_GRANTED;
+        case PH_LOAD_BEGIN: case PH_DUMP_BEGIN: u = U16A(t_unit, i); goto L_BEGIN;
+        case PH_LOAD_RET: case PH_DUMP_RET: u = U16A(t_unit, i); goto L_SVC_RET;
         case PH_MOVE_BEGIN: goto L_MOVE_BEGIN;
         case PH_RUN_INIT:                                              // truck.py:296-302
           U8A(t_cur, i) = 0;
@@ -1539,7 +1592,7 @@ struct Sim {
           kind = OM_ORDER_INIT;
           goto L_ORDER;
         case PH_MOVE_REPAIRED:
-          F64(t_repair, i) = 0.0;
+          repair_clear(i);
           U8A(t_status, i) = ST_MOVING;
           goto L_DEPART;
         case PH_MAINT_DONE:                                            // truck.py:372-379
@@ -1550,6 +1603,7 @@ struct Sim {
         default:
           if (ph0 >= PH_CRASH_BASE) fail(ph0 - PH_CRASH_BASE);           // the failed Process event pops: env.step() raises
           continue;
+      }
       }
 
       // ================= chain 1: ARRIVE -> RET -> (grant) -> GRANTED -> BEGIN =================
@@ -1591,7 +1645,6 @@ struct Sim {
     }
     L_GRANTED:                                                         // truck.py:342-350 / 422-429
       OM_CONV();
-      u = U16A(t_unit, i);
       dump = u >= S;
       if (!dump) rl_close(acc_wait, i);
       if (RL) F64(t_since, i) = now;
@@ -1602,7 +1655,6 @@ struct Sim {
         continue;
       }
     L_BEGIN: {                                                         // truck.py:221-228 / 238-242
-      u = U16A(t_unit, i);
       dump = u >= S;
       U8A(t_status, i) = dump ? ST_UNLOADING : ST_LOADING;
       F64(u_last_start, u) = now;
@@ -1652,7 +1704,6 @@ struct Sim {
       seq++;                                                           // Process(load/unload) event
     }
     L_SVC_RET:                                                         // truck.py:352-370 / 431-441
-      u = U16A(t_unit, i);
       dump = u >= S;
       if (dump) {
         rl_close(acc_dumper, i);
@@ -1695,7 +1746,7 @@ struct Sim {
         if (RNG == OM_RNG_PHILOX) tape_put(OM_S_UNREPAIRABLE, g);
         dead = now >= g;                                               // check_vehicle_availability, truck.py:538-547
       }
-      double rep = F64(t_repair, i);
+      double rep = repair_get(i);
       if (!dead && rep != 0.0) { begin_repair(i, rep); goto L_AFTER_DEPART; }
     }
     L_DEPART:                                                          // truck.py:151-210
@@ -1728,7 +1779,7 @@ struct Sim {
   }
   __device__ __forceinline__ void begin_repair(int i, double rep) {    // truck.py:143-150
     n_brk++;
-    emit(K_BREAKDOWN, (uint32_t)i, 0, 0, F64(t_lastbrk, i), rep);
+    emit(K_BREAKDOWN, (uint32_t)i, 0, 0, lastbrk_get(i), rep);
     U8A(t_status, i) = ST_REPAIRING;
     sched_truck(i, now + rep, OM_KEY_NORMAL, PH_MOVE_REPAIRED);
   }
@@ -1897,6 +1948,7 @@ struct Sim {
       return;
     }
     int pt = h->pending_truck, pk = h->pending_kind;
+    int resume = -1;
     if (pt >= 0) {
       // the agent's action arrives: RLDispatcher._step returns, truck.py:303-317 / 390-402 / 442-453 continue
       int a = io.actions ? io.actions[inst] : 0;
@@ -1906,14 +1958,16 @@ struct Sim {
         sched_truck(pt, now, OM_KEY_NORMAL, (uint8_t)(PH_CRASH_BASE + OM_IERR_BAD_ORDER));
       } else {
         apply_order(pt, pk, a);
-        set_entry(pt, now, seq, PH_MOVE_BEGIN);   // Initialize(move), URGENT
+        if (now > 0.0) resume = pt;                     // Initialize(move), URGENT: the very next pop (see run())
+        else set_entry(pt, now, seq, PH_MOVE_BEGIN);    // t = 0: the other trucks' Initialize(run) entries come first
         seq++;
       }
       h->pending_truck = -1; h->pending_kind = -1;
     }
     bool fresh = false;       // true once this call has auto-reset the env: the finished episode's outputs stay
   L_RUN:
-    run(p.until);
+    run(p.until, resume);
+    resume = -1;
     pt = h->pending_truck; pk = h->pending_kind;
     const bool failed = (err != OM_IERR_NONE && err != OM_IERR_TRACE_OVERFLOW);
     float* ob = io.obs + (size_t)inst * p.obs_dim;
@@ -2009,7 +2063,7 @@ __device__ __forceinline__ void om_init_state(unsigned char* sm, unsigned char* 
 #ifdef OM_BOUNDS_CHECK
   uint32_t dbg_viol = 0;
 #endif
-  const bool SPLIT = true;   // accessors: follow the layout (ly.t_loc != 0 <=> the handle runs the SPLIT kernels)
+  const bool SPLIT = true, LY_DYNAMIC = true;   // accessors: follow the layout (ly.t_loc != 0 <=> the handle runs the SPLIT kernels)
   // zero everything first
   #pragma unroll 1
   for (uint32_t o = lane * 8; o < sm_bytes; o += 256) *(unsigned long long*)(sm + o) = 0ull;

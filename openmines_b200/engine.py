@@ -47,7 +47,7 @@ _LAYOUT_FIELDS = ["total_bytes", "hdr", "t_time", "t_load", "t_jstart", "t_preja
                   "t_status", "t_cur", "t_tgt", "u_last_start", "u_last_done", "u_tons", "u_lastbrk",
                   "u_rel_key", "u_svc", "u_user", "u_head", "u_tail", "u_qlen", "u_repair", "r_repair_end",
                   "j_pos", "j_start", "j_end", "j_road", "s_qtotal", "s_coming", "s_tons", "s_cap", "s_ability", "scratch",
-                  "t_rec", "u_rec", "t_stride", "u_stride", "e_stride", "hot_bytes", "hdr_bytes", "slot_cache", "t_road", "r_jamcnt", "t_loc", "t_lastbrk_hot", "r_on", "r_head", "t_rnext", "t_rprev"]
+                  "t_rec", "u_rec", "t_stride", "u_stride", "e_stride", "hot_bytes", "hdr_bytes", "slot_cache", "t_aux", "r_jamcnt", "t_loc", "t_lastbrk_hot", "r_on", "r_head", "t_rnext", "t_rprev"]
 _ENTRY_FIELDS = {"t_time", "t_key", "t_phase"}                # the truck's 16-byte pending entry
 _SOA_FIELDS = {"u_rel_key", "u_lastbrk", "t_since"}            # every other t_* / u_* field lives in a record
 
@@ -397,9 +397,12 @@ class BatchedMine:
             item = np.dtype(dtype).itemsize
             stride = item
             if ly.t_loc and field in ("t_status", "t_cur", "t_tgt"):
-                stride = 4                                  # split layouts: {status, cur, tgt, -} per truck in the hot part
+                stride = 4                                  # split layouts: {status, cur, tgt, flags} per truck in the hot part
+            elif ly.t_aux and field in ("t_unit", "t_next", "t_epoch", "t_svc"):
+                stride = 8                                  # split layouts: {unit, next, epoch, svc} per truck in the hot part
             elif ly.t_lastbrk_hot and field == "t_lastbrk":
-                stride = 8
+                # split layouts: the minute of the last breakdown as a uint16 (it is always an integer minute)
+                return np.ndarray((count,), dtype=np.uint16, buffer=raw, offset=off, strides=(2,)).astype(np.float64)
             elif field in _ENTRY_FIELDS:
                 stride = ly.e_stride
             elif field not in _SOA_FIELDS and field[:2] in ("t_", "u_"):

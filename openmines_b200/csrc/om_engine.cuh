@@ -246,6 +246,13 @@ struct Sim {
   const double* tape_v;
   const uint8_t* tape_s;
   uint32_t dbg_viol = 0;   // bounds-check build: source line of this lane's first out-of-range state access
+  // Values of the current truck that one continuation stores and a later one of the same chain reads back: the SPLIT
+  // kernels (truck records in HBM: every such load is an L2 round trip in the scalar chain) keep them in registers along
+  // fused chains; the record fields are still written, and an entry through the event loop loads them.  The unsplit
+  // kernels read them back from shared memory (measured: carrying them costs the north_pit kernel 2 %).
+  static constexpr bool CARRY = SPLIT;
+  uint32_t rngw;  // t_rng: Philox word saved for the next draw of this truck (maintenance gap / unrepairable gap)
+  double distw;   // t_dist: length of the move the last order started
   Philox4 ordw;   // words of the current order's Philox call (PHILOX mode)
   bool ordw_ready; // ordw already holds them (computed alongside the load draw earlier in this chain)
   uint32_t dirty; // slots (groups of 32 trucks) whose cached minimum is stale (see run())
@@ -254,7 +261,7 @@ struct Sim {
   int ns_stride, u_stride_out;
   static constexpr bool LY_DYNAMIC = false;   // see OM_SPLIT_HOT
   __device__ __forceinline__ Sim(unsigned char* sm_, unsigned char* blob, const RunParams& p, const DevCfg& cfg, int lane_, long long inst_)
-      : sm(sm_), cold(SPLIT ? blob : sm_), c(cfg), ly(p.ly), out(p.out), lane(lane_), inst(inst_), ordw_ready(false),
+      : sm(sm_), cold(SPLIT ? blob : sm_), c(cfg), ly(p.ly), out(p.out), lane(lane_), inst(inst_), rngw(0u), distw(0.0), ordw_ready(false),
         ns_stride(p.ns_stride), u_stride_out(p.u_stride_out) {}
 
   // State accessors.  Per-truck and per-unit scalars live in fixed-size records (array of structures): the scalar
@@ -556,17 +563,16 @@ struct Sim {
   // truck's record in HBM when there is something to read.
   __device__ __forceinline__ void repair_set(int i, double d) {
     F64(t_repair, i) = d;
-    if (SPLIT) U8A(t_flags, i) = 1;
+    if (SPLIT) U8A(t_flags, i) = (uint8_t)(U8A(t_flags, i) | 1u);
   }
   __device__ __forceinline__ double repair_get(int i) {
-    if (SPLIT && U8A(t_flags, i) == 0) return 0.0;
+    if (SPLIT && (U8A(t_flags, i) & 1u) == 0) return 0.0;
     return F64(t_repair, i);
   }
   __device__ __forceinline__ void repair_clear(int i) {
     F64(t_repair, i) = 0.0;
-    if (SPLIT) U8A(t_flags, i) = 0;
+    if (SPLIT) U8A(t_flags, i) = (uint8_t)(U8A(t_flags, i) & 0xFEu);
   }
-
   // FIFO of waiting trucks per unit (simpy Resource.put_queue), linked through t_next
   __device__ __forceinline__ void q_push(int u, int i) {
     uint32_t n = U16A(u_qlen, u);
@@ -914,6 +920,7 @@ struct Sim {
       if (!ordw_ready) ordw = px(epoch, (uint32_t)i, OM_S_ROAD_GAP);
       ordw_ready = false;
       U32A(t_rng, i) = ordw.y;
+      rngw = ordw.y;
     }
     count_order(kind, site);
     U16A(t_epoch, i) = (uint16_t)(epoch + 1);
@@ -929,13 +936,14 @@ struct Sim {
     emit((kind == OM_ORDER_INIT) ? K_INIT_ORDER : ((kind == OM_ORDER_HAUL) ? K_ORDER_HAUL : K_ORDER_BACK), (uint32_t)i,
          (uint32_t)site, 0, dist, 0.0);
     F64(t_dist, i) = dist;
+    if (CARRY) distw = dist;
   }
 
   // Big mines (SPLIT layouts): the trucks under way on every road are kept as a doubly linked list per road in shared memory
   // (r_head / t_rnext / t_rprev, with the count in r_on), maintained at departure and arrival -- so the per-minute jam
   // sampling neither recounts 500 trucks nor scans them once per sampled position (both were 16-trip passes).
   __device__ __forceinline__ void road_link(int i, int rid) {
-    if (SPLIT && ly.r_head != 0) {
+    if (SPLIT) {
       uint16_t* head = (uint16_t*)(sm + ly.r_head);
       uint16_t* nxt = (uint16_t*)(sm + ly.t_rnext);
       uint16_t* prv = (uint16_t*)(sm + ly.t_rprev);
@@ -948,7 +956,7 @@ struct Sim {
     }
   }
   __device__ __forceinline__ void road_unlink(int i, int rid) {
-    if (SPLIT && ly.r_head != 0) {
+    if (SPLIT) {
       uint16_t* head = (uint16_t*)(sm + ly.r_head);
       uint16_t* nxt = (uint16_t*)(sm + ly.t_rnext);
       uint16_t* prv = (uint16_t*)(sm + ly.t_rprev);
@@ -963,14 +971,14 @@ struct Sim {
   // move(): jam scan + departure (truck.py:151-210)
   __device__ __forceinline__ void move_depart(int i, bool dead) {
     int cur = U8A(t_cur, i), tgt = U8A(t_tgt, i);
-    double dist = F64(t_dist, i);
+    double dist = CARRY ? distw : F64(t_dist, i);   // CARRY: every path into the departure has t_dist in the register
     const int rid = road_id(cur, tgt);
     // (distance / speed) * 60: tabulated per (speed class, road) for the road's own length; only a detour divides
     double duration = __ldg(&c.trip60[__ldg(&c.sclass[i]) * c.R + rid]);
     if (__builtin_expect(dist != __ldg(&c.rdist[rid]), 0)) duration = om_ddiv(dist, __ldg(&c.speed[i])) * 60.0;
     double pre = 0.0;
     if (RNG != OM_RNG_DET && jam_count > 0) {
-      const bool maybe = !(SPLIT && ly.r_jamcnt != 0) || ((const uint16_t*)(sm + ly.r_jamcnt))[rid] != 0;
+      const bool maybe = !SPLIT || ((const uint16_t*)(sm + ly.r_jamcnt))[rid] != 0;
       #pragma unroll 1
       for (uint32_t base = 0; maybe && base < jam_count; base += 32) {
         uint32_t j = base + lane;
@@ -1010,9 +1018,9 @@ struct Sim {
   __device__ __forceinline__ void jam_append(int rid, double pos, double end) {
     // Big mines (SPLIT): per-road count of stored jams in shared memory, so a departure on a road without jams (most
     // of them) does not scan the jam pool in HBM.  Exact after a compaction, an over-estimate (expired jams) between.
-    uint16_t* rjc = (SPLIT && ly.r_jamcnt != 0) ? (uint16_t*)(sm + ly.r_jamcnt) : nullptr;
+    uint16_t* rjc = SPLIT ? (uint16_t*)(sm + ly.r_jamcnt) : nullptr;   // every split layout has it
     if (__builtin_expect(jam_count == (uint32_t)c.J, 0)) {   // drop expired entries, keep creation order
-      if (SPLIT && rjc != nullptr) {
+      if (SPLIT) {
         #pragma unroll 1
         for (int r = lane; r < c.R; r += 32) rjc[r] = 0;
         __syncwarp();
@@ -1029,7 +1037,7 @@ struct Sim {
             F64(j_pos, w) = F64(j_pos, j); if (RL) F64(j_start, w) = F64(j_start, j);
             F64(j_end, w) = F64(j_end, j); U16A(j_road, w) = U16A(j_road, j);
           }
-          if (SPLIT && rjc != nullptr) rjc[U16A(j_road, w)] = (uint16_t)(rjc[U16A(j_road, w)] + 1);
+          if (SPLIT) rjc[U16A(j_road, w)] = (uint16_t)(rjc[U16A(j_road, w)] + 1);
           w++;
         }
       }
@@ -1038,7 +1046,7 @@ struct Sim {
     if (jam_count == (uint32_t)c.J) { fail(OM_IERR_JAM_OVERFLOW); return; }
     F64(j_pos, jam_count) = pos; if (RL) F64(j_start, jam_count) = now; F64(j_end, jam_count) = end;
     U16A(j_road, jam_count) = (uint16_t)rid;
-    if (SPLIT && rjc != nullptr) rjc[rid] = (uint16_t)(rjc[rid] + 1);
+    if (SPLIT) rjc[rid] = (uint16_t)(rjc[rid] + 1);
     jam_count++;
   }
 
@@ -1046,7 +1054,7 @@ struct Sim {
   // delays of the jams on its road in that order).  The pool of the 500-truck mine otherwise fills up with expired entries
   // (it is only compacted when full) and every departure on a road with a stored jam scans all 512 of them.
   __device__ __forceinline__ void jam_compact_parallel() {
-    uint16_t* rjc = (ly.r_jamcnt != 0) ? (uint16_t*)(sm + ly.r_jamcnt) : nullptr;
+    uint16_t* rjc = (uint16_t*)(sm + ly.r_jamcnt);     // only called by the SPLIT kernels, whose layouts have it
     uint32_t w = 0;
     double expired = 0.0;                              // RL: jam minutes of the dropped entries inside the reward window
     #pragma unroll 1
@@ -1069,7 +1077,7 @@ struct Sim {
         F64(j_end, dst) = en; F64(j_pos, dst) = pos; U16A(j_road, dst) = (uint16_t)rd; if (RL) F64(j_start, dst) = st;
       }
       w += (uint32_t)__popc(m);
-      if (rjc != nullptr) {
+      {
         #pragma unroll 1
         while (md) {                                   // stored jams per road: the dropped ones leave (warp-uniform)
           const int b = __ffs(md) - 1;
@@ -1261,8 +1269,8 @@ struct Sim {
   __device__ __forceinline__ void jam_sampling(int k) {
     const int T = c.T, R = c.R;
     uint32_t* rcnt = (uint32_t*)(sm + ly.scratch);   // scratch is sized >= max(U, R/2 + 1, 32) doubles
-    const uint16_t* ron = (SPLIT && ly.r_on != 0) ? (const uint16_t*)(sm + ly.r_on) : nullptr;   // big mines: kept incrementally
-    if (!(SPLIT && ron != nullptr)) {
+    const uint16_t* ron = SPLIT ? (const uint16_t*)(sm + ly.r_on) : nullptr;   // big mines: kept incrementally
+    if (!SPLIT) {
       #pragma unroll 1
       for (int r = lane; r < R; r += 32) rcnt[r] = 0;
       __syncwarp();
@@ -1281,14 +1289,14 @@ struct Sim {
     #pragma unroll 1
     for (int base = 0; base < R; base += 32) {
       int r = base + lane;
-      uint32_t n_on = (r < R) ? ((SPLIT && ron != nullptr) ? (uint32_t)ron[r] : rcnt[r]) : 0u;
+      uint32_t n_on = (r < R) ? (SPLIT ? (uint32_t)ron[r] : rcnt[r]) : 0u;
       bool candidate = n_on >= 2u;                          // road.py:148-176: >= 2 moving trucks
       bool hit = candidate;
       double coin = 0.0;
       const bool second = (base & 32) != 0;
       if (RNG == OM_RNG_PHILOX) {
         if (!second) {
-          uint32_t n2 = (r + 32 < R) ? ((SPLIT && ron != nullptr) ? (uint32_t)ron[r + 32] : rcnt[r + 32]) : 0u;
+          uint32_t n2 = (r + 32 < R) ? (SPLIT ? (uint32_t)ron[r + 32] : rcnt[r + 32]) : 0u;
           if (__any_sync(OM_FULL, candidate || n2 >= 2u)) rr = px((uint32_t)k, (uint32_t)r, OM_S_JAM_COIN);
         }
         uint32_t cw = second ? rr.y : rr.x;
@@ -1347,7 +1355,7 @@ struct Sim {
       Philox4 r = px((uint32_t)k, (uint32_t)rid, OM_S_JAM_POS, it);
       int pick = (int)om_randint(r.x, n_on);               // pick-th truck on this road (truck order; list order for big mines)
       int found = -1;
-      if (SPLIT && ly.r_head != 0) {
+      if (SPLIT) {
         // big mines: walk the road's list (a uniform pick is uniform whatever the order of the list)
         const uint16_t* nxt = (const uint16_t*)(sm + ly.t_rnext);
         uint32_t tk = ((const uint16_t*)(sm + ly.r_head))[rid];
@@ -1443,28 +1451,16 @@ struct Sim {
     if (rel_u >= 0) file_release(rel_u, rel_key);
   }
 
-  // `resume_i` (om_step only): the truck whose order the caller has just applied at `now` > 0.  Its Initialize(move) is
-  // URGENT at the current clock and no other URGENT entry can be pending, so it is the very next pop: the first trip
-  // enters MOVE_BEGIN directly (one hop counted, its eid already consumed by the caller) instead of storing the entry and
-  // finding it again by a warp reduction.  Other entries may share the timestamp (the Release filed at the pause), so no
-  // same-time chain is assumed.
-  __device__ __forceinline__ void run(double until, int resume_i = -1) {
+  // CARRY kernels, a move continued through the event loop: what apply_order() left in registers comes from the record
+  __device__ __forceinline__ void load_move_carry(int i) {
+    if (RNG == OM_RNG_PHILOX) rngw = U32A(t_rng, i);
+    distw = F64(t_dist, i);
+  }
+
+  __device__ __forceinline__ void run(double until) {
     const int T = c.T, U = c.U, L = c.L, D = c.D, S = c.S;
     int pend_truck = -1, pend_kind = -1;
     for (;;) {
-      bool inl, chain;
-      int i, rel_u, kind, u;
-      uint32_t rel_key, ph0;
-      bool dead, dump;
-      if (RL && resume_i >= 0) {
-        i = resume_i; resume_i = -1;
-        n_hops++;
-        inl = true; chain = false; rel_u = -1; rel_key = 0; kind = 0; u = 0; ph0 = 0; dead = false; dump = false;
-        ordw_ready = false;
-        OM_CONV();
-        goto L_MOVE_BEGIN;
-      }
-      {
       // ---- next pending entry.  Times are >= 0, so their bit patterns order as unsigned integers.
       uint32_t bhi = 0x7FF00000u, blo = 0u, bk = OM_KEY_SENTINEL;
       int bid = -1;
@@ -1555,15 +1551,15 @@ struct Sim {
       OM_CONV();
       if (__builtin_expect(is_tick, 0)) { tick_block(); OM_CONV(); continue; }   // 15 % of the pops: keep its 12 KB out of the main path
 
-      inl = now > 0.0;                       // URGENT successors run inline
-      chain = unique && inl;                 // same-time NORMAL successors run inline
-      i = id;
-      rel_u = -1;                            // Release created in this chain, not yet popped (kept in registers)
+      const bool inl = now > 0.0;            // URGENT successors run inline
+      const bool chain = unique && inl;      // same-time NORMAL successors run inline
+      int i = id;
+      int rel_u = -1;                        // Release created in this chain, not yet popped (kept in registers)
       ordw_ready = false;
-      rel_key = 0;
-      kind = 0; u = 0;
-      ph0 = 0;
-      dead = false; dump = false;
+      uint32_t rel_key = 0;
+      int kind = 0, u = 0;
+      uint32_t ph0 = 0;
+      bool dead = false, dump = false;
       if (id >= T) {
         // Release event popped: Resource._trigger_put hands the unit to the queue head
         u = id - T;
@@ -1581,17 +1577,21 @@ struct Sim {
         case PH_MOVE_ARRIVE: goto L_ARRIVE;
         case PH_LOAD_DONE: case PH_DUMP_DONE: goto L_SVC_DONE;
         case PH_MOVE_RET: goto L_MOVE_RET;
-        // `u` (the truck's unit) is in a register on every fused path into the labels below; only these entries load it
-        case PH_LOAD_GRANTED: case PH_DUMP_GRANTED: u = U16A(t_unit, i); goto L_GRANTED;
-        case PH_LOAD_BEGIN: case PH_DUMP_BEGIN: u = U16A(t_unit, i); goto L_BEGIN;
-        case PH_LOAD_RET: case PH_DUMP_RET: u = U16A(t_unit, i); goto L_SVC_RET;
-        case PH_MOVE_BEGIN: goto L_MOVE_BEGIN;
+        // CARRY kernels: `u` (the truck's unit), `rngw` and `distw` are in registers on every fused path into the labels
+        // below; only the entries through the event loop load them
+        case PH_LOAD_GRANTED: case PH_DUMP_GRANTED: if (CARRY) u = U16A(t_unit, i); goto L_GRANTED;
+        case PH_LOAD_BEGIN: case PH_DUMP_BEGIN: if (CARRY) u = U16A(t_unit, i); goto L_BEGIN;
+        case PH_LOAD_RET: case PH_DUMP_RET:
+          if (CARRY) { u = U16A(t_unit, i); if (RNG == OM_RNG_PHILOX) rngw = U32A(t_rng, i); }
+          goto L_SVC_RET;
+        case PH_MOVE_BEGIN: if (CARRY) load_move_carry(i); goto L_MOVE_BEGIN;
         case PH_RUN_INIT:                                              // truck.py:296-302
           U8A(t_cur, i) = 0;
           U8A(t_status, i) = ST_WAIT_INIT;
           kind = OM_ORDER_INIT;
           goto L_ORDER;
         case PH_MOVE_REPAIRED:
+          if (CARRY) load_move_carry(i);
           repair_clear(i);
           U8A(t_status, i) = ST_MOVING;
           goto L_DEPART;
@@ -1603,7 +1603,6 @@ struct Sim {
         default:
           if (ph0 >= PH_CRASH_BASE) fail(ph0 - PH_CRASH_BASE);           // the failed Process event pops: env.step() raises
           continue;
-      }
       }
 
       // ================= chain 1: ARRIVE -> RET -> (grant) -> GRANTED -> BEGIN =================
@@ -1645,6 +1644,7 @@ struct Sim {
     }
     L_GRANTED:                                                         // truck.py:342-350 / 422-429
       OM_CONV();
+      if (!CARRY) u = U16A(t_unit, i);
       dump = u >= S;
       if (!dump) rl_close(acc_wait, i);
       if (RL) F64(t_since, i) = now;
@@ -1655,6 +1655,7 @@ struct Sim {
         continue;
       }
     L_BEGIN: {                                                         // truck.py:221-228 / 238-242
+      if (!CARRY) u = U16A(t_unit, i);
       dump = u >= S;
       U8A(t_status, i) = dump ? ST_UNLOADING : ST_LOADING;
       F64(u_last_start, u) = now;
@@ -1684,6 +1685,7 @@ struct Sim {
           jit = -0.1 + 0.2 * (double)om_u01(r.x);
           tape_put(OM_S_LOAD_JITTER, jit);
           U32A(t_rng, i) = r.y;
+          rngw = r.y;
         } else {
           jit = draw_jitter(U16A(t_epoch, i), (uint32_t)i);
         }
@@ -1704,13 +1706,14 @@ struct Sim {
       seq++;                                                           // Process(load/unload) event
     }
     L_SVC_RET:                                                         // truck.py:352-370 / 431-441
+      if (!CARRY) u = U16A(t_unit, i);
       dump = u >= S;
       if (dump) {
         rl_close(acc_dumper, i);
       } else {
         rl_close(acc_shovel, i);
         if (RNG != OM_RNG_DET) {
-          double gap = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(U32A(t_rng, i)) * c.maint_mean
+          double gap = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(CARRY ? rngw : U32A(t_rng, i)) * c.maint_mean
                                               : draw_exp(OM_S_MAINT_GAP, U16A(t_epoch, i), (uint32_t)i, c.maint_mean);
           if (RNG == OM_RNG_PHILOX) tape_put(OM_S_MAINT_GAP, gap);
           if (__builtin_expect(now >= F64(u_lastbrk, u) + gap, 0)) { shovel_maintenance(i, u); continue; }
@@ -1741,7 +1744,7 @@ struct Sim {
       F64(t_jstart, i) = now;
       dead = false;
       if (RNG != OM_RNG_DET) {
-        double g = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(U32A(t_rng, i)) * c.unrepairable_mean
+        double g = (RNG == OM_RNG_PHILOX) ? (double)om_exp1(CARRY ? rngw : U32A(t_rng, i)) * c.unrepairable_mean
                                           : draw_exp(OM_S_UNREPAIRABLE, U16A(t_epoch, i), (uint32_t)i, c.unrepairable_mean);
         if (RNG == OM_RNG_PHILOX) tape_put(OM_S_UNREPAIRABLE, g);
         dead = now >= g;                                               // check_vehicle_availability, truck.py:538-547
@@ -1948,7 +1951,6 @@ struct Sim {
       return;
     }
     int pt = h->pending_truck, pk = h->pending_kind;
-    int resume = -1;
     if (pt >= 0) {
       // the agent's action arrives: RLDispatcher._step returns, truck.py:303-317 / 390-402 / 442-453 continue
       int a = io.actions ? io.actions[inst] : 0;
@@ -1958,16 +1960,14 @@ struct Sim {
         sched_truck(pt, now, OM_KEY_NORMAL, (uint8_t)(PH_CRASH_BASE + OM_IERR_BAD_ORDER));
       } else {
         apply_order(pt, pk, a);
-        if (now > 0.0) resume = pt;                     // Initialize(move), URGENT: the very next pop (see run())
-        else set_entry(pt, now, seq, PH_MOVE_BEGIN);    // t = 0: the other trucks' Initialize(run) entries come first
+        set_entry(pt, now, seq, PH_MOVE_BEGIN);   // Initialize(move), URGENT
         seq++;
       }
       h->pending_truck = -1; h->pending_kind = -1;
     }
     bool fresh = false;       // true once this call has auto-reset the env: the finished episode's outputs stay
   L_RUN:
-    run(p.until, resume);
-    resume = -1;
+    run(p.until);
     pt = h->pending_truck; pk = h->pending_kind;
     const bool failed = (err != OM_IERR_NONE && err != OM_IERR_TRACE_OVERFLOW);
     float* ob = io.obs + (size_t)inst * p.obs_dim;

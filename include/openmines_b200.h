@@ -236,7 +236,7 @@ typedef struct OmStateLayout {
   uint32_t e_stride;           /* pending-entry size in bytes */
   uint32_t hot_bytes;          /* prefix of the blob the kernels stage in shared memory (== total_bytes unless split) */
   uint32_t hdr_bytes;          /* bytes of the per-instance header present in the blob */
-  uint32_t slot_cache;         /* kernel-internal cache (16 B per 32 trucks); contents are meaningless between calls */
+  uint32_t slot_cache;         /* split layouts only (0 otherwise): kernel-internal cache (16 B per 32 trucks); contents are meaningless between calls */
   uint32_t t_aux, r_jamcnt;    /* split layouts only (0 otherwise): t_aux {unit, next, epoch, service count} u16[4] per truck in the hot
                                   part -- t_unit / t_next / t_epoch / t_svc then point here (stride 8); r_jamcnt u16 [R] stored jams per road */
   uint32_t t_loc, t_lastbrk_hot; /* split layouts only (0 otherwise): {status, cur, tgt, flags} u8[4] per truck (flags bit 0: a repair
@@ -304,8 +304,10 @@ int om_stats_reduce(OmHandle h, const OmSummary* summary, const int32_t* dispatc
                                    dense reward of Mine.start_rl (mine.py:456-459) with last_production never updated */
 
 /* Batched gym-style step (replaces RLDispatcher._step + Mine.start_rl + preprocess_observation:
- * rl_dispatch.py:58-123,194-509, mine.py:397-476, utils/feature_processing.py:3-75).  Instances reset with
- * OM_DISP_EXTERNAL pause at every dispatch decision.  One call = apply `actions[n]` to instance n's pending
+ * rl_dispatch.py:58-123,194-509, mine.py:397-476, utils/feature_processing.py:3-75).  Under om_step EVERY instance
+ * pauses at every dispatch decision and is driven by `actions` -- reset them with OM_DISP_EXTERNAL; an instance reset
+ * with a device dispatcher id is treated the same (the device dispatchers run in om_run and, as the teacher, in
+ * om_step's sug_action).  One call = apply `actions[n]` to instance n's pending
  * order (ignored when none is pending: first call after om_reset), advance to the next decision point (or to
  * `until`), and emit that decision's observation / the reward of the previous decision.  All device pointers;
  * obs rows are written only when a new decision is pending (on the final step the reference re-sends the

@@ -18,7 +18,8 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC",
+              "-diag-suppress", "128"]   # "loop is not reachable": the OM_CONV() probe stub behind a compile-time-certain break
 
 _lib = None
 
@@ -81,8 +82,10 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("openmines_b200: %s is missing -- build it first (__graft_entry__.build()); "
                            "the engine has no CPU fallback" % LIB_PATH)
-    if needs_build():
-        # a stale binary with changed struct layouts would corrupt memory silently
+    if needs_build() and not os.environ.get("OM_LIB_PATH"):
+        # a stale binary with changed struct layouts would corrupt memory silently.  (An explicit OM_LIB_PATH names a
+        # variant build for an A/B measurement -- tools/build_variant.sh -- and is loaded as it is: rebuilding it from the
+        # tree's sources would silently turn it into a copy of the default build; the ABI check below still applies.)
         import shutil
         if shutil.which(os.environ.get("NVCC", "nvcc")) is None:
             raise RuntimeError("openmines_b200: %s is older than its sources and nvcc is not available to rebuild it"

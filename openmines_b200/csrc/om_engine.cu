@@ -438,7 +438,7 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl, bool split
   if (nscr < 32) nscr = 32;
   ly.scratch = take(off, 8, nscr);
   // per-slot minima of the truck entries, used by the SPLIT kernels (valid within one kernel invocation only)
-  ly.slot_cache = take(off, 16, (T + 31) / 32);
+  if (split) ly.slot_cache = take(off, 16, (T + 31) / 32);   // (0 in unsplit layouts: their kernels scan the entries directly)
   ly.u_rel_key = take(off, 4, U);
   ly.s_qtotal = take(off, 2, NS); ly.s_coming = take(off, 2, NS);
   if (split) {   // shared-memory helpers that keep the per-minute / per-departure scans of a big mine out of HBM

@@ -374,7 +374,7 @@ struct Sim {
 #define OM_B_s_tons c.NS
 #define OM_B_s_cap c.NS
 #define OM_B_s_ability c.NS
-#define OM_B_scratch ((ly.slot_cache - ly.scratch) / 8u)
+#define OM_B_scratch (((ly.slot_cache ? ly.slot_cache : ly.u_rel_key) - ly.scratch) / 8u)
 #ifdef OM_BOUNDS_CHECK
 #define OM_IDX(field, i) om_chk((long long)(i), (long long)(OM_B_##field), __LINE__, dbg_viol)
 #else
@@ -1726,7 +1726,10 @@ struct Sim {
       U8A(t_status, i) = dump ? ST_WAIT_BACK : ST_WAIT_HAUL;
       kind = dump ? OM_ORDER_BACK : OM_ORDER_HAUL;
     L_ORDER: {                                                         // dispatcher.py:35-89 + truck.py:303-317,389-402,441-453
-      if (__builtin_expect(disp == OM_DISP_EXTERNAL, 0)) { pause_for_order(i, kind, rel_u, rel_key, pend_truck, pend_kind); break; }
+      // om_step (the RL kernels) drives EVERY instance by actions: the dispatcher id an instance was reset with plays no
+      // part there, and the device dispatchers below are not compiled into those kernels' event loop -- the teacher's
+      // decide() in rl_step() is their only copy (5936 -> 4952 SASS instructions; +2 % env steps per second)
+      if (RL || __builtin_expect(disp == OM_DISP_EXTERNAL, 0)) { pause_for_order(i, kind, rel_u, rel_key, pend_truck, pend_kind); break; }
       OM_CONV();
       int site = decide(kind, i);
       OM_CONV();
@@ -1975,10 +1978,17 @@ struct Sim {
       double delta_time = now - rl_last;
       int pair_cnt, on_cnt;
       double capsum;
+#ifdef OM_STEP_NO_OBS   /* measurement aid: the DES part of an env step alone (outputs are meaningless) */
+      pair_cnt = on_cnt = 0; capsum = 0.0;
+      double reward = 0.0;
+      int sug = -1;
+      if (false) {
+#else
       rl_observation(pt, pk, ob, (io.flags & OM_STEP_WRITE_STATIC) != 0, pair_cnt, on_cnt, capsum);
       double reward = rl_reward(false, (io.flags & OM_STEP_SPARSE_REWARD) != 0);
       int sug = -1;
       if (io.teacher >= 0 && io.teacher != OM_DISP_RANDOM) {
+#endif
         int saved_disp = disp;
         uint32_t saved_err = err;
         disp = io.teacher;

@@ -39,8 +39,12 @@ def _spaces(n_actions, obs_dim):
 
 class BatchedMineEnv:
     def __init__(self, config, num_envs, device=0, rng_mode="philox", sug_dispatcher="ShortestTripDispatcher",
-                 auto_reset=False, jam_capacity=64, reward_mode="dense", copy_outputs=False):
-        """``copy_outputs``: ``reset()`` / ``step()`` return the engine's OWN output buffers (``env.io[...]``), which the next
+                 auto_reset=False, jam_capacity=56, reward_mode="dense", copy_outputs=False):
+        """``jam_capacity``: stored road jams per env.  56 (a pool of 48 never overflowed in 49152 live north_pit episodes, DESIGN.md
+        section 2) instead of the episode runs' 64: with the RL surface's bigger state that is what lets 18 instead of 17 envs share an SM's
+        shared memory.  An env whose pool overflows ends its episode with ``OM_IERR_JAM_OVERFLOW``.
+
+        ``copy_outputs``: ``reset()`` / ``step()`` return the engine's OWN output buffers (``env.io[...]``), which the next
         ``step()`` overwrites in place -- zero-copy, what a fused rollout loop wants, but a trainer that stores the returned
         ``obs`` / ``reward`` / ``terminated`` / ``info`` tensors in a rollout buffer without ``.clone()`` would see every
         stored step turn into the latest one.  ``copy_outputs=True`` returns fresh tensors every call instead (one extra

@@ -253,3 +253,31 @@ def test_stats_are_exact_and_order_independent(north_pit):
         fwd = fwd + p
     tree = ((parts[7] + parts[3]) + (parts[5] + parts[1])) + ((parts[6] + parts[2]) + (parts[4] + parts[0]))
     assert np.array_equal(fwd, got) and np.array_equal(tree, got)
+
+
+def test_split_layout_hot_truck_arrays_and_its_limit(north_pit, monkeypatch):
+    """Split layouts keep a truck's unit / queue link / order epoch / service count in a hot 8-byte record, the minute of
+    its last breakdown as a uint16 and a pending-repair flag: after the replay of a live reference tape (breakdowns, repairs,
+    jams) the decoded state must equal the unsplit layout's field by field, and a clock beyond what a uint16 minute holds is
+    refused, not wrapped.  (Replay, not Philox: the two kernels pick the truck a jam position is drawn around from
+    differently ordered lists, so their live trajectories are different samples of the same law.)"""
+    g = Golden("live_north_pit_mine_SQDispatcher_s11")
+    outs = []
+    for split in ("0", "1"):
+        monkeypatch.setenv("OM_SPLIT", split)
+        mine = _mine(north_pit, 2)
+        assert bool(mine.layout.t_aux) == (split == "1") and bool(mine.layout.t_lastbrk_hot) == (split == "1")
+        assert bool(mine.layout.slot_cache) == (split == "1")
+        mine.reset("SQDispatcher", rng_mode="tape", tapes=[g.tape, g.tape])
+        s = mine.run(until=200.0).summary_np().copy()          # stop mid-episode: queues, moves and repairs under way
+        outs.append((s, [mine.state_arrays(i) for i in range(2)]))
+        if split == "1":
+            with pytest.raises(RuntimeError, match="65535"):
+                mine.run(until=70000.0)
+    assert np.array_equal(outs[0][0], outs[1][0]) and (outs[0][0]["err"] == 0).all()
+    assert outs[0][0]["n_truck_repairs"].sum() > 0            # breakdowns happened: t_lastbrk / t_repair were exercised
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert (a["t_lastbrk"] > 0).any() and (a["t_unit"] != 0xFFFF).any()
+        for f in ("t_unit", "t_next", "t_epoch", "t_svc", "t_lastbrk", "t_repair", "t_status", "t_cur", "t_tgt", "t_total",
+                  "t_cycle", "t_dist", "t_load", "t_time", "t_key", "u_tons", "u_qlen", "u_head", "u_tail"):
+            assert np.array_equal(a[f], b[f]), f

@@ -62,9 +62,13 @@ def _compare(log, ref_obs, ref_reward, ref_kind, ref_sug, ref_done, ref_action):
         assert abs(rec["reward"] - ref_reward[k]) <= 1e-9 * max(1.0, abs(ref_reward[k])), (k, rec["reward"], ref_reward[k])
 
 
-def test_rl_step_vs_reference_goldens(north_pit):
-    """det + tape replays of the reference's own RL loop (ShortestTrip and SQ teachers; dense and sparse reward modes)."""
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_rl_step_vs_reference_goldens(north_pit, monkeypatch, split):
+    """det + tape replays of the reference's own RL loop (ShortestTrip and SQ teachers; dense and sparse reward modes), on
+    the unsplit layout and on a forced split layout (the big-mine step kernels: hot truck arrays, uint16 breakdown minutes,
+    pending-repair flag, register-carried chain values)."""
     import openmines_b200 as om
+    monkeypatch.setenv("OM_SPLIT", split)
     from openmines_b200.rl_env import BatchedMineEnv
     from oracle import rl_oracle as ro
     names = ["rl_north_pit_mine_det_s0_ShortestTripDispatcher_p1", "rl_north_pit_mine_live_s21_ShortestTripDispatcher_p2",
@@ -74,7 +78,7 @@ def test_rl_step_vs_reference_goldens(north_pit):
         mode = "det" if str(z["mode"]) == "det" else "tape"
         env = BatchedMineEnv(north_pit, 1, rng_mode=mode, sug_dispatcher=str(z["teacher"]),
                              reward_mode="sparse" if name.endswith("_sparse") else "dense")
-        assert env.obs_dim == 194
+        assert env.obs_dim == 194 and bool(env.mine.layout.t_aux) == (split == "1")
         pol = {"fn": ro.keyed_policy(int(z["policy_seed"])), "seed": int(z["seed"]),
                "tape": (z["tape_sites"], z["tape_values"])}
         logs = _drive(env, [pol])

@@ -226,11 +226,11 @@ typedef struct OmStateLayout {
   uint32_t u_user, u_head, u_tail, u_qlen;                                                   /* u16 */
   uint32_t u_repair;                                                                         /* u8  */
   uint32_t r_repair_end;                                                                     /* f64 */
-  uint32_t j_pos, j_start, j_end;                                                            /* f64 [jam_capacity] */
+  uint32_t j_pos, j_start, j_end;                                                            /* f64 [jam_capacity]; j_start: uint16 minute */
   uint32_t j_road;                                                                           /* u16 [jam_capacity] */
   uint32_t s_qtotal, s_coming;                                                               /* u16 [L+D] */
-  uint32_t s_tons, s_cap, s_ability;                                                         /* f64 [L+D] minute-sampled */
-  uint32_t scratch;                                                                          /* f64 [max(U, 32)] */
+  uint32_t s_tons, s_cap, s_ability;                                                         /* f32 [L+D] minute-sampled: log(tons + 1), log(capacity + 1), ability ratio */
+  uint32_t scratch;                                                                          /* f64 [max(S, M, R/2 + 1, 32)] kernel scratch */
   uint32_t t_rec, u_rec;       /* start of the truck / unit record arrays */
   uint32_t t_stride, u_stride; /* record sizes in bytes */
   uint32_t e_stride;           /* pending-entry size in bytes */

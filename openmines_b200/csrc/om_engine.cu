@@ -431,9 +431,10 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl, bool split
   ly.u_qlen = ly.u_rec + 34; ly.u_repair = ly.u_rec + 36;
   ly.u_lastbrk = take(off, 8, c.S);
   ly.r_repair_end = take(off, 8, R);
-  if (rl) { ly.s_tons = take(off, 8, NS); ly.s_cap = take(off, 8, NS); ly.s_ability = take(off, 8, NS); }
-  // scratch: unit_est_all() results (both sides live at once only for the RL observation) or per-road counters (u32)
-  size_t nscr = rl ? U : ((size_t)c.S > (size_t)c.M ? (size_t)c.S : (size_t)c.M);
+  if (rl) { ly.s_tons = take(off, 4, NS); ly.s_cap = take(off, 4, NS); ly.s_ability = take(off, 4, NS); }   // float32
+  // scratch: unit_est_all() results of ONE side (dumpers share the shovels' slots) or per-road counters (u32)
+  (void)U;
+  size_t nscr = ((size_t)c.S > (size_t)c.M ? (size_t)c.S : (size_t)c.M);
   if (nscr < (R + 1) / 2) nscr = (R + 1) / 2;
   if (nscr < 32) nscr = 32;
   ly.scratch = take(off, 8, nscr);
@@ -465,7 +466,7 @@ static void build_layout(const DevCfg& c, OmStateLayout& ly, bool rl, bool split
   }
   if (rl) ly.t_since = take(off, 8, T);
   ly.j_pos = take(off, 8, J); ly.j_end = take(off, 8, J);
-  if (rl) ly.j_start = take(off, 8, J);
+  if (rl) ly.j_start = take(off, 2, J);   // uint16: the minute the jam was created at
   ly.j_road = take(off, 2, J);
   ly.total_bytes = (off + 15u) & ~15u;
 }
@@ -856,7 +857,7 @@ int om_step(OmHandle h, double until, void* state, const OmStepIO* io, void* str
   if (!h->rl) return set_err(h, OM_E_INVALID, "om_step: the handle was created without OM_CFG_RL_SURFACE (OmConfig.flags)");
   if (h->multi) return set_err(h, OM_E_UNSUPPORTED, "om_step: not available on a mixed-config handle");
   if (((uintptr_t)state & 15u) != 0) return set_err(h, OM_E_INVALID, "om_step: state must be 16-byte aligned (TMA bulk copies)");
-  if (h->split && !(until <= 65535.0)) return set_err(h, OM_E_UNSUPPORTED, "om_step: split layouts (big mines) hold breakdown minutes as uint16: until <= 65535");
+  if (!(until <= 65535.0)) return set_err(h, OM_E_UNSUPPORTED, "om_step: the RL surface holds jam start minutes as uint16: until <= 65535");
   CK(cudaSetDevice(h->device));
   RunParams p;
   memset(&p, 0, sizeof(p));

@@ -381,6 +381,7 @@ struct Sim {
 #define OM_IDX(field, i) (i)
 #endif
 #define F64(field, i) OM_A_##field(double, OM_IDX(field, i))
+#define F32A(field, i) OM_A_##field(float, OM_IDX(field, i))
 #define U32A(field, i) OM_A_##field(uint32_t, OM_IDX(field, i))
 #define U16A(field, i) OM_A_##field(uint16_t, OM_IDX(field, i))
 #define U8A(field, i) OM_A_##field(uint8_t, OM_IDX(field, i))
@@ -573,6 +574,11 @@ struct Sim {
     F64(t_repair, i) = 0.0;
     if (SPLIT) U8A(t_flags, i) = (uint8_t)(U8A(t_flags, i) & 0xFEu);
   }
+  // RL surface: start time of a stored jam (the reward integrates jam minutes over its window, rl_dispatch.py:258-273).
+  // Jams are only ever created by the monitor block, i.e. at an integer minute: a uint16 per jam (om_step refuses until > 65535).
+  __device__ __forceinline__ double jstart_get(uint32_t j) { return (double)U16A(j_start, j); }
+  __device__ __forceinline__ void jstart_set(uint32_t j, double t) { U16A(j_start, j) = (uint16_t)(int)t; }
+
   // FIFO of waiting trucks per unit (simpy Resource.put_queue), linked through t_next
   __device__ __forceinline__ void q_push(int u, int i) {
     uint32_t n = U16A(u_qlen, u);
@@ -669,8 +675,9 @@ struct Sim {
   // site minima with site_est().
   __device__ __forceinline__ void unit_est_all(bool load_side) {
     int ub = load_side ? 0 : c.S, ue = load_side ? c.S : c.U;
-    // without the RL surface only one side's estimates are live at a time: dumpers share the shovels' slots
-    const int sbase = (!RL && !load_side) ? c.S : 0;
+    // only one side's estimates are live at a time (the RL observation reduces each side to per-site minima before it
+    // computes the other): dumpers share the shovels' slots
+    const int sbase = (!load_side) ? c.S : 0;
     #pragma unroll 1
     for (int u = ub + lane; u < ue; u += 32) {
       double est;
@@ -704,7 +711,7 @@ struct Sim {
   // min over the site's units (call after unit_est_all); lane-local loop
   __device__ __forceinline__ double site_est(int site) {
     int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
-    const int sbase = (!RL && site >= c.L) ? c.S : 0;
+    const int sbase = (site >= c.L) ? c.S : 0;
     double m = F64(scratch, ub - sbase);
     #pragma unroll 1
     for (int u = ub + 1; u < ue; ++u) {
@@ -766,11 +773,11 @@ struct Sim {
   // ---------------------------------------------------------------------------------------------
   // Every helper below (unit_est_all, site_est, road_load, argmin_lanes) has ONE call site: they are force-inlined,
   // and duplicated copies of them used to make this function 14 KB of SASS in the middle of the hot order chain.
-  // `est_ready`: both sides' wait estimates are in scratch already; `shared_on` / `shared_cap` (lane q = candidate q): the
+  // `est_ready`: lane s of `est_all` holds site s's estimated queue wait already; `shared_on` / `shared_cap` (lane q = candidate q): the
   // moving trucks / their capacity sum on the roads from the truck's CURRENT location, as the RL observation just counted
   // them -- the ShortestTrip teacher looks at the same roads for haul and init orders (have_shared).
   __device__ __forceinline__ int decide(int kind, int i, bool est_ready = false, bool have_shared = false, int shared_on = 0,
-                                        double shared_cap = 0.0) {
+                                        double shared_cap = 0.0, double est_all = 0.0) {
     int r = 0;
     const int L = c.L, D = c.D;
     const bool haul = kind == OM_ORDER_HAUL;
@@ -781,8 +788,13 @@ struct Sim {
     double wait = 0.0;                          // lane q < n: estimated_queue_wait_time of candidate q
     if (est) {
       // dispatcher.update_mine (dispatcher.py:24-33) for the side that matters; the RL step has both sides in scratch already
-      if (!est_ready) unit_est_all(!haul);
-      if (lane < n) wait = site_est(sbase_site + lane);
+      if (est_ready) {                            // lane s of est_all = estimated_queue_wait_time of site s (rl_observation)
+        const double w = __shfl_sync(OM_FULL, est_all, (lane < n) ? sbase_site + lane : 0);
+        if (lane < n) wait = w;
+      } else {
+        unit_est_all(!haul);
+        if (lane < n) wait = site_est(sbase_site + lane);
+      }
     }
     switch (disp) {
       case OM_DISP_NAIVE:
@@ -1029,12 +1041,12 @@ struct Sim {
       #pragma unroll 1
       for (uint32_t j = 0; j < jam_count; ++j) {
         if (RL && !(F64(j_end, j) >= now)) {
-          double st = F64(j_start, j), lo = (st > rl_last) ? st : rl_last;
+          double st = jstart_get(j), lo = (st > rl_last) ? st : rl_last;
           if (lo < F64(j_end, j)) acc_jam += F64(j_end, j) - lo;
         }
         if (F64(j_end, j) >= now) {
           if (w != j) {
-            F64(j_pos, w) = F64(j_pos, j); if (RL) F64(j_start, w) = F64(j_start, j);
+            F64(j_pos, w) = F64(j_pos, j); if (RL) U16A(j_start, w) = U16A(j_start, j);
             F64(j_end, w) = F64(j_end, j); U16A(j_road, w) = U16A(j_road, j);
           }
           if (SPLIT) rjc[U16A(j_road, w)] = (uint16_t)(rjc[U16A(j_road, w)] + 1);
@@ -1044,7 +1056,7 @@ struct Sim {
       jam_count = w;
     }
     if (jam_count == (uint32_t)c.J) { fail(OM_IERR_JAM_OVERFLOW); return; }
-    F64(j_pos, jam_count) = pos; if (RL) F64(j_start, jam_count) = now; F64(j_end, jam_count) = end;
+    F64(j_pos, jam_count) = pos; if (RL) jstart_set(jam_count, now); F64(j_end, jam_count) = end;
     U16A(j_road, jam_count) = (uint16_t)rid;
     if (SPLIT) rjc[rid] = (uint16_t)(rjc[rid] + 1);
     jam_count++;
@@ -1063,7 +1075,7 @@ struct Sim {
       const bool valid = j < jam_count;
       double en = 0.0, pos = 0.0, st = 0.0;
       uint32_t rd = 0;
-      if (valid) { en = F64(j_end, j); pos = F64(j_pos, j); rd = U16A(j_road, j); if (RL) st = F64(j_start, j); }
+      if (valid) { en = F64(j_end, j); pos = F64(j_pos, j); rd = U16A(j_road, j); if (RL) st = jstart_get(j); }
       const bool keep = valid && en >= now;
       if (RL && valid && !keep) {
         const double lo = (st > rl_last) ? st : rl_last;
@@ -1074,7 +1086,7 @@ struct Sim {
       const uint32_t dst = w + (uint32_t)__popc(m & ((1u << lane) - 1u));
       __syncwarp();                                    // the chunk is in registers before any lane overwrites part of it
       if (keep) {
-        F64(j_end, dst) = en; F64(j_pos, dst) = pos; U16A(j_road, dst) = (uint16_t)rd; if (RL) F64(j_start, dst) = st;
+        F64(j_end, dst) = en; F64(j_pos, dst) = pos; U16A(j_road, dst) = (uint16_t)rd; if (RL) jstart_set(dst, st);
       }
       w += (uint32_t)__popc(m);
       {
@@ -1118,7 +1130,8 @@ struct Sim {
       site_tons = ps.result(neu);
       U16A(s_qtotal, lane) = (uint16_t)qtot;
       if (RL) {
-        // minute-sampled values the observation reads (load_site.py:175-185, dump_site.py:69-78).  They change once per
+        // minute-sampled values the observation reads (load_site.py:175-185, dump_site.py:69-78), held as float32 (what
+        // the observation is).  They change once per
         // minute but are observed at every decision, so the observation's log(x + 1) of them is taken here, once:
         // s_tons <- log(site tons + 1), s_cap <- log(capacity + 1), s_ability <- service ability ratio.
         if (lane < L) {
@@ -1126,13 +1139,13 @@ struct Sim {
 #pragma unroll 1
           for (int u = ub; u < ue; ++u) pa.add(__ldg(&c.shovel_rate[u]) * (U8A(u_repair, u) ? 0.0 : 1.0), neu);
           rl_cap = __ldg(&c.site_prod[lane]);
-          F64(s_ability, lane) = pa.result(neu) * __ldg(&c.inv_prod[lane]);
+          F32A(s_ability, lane) = (float)(pa.result(neu) * __ldg(&c.inv_prod[lane]));
         } else {
           PySum pd; pd.init();
 #pragma unroll 1
           for (int u = ub; u < ue; ++u) pd.add(F64(u_tons, u) * __ldg(&c.inv_dcycle[u - c.S]), neu);
           rl_cap = pd.result(neu);
-          F64(s_ability, lane) = 1.0;
+          F32A(s_ability, lane) = 1.0f;
         }
       }
     }
@@ -1141,7 +1154,7 @@ struct Sim {
 #pragma unroll 1
       for (int w = 0; w < 2; ++w) {
         const double v = om_dlog(((w == 0) ? rl_cap : site_tons) + 1.0);
-        if (lane < NS) { if (w == 0) F64(s_cap, lane) = v; else F64(s_tons, lane) = v; }
+        if (lane < NS) { if (w == 0) F32A(s_cap, lane) = (float)v; else F32A(s_tons, lane) = (float)v; }
       }
     }
     tick_k = k;
@@ -1820,7 +1833,7 @@ struct Sim {
     }
 #pragma unroll 1
     for (uint32_t j = lane; j < jam_count; j += 32) {
-      double st = F64(j_start, j), en = F64(j_end, j);
+      double st = jstart_get(j), en = F64(j_end, j);
       double lo = (st > rl_last) ? st : rl_last, hi = (en < now) ? en : now;
       if (lo < hi) pen += 0.05 * (hi - lo);
     }
@@ -1846,7 +1859,7 @@ struct Sim {
   // Returns (through the reference parameters) the trucks on the candidate roads from the current location as
   // road_load() found them (lane q = candidate q), for the teacher to reuse when it looks at the same roads.
   __device__ __forceinline__ void rl_observation(int i, int kind, float* ob, bool write_static, int& pair_cnt, int& on_cnt,
-                                                 double& capsum) {
+                                                 double& capsum, double& est_site_out) {
     const int L = c.L, D = c.D, NS = c.NS, R = c.R;
     const int C = L > D ? L : D;
     const int o1 = 6, o2 = o1 + 1 + NS, o3 = o2 + 2, o4 = o3 + C, o5 = o4 + C, o6 = o5 + R, o7 = o6 + R,
@@ -1870,11 +1883,16 @@ struct Sim {
       }
       __syncwarp();
     }
-    // dispatcher.update_mine (dispatcher.py:24-33): both sides' wait estimates (one inlined copy, two trips)
+    // dispatcher.update_mine (dispatcher.py:24-33): both sides' wait estimates (one inlined copy, two trips), each side
+    // reduced to estimated_queue_wait_time per site (lane = site, NS <= 32) before the other side reuses the scratch slots
+    double est_site = 0.0;
 #pragma unroll 1
-    for (int side = 0; side < 2; ++side) unit_est_all(side == 0);
-    // estimated_queue_wait_time of every site, lane = site (NS <= 32)
-    const double est_site = (lane < NS) ? site_est(lane) : 0.0;
+    for (int side = 0; side < 2; ++side) {
+      unit_est_all(side == 0);
+      if (lane < NS && ((lane < L) == (side == 0))) est_site = site_est(lane);
+      __syncwarp();
+    }
+    est_site_out = est_site;
     if (lane == 0) {
       ob[0] = kind == OM_ORDER_INIT ? 1.f : 0.f; ob[1] = kind == OM_ORDER_HAUL ? 1.f : 0.f;
       ob[2] = kind == OM_ORDER_BACK ? 1.f : 0.f;
@@ -1932,9 +1950,9 @@ struct Sim {
 #pragma unroll 1
     for (int s2 = lane; s2 < NS; s2 += 32) {
       ob[o9 + s2] = (float)((double)U16A(s_qtotal, s2) * c.inv_tn);
-      ob[o10 + s2] = (float)F64(s_cap, s2);
-      ob[o11 + s2] = (float)F64(s_ability, s2);
-      ob[o12 + s2] = (float)F64(s_tons, s2);
+      ob[o10 + s2] = F32A(s_cap, s2);            // float32 already (the observation is all they feed)
+      ob[o11 + s2] = F32A(s_ability, s2);
+      ob[o12 + s2] = F32A(s_tons, s2);
     }
     __syncwarp();
   }
@@ -1980,11 +1998,13 @@ struct Sim {
       double capsum;
 #ifdef OM_STEP_NO_OBS   /* measurement aid: the DES part of an env step alone (outputs are meaningless) */
       pair_cnt = on_cnt = 0; capsum = 0.0;
+      double est_all = 0.0;
       double reward = 0.0;
       int sug = -1;
       if (false) {
 #else
-      rl_observation(pt, pk, ob, (io.flags & OM_STEP_WRITE_STATIC) != 0, pair_cnt, on_cnt, capsum);
+      double est_all;
+      rl_observation(pt, pk, ob, (io.flags & OM_STEP_WRITE_STATIC) != 0, pair_cnt, on_cnt, capsum, est_all);
       double reward = rl_reward(false, (io.flags & OM_STEP_SPARSE_REWARD) != 0);
       int sug = -1;
       if (io.teacher >= 0 && io.teacher != OM_DISP_RANDOM) {
@@ -1992,7 +2012,7 @@ struct Sim {
         int saved_disp = disp;
         uint32_t saved_err = err;
         disp = io.teacher;
-        sug = decide(pk, pt, true, true, on_cnt, capsum);   // rl_observation() left both sides' wait estimates in scratch
+        sug = decide(pk, pt, true, true, on_cnt, capsum, est_all);   // rl_observation() computed every site's wait estimate
         if (sug < 0) sug = -1;                       // the teacher raised (e.g. SQ before its minute's sample)
         disp = saved_disp; err = saved_err;
       }

@@ -39,10 +39,10 @@ def _spaces(n_actions, obs_dim):
 
 class BatchedMineEnv:
     def __init__(self, config, num_envs, device=0, rng_mode="philox", sug_dispatcher="ShortestTripDispatcher",
-                 auto_reset=False, jam_capacity=56, reward_mode="dense", copy_outputs=False):
-        """``jam_capacity``: stored road jams per env.  56 (a pool of 48 never overflowed in 49152 live north_pit episodes, DESIGN.md
-        section 2) instead of the episode runs' 64: with the RL surface's bigger state that is what lets 18 instead of 17 envs share an SM's
-        shared memory.  An env whose pool overflows ends its episode with ``OM_IERR_JAM_OVERFLOW``.
+                 auto_reset=False, jam_capacity=52, reward_mode="dense", copy_outputs=False):
+        """``jam_capacity``: stored road jams per env.  52 (a pool of 48 never overflowed in 49152 live north_pit episodes, DESIGN.md
+        section 2) instead of the episode runs' 64: with the RL surface's bigger state that is what lets 19 instead of 17 envs share an SM's
+        shared memory (12192 bytes per env).  An env whose pool overflows ends its episode with ``OM_IERR_JAM_OVERFLOW``.
 
         ``copy_outputs``: ``reset()`` / ``step()`` return the engine's OWN output buffers (``env.io[...]``), which the next
         ``step()`` overwrites in place -- zero-copy, what a fused rollout loop wants, but a trainer that stores the returned

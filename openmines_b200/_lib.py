@@ -19,7 +19,10 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC",
-              "-diag-suppress", "128"]   # "loop is not reachable": the OM_CONV() probe stub behind a compile-time-certain break
+              "-diag-suppress", "128",   # "loop is not reachable": the OM_CONV() probe stub behind a compile-time-certain break
+              # immediates stay in the instructions instead of a compiler-made constant bank (measured, same-call A/B:
+              # -0.6 % on the north_pit episode kernel, -1.9 % on the split kernel)
+              "-Xptxas", "--disable-optimizer-constants"]
 
 _lib = None
 

@@ -171,6 +171,10 @@ struct RunParams {
   double seg_tail;     // every segment after the first covers this fraction of the episode (the last one sets the tail)
 };
 
+// Identity the optimiser cannot see through: a chain of `if (om_opaque(x) == K)` stays a chain of compares and branches
+// (the compiler otherwise folds compares of one value back into a switch and lowers that to an indirect branch, BRX).
+__device__ __forceinline__ uint32_t om_opaque(uint32_t v) { asm volatile("" : "+r"(v)); return v; }   // volatile: two of them are not merged
+
 __device__ __forceinline__ double om_inf() { return __longlong_as_double(0x7FF0000000000000LL); }
 
 // bounds-check build: {violations, source line of the first, its index, the extent, warp-convergence probes that saw a
@@ -796,25 +800,33 @@ struct Sim {
         if (lane < n) wait = site_est(sbase_site + lane);
       }
     }
-    switch (disp) {
-      case OM_DISP_NAIVE:
-        r = 0;
-        break;
-      case OM_DISP_RANDOM: {
-        // haul draws over len(load_sites), back over len(dump_sites)  (random_dispatcher.py:21-29)
-        r = draw_randint(U16A(t_epoch, i), (uint32_t)i, (kind == OM_ORDER_BACK) ? D : L);
+    // Dispatch on the dispatcher id as a chain of compares, the two dispatchers of the headline workload first: a
+    // `switch` over seven ids compiles to an indirect branch (BRX), which stalls instruction fetch until it resolves
+    // (same-call A/B on the C3 shard).  OM_X_SWITCH_DISP restores the switch for measurements.
+#ifdef OM_X_SWITCH_DISP
+#define OM_DISPATCH_BEGIN switch (disp) {
+#define OM_DISPATCH_CASE(x) case x:
+#define OM_DISPATCH_END(e) default: return (e); }
+#else
+#define OM_DISPATCH_BEGIN do {
+#define OM_DISPATCH_CASE(x) if (om_opaque((uint32_t)disp) == (uint32_t)(x))
+#define OM_DISPATCH_END(e) return (e); } while (0);
+#endif
+    OM_DISPATCH_BEGIN
+      OM_DISPATCH_CASE(OM_DISP_SQ) {
+        // coming trucks + minute-sampled total queue length (sq_dispatcher.py:18-100)
+        int k = (int)now;   // int(env.now)
+        if (k != tick_k) return -OM_IERR_SQ_KEYERROR;   // KeyError: queue_status['total'][int(now)] not sampled yet
+        uint32_t v = 0xFFFFFFFFu;
+        if (lane < n) {
+          int site = sbase_site + lane;
+          uint32_t coming = (uint32_t)U16A(s_coming, site) - ((U8A(t_tgt, i) == 1 + site) ? 1u : 0u);
+          v = ((coming + (uint32_t)U16A(s_qtotal, site)) << 8) | (uint32_t)lane;
+        }
+        r = (int)(__reduce_min_sync(OM_FULL, v) & 0xFFu);
         break;
       }
-      case OM_DISP_NEAREST:
-        if (kind == OM_ORDER_INIT) r = c.nearest_init;
-        else if (haul) r = __ldg(&c.near_haul[U8A(t_cur, i) - 1]);
-        else r = __ldg(&c.near_back[U8A(t_cur, i) - 1 - L]);
-        break;
-      case OM_DISP_FIXEDGROUP:
-        if (haul) r = __ldg(&c.near_haul[U8A(t_cur, i) - 1]);
-        else r = __ldg(&c.fixed_group[i]);
-        break;
-      case OM_DISP_SPTF: {
+      OM_DISPATCH_CASE(OM_DISP_SPTF) {
         if (haul) {
           // len(coming) + estimated_queue_wait_time   (sptf_dispatcher.py:40-57)
           if (lane < D) {
@@ -853,20 +865,27 @@ struct Sim {
         }
         break;
       }
-      case OM_DISP_SQ: {
-        // coming trucks + minute-sampled total queue length (sq_dispatcher.py:18-100)
-        int k = (int)now;   // int(env.now)
-        if (k != tick_k) return -OM_IERR_SQ_KEYERROR;   // KeyError: queue_status['total'][int(now)] not sampled yet
-        uint32_t v = 0xFFFFFFFFu;
-        if (lane < n) {
-          int site = sbase_site + lane;
-          uint32_t coming = (uint32_t)U16A(s_coming, site) - ((U8A(t_tgt, i) == 1 + site) ? 1u : 0u);
-          v = ((coming + (uint32_t)U16A(s_qtotal, site)) << 8) | (uint32_t)lane;
-        }
-        r = (int)(__reduce_min_sync(OM_FULL, v) & 0xFFu);
+      OM_DISPATCH_CASE(OM_DISP_NAIVE) {
+        r = 0;
         break;
       }
-      case OM_DISP_SHORTESTTRIP: {
+      OM_DISPATCH_CASE(OM_DISP_NEAREST) {
+        if (kind == OM_ORDER_INIT) r = c.nearest_init;
+        else if (haul) r = __ldg(&c.near_haul[U8A(t_cur, i) - 1]);
+        else r = __ldg(&c.near_back[U8A(t_cur, i) - 1 - L]);
+        break;
+      }
+      OM_DISPATCH_CASE(OM_DISP_FIXEDGROUP) {
+        if (haul) r = __ldg(&c.near_haul[U8A(t_cur, i) - 1]);
+        else r = __ldg(&c.fixed_group[i]);
+        break;
+      }
+      OM_DISPATCH_CASE(OM_DISP_RANDOM) {
+        // haul draws over len(load_sites), back over len(dump_sites)  (random_dispatcher.py:21-29)
+        r = draw_randint(U16A(t_epoch, i), (uint32_t)i, (kind == OM_ORDER_BACK) ? D : L);
+        break;
+      }
+      OM_DISPATCH_CASE(OM_DISP_SHORTESTTRIP) {
         // shortest_trip_dispatcher.py:12-84: earliest expected finish of (travel | queue + on-road trucks) + service.
         // Trucks already on the road: for haul orders those from the current load site, for init AND back orders those
         // on the charging-site roads (:71).
@@ -895,9 +914,7 @@ struct Sim {
         }
         break;
       }
-      default:
-        return -OM_IERR_BAD_ORDER;
-    }
+    OM_DISPATCH_END(-OM_IERR_BAD_ORDER)
     if (est) {
       r = argmin_lanes(val, n);
       __syncwarp();
@@ -1586,37 +1603,58 @@ struct Sim {
         goto L_GRANTED;
       }
       ph0 = U32A(t_phase, i);
-      switch (ph0) {
-        case PH_MOVE_ARRIVE: goto L_ARRIVE;
-        case PH_LOAD_DONE: case PH_DUMP_DONE: goto L_SVC_DONE;
-        case PH_MOVE_RET: goto L_MOVE_RET;
-        // CARRY kernels: `u` (the truck's unit), `rngw` and `distw` are in registers on every fused path into the labels
-        // below; only the entries through the event loop load them
-        case PH_LOAD_GRANTED: case PH_DUMP_GRANTED: if (CARRY) u = U16A(t_unit, i); goto L_GRANTED;
-        case PH_LOAD_BEGIN: case PH_DUMP_BEGIN: if (CARRY) u = U16A(t_unit, i); goto L_BEGIN;
-        case PH_LOAD_RET: case PH_DUMP_RET:
-          if (CARRY) { u = U16A(t_unit, i); if (RNG == OM_RNG_PHILOX) rngw = U32A(t_rng, i); }
-          goto L_SVC_RET;
-        case PH_MOVE_BEGIN: if (CARRY) load_move_carry(i); goto L_MOVE_BEGIN;
-        case PH_RUN_INIT:                                              // truck.py:296-302
-          U8A(t_cur, i) = 0;
-          U8A(t_status, i) = ST_WAIT_INIT;
-          kind = OM_ORDER_INIT;
-          goto L_ORDER;
-        case PH_MOVE_REPAIRED:
+      // The continuation is picked by a chain of compares, most frequent first (live RNG: four pops per truck cycle, two
+      // arrivals and two service ends): as a `switch` this was two indirect branches (BRX) per pop.
+      // OM_X_SWITCH_PHASE restores the switch for measurements.
+#ifdef OM_X_SWITCH_PHASE
+#define OM_PH_BEGIN switch (ph0) {
+#define OM_PH1(a) case a:
+#define OM_PH2(a, b) case a: case b:
+#define OM_PH_DEFAULT default:
+#define OM_PH_END }
+#else
+#define OM_PH_BEGIN {
+#define OM_PH1(a) if (om_opaque(ph0) == (uint32_t)(a))
+#define OM_PH2(a, b) if (om_opaque(ph0) == (uint32_t)(a) || om_opaque(ph0) == (uint32_t)(b))
+#define OM_PH_DEFAULT
+#define OM_PH_END }
+#endif
+      OM_PH_BEGIN
+        OM_PH1(PH_MOVE_ARRIVE) goto L_ARRIVE;
+        OM_PH2(PH_LOAD_DONE, PH_DUMP_DONE) goto L_SVC_DONE;
+        OM_PH1(PH_MOVE_REPAIRED) {
           if (CARRY) load_move_carry(i);
           repair_clear(i);
           U8A(t_status, i) = ST_MOVING;
           goto L_DEPART;
-        case PH_MAINT_DONE:                                            // truck.py:372-379
+        }
+        OM_PH1(PH_MOVE_RET) goto L_MOVE_RET;
+        // CARRY kernels: `u` (the truck's unit), `rngw` and `distw` are in registers on every fused path into the labels
+        // below; only the entries through the event loop load them
+        OM_PH2(PH_LOAD_GRANTED, PH_DUMP_GRANTED) { if (CARRY) u = U16A(t_unit, i); goto L_GRANTED; }
+        OM_PH2(PH_LOAD_BEGIN, PH_DUMP_BEGIN) { if (CARRY) u = U16A(t_unit, i); goto L_BEGIN; }
+        OM_PH2(PH_LOAD_RET, PH_DUMP_RET) {
+          if (CARRY) { u = U16A(t_unit, i); if (RNG == OM_RNG_PHILOX) rngw = U32A(t_rng, i); }
+          goto L_SVC_RET;
+        }
+        OM_PH1(PH_MOVE_BEGIN) { if (CARRY) load_move_carry(i); goto L_MOVE_BEGIN; }
+        OM_PH1(PH_RUN_INIT) {                                          // truck.py:296-302
+          U8A(t_cur, i) = 0;
+          U8A(t_status, i) = ST_WAIT_INIT;
+          kind = OM_ORDER_INIT;
+          goto L_ORDER;
+        }
+        OM_PH1(PH_MAINT_DONE) {                                        // truck.py:372-379
           u = U16A(t_unit, i);
           emit(K_SHOVEL_MAINT_DONE, (uint32_t)i, (uint32_t)u, 0, 0.0, 0.0);
           F64(u_lastbrk, u) = now;
           goto L_RELEASE;
-        default:
+        }
+        OM_PH_DEFAULT {
           if (ph0 >= PH_CRASH_BASE) fail(ph0 - PH_CRASH_BASE);           // the failed Process event pops: env.step() raises
           continue;
-      }
+        }
+      OM_PH_END
 
       // ================= chain 1: ARRIVE -> RET -> (grant) -> GRANTED -> BEGIN =================
     L_ARRIVE:                                                          // truck.py:211-218

@@ -264,6 +264,17 @@ struct Sim {
 
   int ns_stride, u_stride_out;
   static constexpr bool LY_DYNAMIC = false;   // see OM_SPLIT_HOT
+  // Which helpers a kernel family inlines and which it calls is a measured choice (same-call A/B on the C3 / C5 shards and
+  // the C4 rollout): a call costs a CALL and an indirect RET on the critical path, an inlined copy
+  // costs code in a fetch-bound kernel.  fp64 division: inlined in the unsplit episode kernels (-2.0 % on C3), called
+  // elsewhere (+1 % when inlined in the step kernel); Box-Muller: inlined in the split episode kernels (-2.3 % on C5),
+  // called elsewhere (both inlined in the unsplit episode kernel: +4.4 %).  Philox stays out of line everywhere (+2 %).
+  static constexpr bool DDIV_INLINE = !RL && !SPLIT, NORMAL_INLINE = !RL && SPLIT;
+  __device__ __forceinline__ double ddiv(double a, double b) const { return DDIV_INLINE ? (a / b) : om_ddiv(a, b); }
+  __device__ __forceinline__ double ddiv0(double a, double b) const { return (a == 0.0) ? 0.0 : ddiv(a, b); }
+  __device__ __forceinline__ float normal_fast(uint32_t a, uint32_t b) const {
+    return NORMAL_INLINE ? om_normal_fast_inl(a, b) : om_normal_fast(a, b);
+  }
   __device__ __forceinline__ Sim(unsigned char* sm_, unsigned char* blob, const RunParams& p, const DevCfg& cfg, int lane_, long long inst_)
       : sm(sm_), cold(SPLIT ? blob : sm_), c(cfg), ly(p.ly), out(p.out), lane(lane_), inst(inst_), rngw(0u), distw(0.0), ordw_ready(false),
         ns_stride(p.ns_stride), u_stride_out(p.u_stride_out) {}
@@ -509,7 +520,7 @@ struct Sim {
   __device__ __forceinline__ double draw_normal(int site, uint32_t epoch, uint32_t entity, double mu, double sigma) {
     if (RNG == OM_RNG_TAPE) return tape_next(site);
     Philox4 r = px(epoch, entity, site);
-    double v = mu + sigma * (double)om_normal_fast(r.x, r.y);
+    double v = mu + sigma * (double)normal_fast(r.x, r.y);
     tape_put(site, v);
     return v;
   }
@@ -897,16 +908,16 @@ struct Sim {
         if (lane < n) {
           int site = sbase_site + lane, tgt = 1 + site;
           int ub = __ldg(&c.ubeg[site]), ue = __ldg(&c.ubeg[site + 1]);
-          double reach = now + om_ddiv(60.0 * __ldg(&c.rdist[road_id(cur, tgt)]), v);
+          double reach = now + ddiv(60.0 * __ldg(&c.rdist[road_id(cur, tgt)]), v);
           double busy, service_time;
           if (haul) {
             double dt0 = __ldg(&c.dcycle[ub - c.S]);
-            busy = om_ddiv0((double)cnt, (double)(ue - ub)) * dt0;
+            busy = ddiv0((double)cnt, (double)(ue - ub)) * dt0;
             service_time = dt0;
           } else {
             double prod = __ldg(&c.site_prod[lane]);
-            busy = om_ddiv0(capsum, prod);
-            service_time = om_ddiv(__ldg(&c.cap[i]), om_ddiv(prod, (double)(ue - ub)));
+            busy = ddiv0(capsum, prod);
+            service_time = ddiv(__ldg(&c.cap[i]), ddiv(prod, (double)(ue - ub)));
           }
           double avail = (now + wait) + busy;
           double service = (avail > reach) ? avail : reach;        // np.maximum
@@ -1004,7 +1015,7 @@ struct Sim {
     const int rid = road_id(cur, tgt);
     // (distance / speed) * 60: tabulated per (speed class, road) for the road's own length; only a detour divides
     double duration = __ldg(&c.trip60[__ldg(&c.sclass[i]) * c.R + rid]);
-    if (__builtin_expect(dist != __ldg(&c.rdist[rid]), 0)) duration = om_ddiv(dist, __ldg(&c.speed[i])) * 60.0;
+    if (__builtin_expect(dist != __ldg(&c.rdist[rid]), 0)) duration = ddiv(dist, __ldg(&c.speed[i])) * 60.0;
     double pre = 0.0;
     if (RNG != OM_RNG_DET && jam_count > 0) {
       const bool maybe = !SPLIT || ((const uint16_t*)(sm + ly.r_jamcnt))[rid] != 0;
@@ -1275,7 +1286,7 @@ struct Sim {
                   na = r2.x; nb2 = r2.y;
                 }
                 used = true;
-                double d = c.repair_mu + c.repair_sigma * (double)om_normal_fast(na, nb2);
+                double d = c.repair_mu + c.repair_sigma * (double)normal_fast(na, nb2);
                 if (TAPE_OUT && tp) tape_put_at(tbase + 2ull * (unsigned long long)i + 1ull, OM_S_BREAK_DUR, d);
                 repair_set(i, (0.0 > d) ? 0.0 : d);
                 lastbrk_set_now(i);
@@ -1415,7 +1426,7 @@ struct Sim {
       }
       if (found < 0) break;                                 // cannot happen: n_on trucks are on the road
       float cv = coverage(found, rid);
-      float xx = cv + sd * om_normal_fast(r.y, r.z);
+      float xx = cv + sd * normal_fast(r.y, r.z);
       if (xx >= -0.5f * h && xx <= 1.0f + 0.5f * h) { x = xx; break; }
       if (DBG && it == 63 && fallbacks != nullptr) (*fallbacks)++;      // 64 rejections in a row (p <= 2^-64): x stays 0.5
     }
@@ -1443,7 +1454,7 @@ struct Sim {
   // Truck.get_route_coverage (truck.py:496-520)
   __device__ __forceinline__ float coverage(int i, int rid) {
     double total = __ldg(&c.trip60[__ldg(&c.sclass[i]) * c.R + rid]) + F64(t_prejam, i) + repair_get(i);
-    double cov = om_ddiv0(now - F64(t_jstart, i), total);
+    double cov = ddiv0(now - F64(t_jstart, i), total);
     if (cov > 1.0) cov = 1.0;
     return (float)cov;
   }
@@ -1747,7 +1758,7 @@ struct Sim {
         F64(t_total, i) = F64(t_total, i) + load;
         uint32_t sc = (uint32_t)U16A(t_svc, i) + 1;
         U16A(t_svc, i) = (uint16_t)sc;
-        F64(t_cycle, i) = om_ddiv(now - 0.0, (double)sc);              // first_order_time is always 0 (truck.py:304)
+        F64(t_cycle, i) = ddiv(now - 0.0, (double)sc);              // first_order_time is always 0 (truck.py:304)
         F64(t_load, i) = 0.0;
       }
       F64(u_tons, u) = F64(u_tons, u) + load;
@@ -1887,7 +1898,7 @@ struct Sim {
     rl_last_prod = reported_tons;
     double reward = -pen + 5.0 * om_dlog(delta + 1.0) + final_reward;
     double dt = now - rl_last;
-    if (dt > 0.0) reward += 0.1 * om_ddiv0(delta, dt + 1e-6);
+    if (dt > 0.0) reward += 0.1 * ddiv0(delta, dt + 1e-6);
     acc_wait = acc_shovel = acc_dumper = acc_move = acc_jam = 0.0;
     return reward;
   }

@@ -51,11 +51,13 @@ __device__ __forceinline__ float om_exp1(uint32_t x) { return -__logf(om_u01(x))
 
 // standard normal from two 32-bit words (Box-Muller on the MUFU log2 / rsqrt / cos units; live-mode draws are
 // distribution-level only): ~12 instructions inline
-__device__ __noinline__ float om_normal_fast(uint32_t a, uint32_t b) {
+__device__ __forceinline__ float om_normal_fast_inl(uint32_t a, uint32_t b) {
   float x = -2.0f * __logf(om_u01(a));
   float r = x * rsqrtf(fmaxf(x, 1e-30f));
   return r * __cosf(6.283185307179586f * om_u01(b) - 3.14159265358979f);   // cos(2 pi u - pi) = -cos(2 pi u): same law
 }
+// one out-of-line copy (the kernels choose per family which of the two they use, see Sim::normal_fast)
+__device__ __noinline__ float om_normal_fast(uint32_t a, uint32_t b) { return om_normal_fast_inl(a, b); }
 
 // bounded integer in [0, n): Lemire multiply-shift (no rejection); mirrored by oracle/philox.py
 __device__ __forceinline__ uint32_t om_randint(uint32_t x, uint32_t n) { return __umulhi(x, n); }

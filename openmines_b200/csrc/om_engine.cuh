@@ -199,8 +199,9 @@ __device__ __forceinline__ void om_publish_violation(uint32_t latch) {
 
 // Out-of-line helpers: the hot loop must stay small enough for the instruction caches (profiles/r1_a),
 // so the 10-round Philox and the fp64 division (a ~35-instruction Newton sequence) exist once.
+template <int UNROLL>
 __device__ __noinline__ Philox4 om_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-  return philox4x32_10(c0, c1, c2, c3, k0, k1);
+  return philox4x32_10<UNROLL>(c0, c1, c2, c3, k0, k1);
 }
 __device__ __noinline__ double om_ddiv(double a, double b) { return a / b; }
 // 0 / b without the division: a zero (or denormal) numerator sends div.rn.f64 down its ~110-instruction slow path, and the
@@ -507,7 +508,7 @@ struct Sim {
     }
   }
   __device__ __forceinline__ Philox4 px(uint32_t epoch, uint32_t entity, uint32_t site, uint32_t stream = 0) const {
-    return om_philox(epoch, entity, site, stream, k0, k1);
+    return om_philox<(SPLIT && !RL) ? 10 : 2>(epoch, entity, site, stream, k0, k1);
   }
   // exponential with mean `mean` (np.random.exponential(scale) / random.expovariate(1/mean))
   __device__ __forceinline__ double draw_exp(int site, uint32_t epoch, uint32_t entity, double mean) {

@@ -25,12 +25,15 @@ struct Philox4 {
   uint32_t x, y, z, w;
 };
 
+// UNROLL: trips of the 10-round loop per loop iteration.  The engine is bound by instruction fetch and dependent-issue
+// latency, so this is a measured choice per kernel family (same-call A/B): the fully unrolled body
+// (~110 instructions, 14 cache lines) costs the north_pit episode kernel 4 %, two rounds per trip gain it 0.5 %; the
+// split kernels of the big mines (7 warps per SM, little fetch pressure) gain 2.7 % from the full unroll.
+template <int UNROLL = 2>
 __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                  uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-  // rolled on purpose: the engine is instruction-fetch bound (profiles/r1_d), a 10-trip loop of ~12 instructions
-  // stays in the L0 instruction cache while the unrolled body (~110 instructions, 14 cache lines) does not
-#pragma unroll 1
+#pragma unroll UNROLL
   for (int r = 0; r < 10; ++r) {
     uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
     uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;

@@ -1,2 +1,3 @@
-timeout -k 10 600 python -m pytest tests -m gpu -x -q -k "draw_tape or marginals or rl_step or det_all" 2>&1 | tail -2
-for l in openmines_b200/libopenmines_b200.so variants/lib_prev.so; do tools/variant_bench.sh $l c3; tools/variant_bench.sh $l c5; tools/variant_bench.sh $l c4 --steps 1; tools/variant_bench.sh $l c2; done
+for l in openmines_b200/libopenmines_b200.so variants/lib_r_n_all.so variants/lib_r_both_all.so; do tools/variant_bench.sh $l c3; done
+for l in openmines_b200/libopenmines_b200.so variants/lib_r_d_all.so variants/lib_r_both_all.so; do tools/variant_bench.sh $l c5; done
+tools/variant_bench.sh openmines_b200/libopenmines_b200.so c4 --steps 1

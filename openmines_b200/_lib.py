@@ -45,12 +45,18 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     cus = [s for s in sources() if s.endswith(".cu")]
+    # nvcc writes a private file that then replaces the library in one step: a process that loads the library while
+    # another one rebuilds it (eight ranks starting together) sees the old file or the new one, never a partial one
+    tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
     cmd = [nvcc] + NVCC_FLAGS + (["-DOM_BOUNDS_CHECK=" + (os.environ.get("OM_DEBUG_LIB") or "1")] if DEBUG and os.environ.get("OM_DEBUG_LIB") != "probes" else []) + \
         (os.environ.get("OM_EXTRA_NVCC_FLAGS", "").split()) + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-I", INCLUDE, "-o", LIB_PATH] + cus
+        ["-I", INCLUDE, "-o", tmp] + cus
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(r.stderr)
     return LIB_PATH
@@ -93,7 +99,15 @@ def load():
         if shutil.which(os.environ.get("NVCC", "nvcc")) is None:
             raise RuntimeError("openmines_b200: %s is older than its sources and nvcc is not available to rebuild it"
                                % LIB_PATH)
-        build(force=True)
+        # one process rebuilds, the others of the node (ranks of one launch) wait for it and find the library current
+        import fcntl
+        with open(LIB_PATH + ".lock", "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if needs_build():
+                    build(force=True)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     lib = ctypes.CDLL(LIB_PATH)
     vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
     lib.om_last_error.restype = ctypes.c_char_p

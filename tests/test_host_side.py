@@ -200,3 +200,36 @@ def test_om_create_rejects_mines_beyond_the_engine_limits():
     assert rc == -1 and b"empty mine" in msg
     rc, msg = create(mutate=lambda s: setattr(s, "jam_capacity", 0))
     assert rc == -4
+
+
+def test_stale_library_is_rebuilt_once_and_never_loaded_half_written():
+    """Ranks of one launch that start together on a library older than its sources (it happened: eight ranks, eight nvcc
+    runs into the same file, `file too short`): one of them rebuilds under a lock into a private file that replaces the
+    library in one step, the others wait and load the finished one."""
+    import shutil
+    import subprocess
+    import sys
+    import time
+    if shutil.which(os.environ.get("NVCC", "nvcc")) is None:
+        pytest.skip("no nvcc")
+    src = os.path.join(_lib.CSRC, "om_engine.cu")
+    st = os.stat(src)
+    code = ("import time; from openmines_b200 import _lib; lib = _lib.load(); "
+            "assert not _lib.needs_build(); print('abi', _lib.abi_info()['abi_version'])")
+    env = dict(os.environ)
+    env.pop("OM_LIB_PATH", None)
+    env.pop("OM_DEBUG_LIB", None)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(_lib.__file__)))
+    try:
+        os.utime(src, (time.time(), time.time()))            # the sources are now newer than the library
+        assert _lib.needs_build()
+        procs = [subprocess.Popen([sys.executable, "-c", code], cwd=root, env=env, stdout=subprocess.PIPE,
+                                  stderr=subprocess.PIPE, text=True) for _ in range(3)]
+        outs = [p.communicate(timeout=600) for p in procs]
+        for p, (out, err) in zip(procs, outs):
+            assert p.returncode == 0, err[-2000:]
+            assert "abi %d" % cfgmod.OM_ABI_VERSION in out
+        assert not _lib.needs_build()
+        assert not [f for f in os.listdir(os.path.dirname(_lib.LIB_PATH)) if ".so.tmp." in f]     # no private file left behind
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))

@@ -284,7 +284,9 @@ int om_reset(OmHandle h, const uint64_t* seeds, const int32_t* dispatcher, int r
 
 /* Replaces env.run(until) (mine.py:391): advances every instance until no pending entry has
  * time < until (the reference's stop event is URGENT at `until`).  May be called repeatedly
- * with increasing `until`. */
+ * with increasing `until`.  Handles whose layout is split (big mines: om_state_layout().t_aux != 0) hold breakdown
+ * minutes as uint16 and return OM_E_UNSUPPORTED for until > 65535 (45 simulated days); om_step has the same limit on
+ * every handle (jam start minutes of the RL surface). */
 int om_run(OmHandle h, double until, void* state, const OmOutputs* outs, void* stream);
 
 /* Local partial statistics for the cross-GPU all-reduce (issued by the caller with NCCL):

@@ -334,6 +334,11 @@ def run_c4(a, emit=True):
         sm = tot[1:].clone(); dist.all_reduce(sm)
         ms, delta = float(mx[0]), sm.cpu().numpy()
     n_episodes, n_events, n_dec = float(delta[0]), float(delta[1]), float(delta[2])
+    herr = env.mine.headers()["err"]
+    failed_t = torch.tensor([float(((herr != 0) & (herr != 5)).sum())], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(failed_t)
+    n_failed = float(failed_t.item())
     ms_per_step = ms / a.steps
     sec = ms / 1000.0
     # ---- end to end with the policy on the HOST (the reference's trainers: actions arrive from host memory, observations,
@@ -428,6 +433,7 @@ def run_c4(a, emit=True):
                        "l2_policy": "inputs larger than L2 (state %.0f MB/GPU round-trips HBM every env step)" % (n * env.mine.state_bytes / 1e6),
                        "launch": env.mine.launch_info()},
             "episodes_per_s": n_episodes / sec,
+            "instance_errors": n_failed,          # envs stopped by an engine error (e.g. a jam pool that overflowed): they never restart
             "decisions_per_s": n_dec / sec,
             "env_steps_per_s": n * world * a.steps * steps_per / sec,
             "clocks": clocks,
@@ -786,7 +792,7 @@ def main():
             line["extras"]["c4"] = {"workload": c4["config"]["workload"], "value": c4["value"], "unit": UNIT,
                                     "decisions_per_s": c4["decisions_per_s"], "env_steps_per_s": c4["env_steps_per_s"],
                                     "ms_per_step": c4["ms_per_step"], "om_step_kernel_ms": c4["roofline"]["kernel_ms"],
-                                    "hbm_frac": c4["roofline"]["frac"], "e2e_host_policy": c4["e2e"]}
+                                    "hbm_frac": c4["roofline"]["frac"], "instance_errors": c4.get("instance_errors"), "e2e_host_policy": c4["e2e"]}
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
             s = cpu_sample(a.workload, 32)
